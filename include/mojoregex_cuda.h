@@ -1,0 +1,187 @@
+/* libmojoregex_cuda.so -- C ABI of the B200-native matching hot path of mojo-regex.
+ *
+ * The reference (msaelices/mojo-regex v0.21.0, pure Mojo) has no FFI seam; this ABI is
+ * the seam a maintainer adds at the places where HybridMatcher calls its DFAMatcher
+ * (src/regex/matcher.mojo:748-750, 793-802, 859-860, 889) and in _sub_impl_with_repl /
+ * split (matcher.mojo:1679-1854, 1357-1393).  Each entry point names the reference
+ * interface it replaces.  Plain pointers and sizes only; no torch / C++ types.
+ *
+ * Conventions inherited from the reference:
+ *  - compiling may fail (Mojo `raises`): MRX_E_PARSE / MRX_E_UNSUPPORTED;
+ *  - matching never fails: "no match" is a normal result, not an error;
+ *  - spans are byte offsets into the text, end-exclusive (matching.mojo:5-46);
+ *  - results borrow nothing: span arrays / output bytes are owned by the library until
+ *    the matching *_free call; the text must stay alive only for the duration of a call;
+ *  - one calling thread per library instance (matcher.mojo:1206-1210).
+ *
+ * There is no CPU fallback: every matching entry point runs CUDA kernels (sm_100a) and
+ * returns MRX_E_CUDA / MRX_E_NO_DEVICE when it cannot.
+ */
+#ifndef MOJOREGEX_CUDA_H
+#define MOJOREGEX_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRX_ABI_VERSION 1
+
+/* return codes */
+#define MRX_OK 0
+#define MRX_E_INVALID (-1)     /* bad argument / corrupt blob                                   */
+#define MRX_E_PARSE (-2)       /* pattern rejected by the parser (parser.mojo:225-237,340,399)   */
+#define MRX_E_UNSUPPORTED (-3) /* pattern the reference routes to its NFA engines (or a path whose
+                                  reference behaviour is host-SIMD-width dependent); the Mojo
+                                  caller keeps its CPU engine for these, as it does today when
+                                  DFA compilation raises (matcher.mojo:665-675)                  */
+#define MRX_E_CUDA (-4)        /* CUDA runtime error; see mrx_last_error()                       */
+#define MRX_E_NO_DEVICE (-5)   /* no CUDA device / mrx_init not called                           */
+#define MRX_E_UNDEFINED (-6)   /* input on which the reference's own behaviour is undefined
+                                  (split with overlapping separator spans)  */
+
+/* where result arrays live */
+#define MRX_OUT_HOST 0   /* pinned host memory, valid on return                                  */
+#define MRX_OUT_DEVICE 1 /* device memory on the library stream (for callers that keep data in HBM) */
+
+typedef struct mrx_regex mrx_regex; /* CompiledRegex: tables + dispatch plan (matcher.mojo:929-1035) */
+typedef struct mrx_text mrx_text;   /* a text resident in HBM                                     */
+
+/* MatchList replacement (matching.mojo:49-157): n spans, start_end[2*i], start_end[2*i+1]. */
+typedef struct {
+  int64_t *start_end;
+  size_t n;
+  int location; /* MRX_OUT_HOST or MRX_OUT_DEVICE */
+  void *_owner;
+} mrx_spans;
+
+/* String result of sub() (matcher.mojo:1857-1917). */
+typedef struct {
+  uint8_t *bytes;
+  size_t n;
+  int location;
+  void *_owner;
+} mrx_bytes;
+
+/* List[String] result of split() (matcher.mojo:1357-1393): piece i is
+ * bytes[offsets[i] .. offsets[i+1]); n pieces, n+1 offsets. */
+typedef struct {
+  uint8_t *bytes;
+  int64_t *offsets;
+  size_t n;
+  int location;
+  void *_owner;
+} mrx_pieces;
+
+/* Introspection for tests / the Mojo side's get_stats() (matcher.mojo:1139-1163). */
+typedef struct {
+  int32_t n_states, n_classes, start_state;
+  int32_t has_start_anchor, has_end_anchor, is_pure_literal, has_matcher, scan_eligible;
+  int32_t required_byte;     /* -1 = none (matcher.mojo:558-564)                                  */
+  int32_t is_wildcard_any, is_exact_literal, has_prefilter;
+  int32_t findall_mode;      /* MRX_MODE_* chosen for match_all                                   */
+  int32_t search_mode;       /* MRX_MODE_* chosen for match_next / sub                            */
+  int32_t findall_direct;    /* 1 = potential matches are provably non-overlapping (no selection) */
+  int32_t search_direct;
+  int32_t fixed_sub_total_width, fixed_sub_num_groups, fixed_sub_concat;
+} mrx_info;
+
+#define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */
+#define MRX_MODE_ANCHORED 1      /* ^ or $: one attempt chain    dfa.mojo:2046-2050, 1888-1892    */
+#define MRX_MODE_EXACT_LITERAL 2 /* overlapping literal hits     matcher.mojo:815-847            */
+#define MRX_MODE_LITERAL 3       /* pure literal, non-overlapping dfa.mojo:2062-2071             */
+#define MRX_MODE_CLASS_RUNS 4    /* maximal class runs           dfa.mojo:2075-2094              */
+#define MRX_MODE_FIRST_CLASS 5   /* first-class skip + DFA       dfa.mojo:2097-2115, 2241-2253    */
+#define MRX_MODE_EVERY_POS 6     /* DFA at every position        dfa.mojo:2117-2128, 1898-1903    */
+#define MRX_MODE_REQUIRED_BYTE 7 /* memchr + back-scan + DFA     matcher.mojo:864-898            */
+#define MRX_MODE_UNIFORM_RUN 8   /* FIRST_CLASS/EVERY_POS specialised: chain DFA over one class    */
+
+/* ---- library ------------------------------------------------------------------------- */
+int mrx_abi_version(void);
+/* Select CUDA device `device` for this process and create the library stream. */
+int mrx_init(int device);
+int mrx_shutdown(void);
+const char *mrx_last_error(void);
+/* cudaStream_t the kernels are launched on (so callers can bracket them with events). */
+void *mrx_stream(void);
+/* Number of kernels this library has launched since mrx_init (bench.py's gpu_launches). */
+uint64_t mrx_launch_count(void);
+int mrx_synchronize(void);
+
+/* ---- front end ------------------------------------------------------------------------ */
+/* Replaces compile_regex()/CompiledRegex(pattern) (matcher.mojo:964-978, 1292-1315) for
+ * callers without the Mojo front end: parse, classify, build the reference's automaton,
+ * pack it.  Pure host code; needs no GPU. */
+int mrx_compile(const uint8_t *pattern, size_t n, mrx_regex **out);
+/* Serializer entry for the Mojo front end: pack a DFAEngine as it sits in memory
+ * (dfa.mojo:257-294: `states[i].transitions` = 256 x int32 with -1 = none,
+ * `states[i].is_accepting`) plus the HybridMatcher/CompiledRegex flags into a blob.
+ * `matcher_lookup` = _simd_char_matcher.lookup_table (256 bytes) or NULL when
+ * !_has_simd_matcher; `literal` = literal_pattern.  Call with blob == NULL to get the size. */
+typedef struct {
+  int32_t n_states, start_state;
+  int32_t has_start_anchor, has_end_anchor, is_pure_literal, scan_eligible;
+  int32_t required_byte;       /* HybridMatcher._required_byte                                  */
+  int32_t is_wildcard_any, is_exact_literal, has_anchors_info;
+  int32_t fixed_sub_total_width, fixed_sub_num_groups, fixed_sub_concat;
+  int32_t fixed_sub_offsets[10], fixed_sub_widths[10];
+} mrx_dfa_desc;
+int mrx_dfa_pack(const mrx_dfa_desc *desc, const int32_t *transitions /* n_states*256 */,
+                 const uint8_t *accepting /* n_states */, const uint8_t *matcher_lookup /* 256|NULL */,
+                 const uint8_t *literal, size_t literal_len, const uint8_t *exact_literal,
+                 size_t exact_len, const uint8_t *prefilter, size_t prefilter_len, uint8_t *blob,
+                 size_t *blob_len);
+/* Load a blob produced by mrx_dfa_pack / mrx_regex_blob. */
+int mrx_regex_load(const uint8_t *blob, size_t n, mrx_regex **out);
+int mrx_regex_blob(const mrx_regex *re, uint8_t *buf, size_t *len);
+int mrx_regex_info(const mrx_regex *re, mrx_info *out);
+void mrx_regex_free(mrx_regex *re);
+
+/* ---- texts ---------------------------------------------------------------------------- */
+/* Copy `n` host bytes into HBM (staged through pinned memory, async on the library stream). */
+int mrx_text_upload(const uint8_t *host, size_t n, mrx_text **out);
+/* Wrap `n` bytes already in device memory (not copied, not freed). */
+int mrx_text_wrap_device(const void *dptr, size_t n, mrx_text **out);
+/* Multi-GPU shards: the buffer is [left halo | core | right halo].  Matching behaves as if
+ * the text were exactly the buffer, but only matches whose key (start; the needle hit for
+ * required-byte patterns) lies in [core_begin, core_end) are reported, and spans are
+ * rebased by `global_offset` (the buffer's position in the whole corpus). */
+int mrx_text_set_window(mrx_text *t, size_t core_begin, size_t core_end, int64_t global_offset);
+size_t mrx_text_len(const mrx_text *t);
+void mrx_text_free(mrx_text *t);
+
+/* ---- matching (all of these launch CUDA kernels) ----------------------------------------- */
+/* CompiledRegex.match_all / findall (matcher.mojo:1078-1089, 1341-1354). */
+int mrx_findall(const mrx_regex *re, const mrx_text *t, int location, mrx_spans *out);
+/* CompiledRegex.match_next(text, start) / search (matcher.mojo:1064-1076, 1325-1338).
+ * Returns 1 and fills out[0..1] on a match, 0 on no match, <0 on error. */
+int mrx_search(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]);
+/* CompiledRegex.match_first(text, start) (matcher.mojo:1048-1061); same return convention.
+ * The module-level match_first additionally requires start_idx == 0 (matcher.mojo:1411-1415);
+ * that filter is the caller's. */
+int mrx_match_first(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]);
+/* Batch search: one match_next(doc, 0) per document (the reference has no batch API; its
+ * callers loop).  Document i is t[doc_offsets[i] .. doc_offsets[i+1]);
+ * out_start_end[2i..2i+1] are relative to the document, (-1,-1) = None.  `doc_offsets`
+ * (n_docs+1 entries) and `out_start_end` are host pointers when location == MRX_OUT_HOST,
+ * device pointers when MRX_OUT_DEVICE.  doc_offsets == NULL means fixed-size documents of
+ * `doc_stride` bytes. */
+int mrx_search_batch(const mrx_regex *re, const mrx_text *t, const int64_t *doc_offsets,
+                     size_t n_docs, int64_t doc_stride, int location, int64_t *out_start_end);
+/* sub(pattern, repl, text, count) (matcher.mojo:1857-1917, 1679-1854). count == 0: all. */
+int mrx_sub(const mrx_regex *re, const uint8_t *repl, size_t repl_n, int64_t count,
+            const mrx_text *t, int location, mrx_bytes *out);
+/* split(pattern, text, maxsplit) (matcher.mojo:1357-1393). */
+int mrx_split(const mrx_regex *re, const mrx_text *t, int64_t maxsplit, int location,
+              mrx_pieces *out);
+
+void mrx_spans_free(mrx_spans *s);
+void mrx_bytes_free(mrx_bytes *b);
+void mrx_pieces_free(mrx_pieces *p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOJOREGEX_CUDA_H */

@@ -1,0 +1,481 @@
+"""mojo_regex_b200 -- B200-native matching hot path behind mojo-regex's `re`-style API.
+
+Host-side mirror (Python over ctypes) of the reference's public interface for the
+matching path -- same names, argument meaning and error behaviour as
+/root/reference/src/regex/matcher.mojo:1325-1415, 1857-1917:
+
+    compile_regex(pattern) -> CompiledRegex
+    search(pattern, text) / match_first(pattern, text) / findall(pattern, text)
+    sub(pattern, repl, text, count=0) / split(pattern, text, maxsplit=0)
+
+All matching runs in libmojoregex_cuda.so (hand-written sm_100a kernels); there is no
+CPU fallback.  Importing the package without the built library raises ImportError;
+matching without a CUDA device raises RegexCudaError.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libmojoregex_cuda.so")
+
+MRX_OK, MRX_E_INVALID, MRX_E_PARSE, MRX_E_UNSUPPORTED, MRX_E_CUDA, MRX_E_NO_DEVICE, MRX_E_UNDEFINED = 0, -1, -2, -3, -4, -5, -6
+OUT_HOST, OUT_DEVICE = 0, 1
+
+MODE_NAMES = {0: "WILDCARD_ANY", 1: "ANCHORED", 2: "EXACT_LITERAL", 3: "LITERAL", 4: "CLASS_RUNS",
+              5: "FIRST_CLASS", 6: "EVERY_POS", 7: "REQUIRED_BYTE", 8: "UNIFORM_RUN", -1: "UNSUPPORTED"}
+
+
+class RegexError(Exception):
+    """Pattern rejected by the parser (the reference `raises`, parser.mojo:225-237,340,399)."""
+
+
+class UnsupportedPattern(Exception):
+    """Pattern the reference serves from its NFA engines; the GPU path refuses it loudly."""
+
+
+class UndefinedBehaviour(Exception):
+    """Input on which the reference's own behaviour is undefined."""
+
+
+class RegexCudaError(RuntimeError):
+    """CUDA failure or missing device.  There is no CPU fallback."""
+
+
+class _Spans(ctypes.Structure):
+    _fields_ = [("start_end", ctypes.POINTER(ctypes.c_int64)), ("n", ctypes.c_size_t),
+                ("location", ctypes.c_int), ("_owner", ctypes.c_void_p)]
+
+
+class _Bytes(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.POINTER(ctypes.c_uint8)), ("n", ctypes.c_size_t),
+                ("location", ctypes.c_int), ("_owner", ctypes.c_void_p)]
+
+
+class _Pieces(ctypes.Structure):
+    _fields_ = [("bytes", ctypes.POINTER(ctypes.c_uint8)), ("offsets", ctypes.POINTER(ctypes.c_int64)),
+                ("n", ctypes.c_size_t), ("location", ctypes.c_int), ("_owner", ctypes.c_void_p)]
+
+
+class Info(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "n_states", "n_classes", "start_state", "has_start_anchor", "has_end_anchor", "is_pure_literal",
+        "has_matcher", "scan_eligible", "required_byte", "is_wildcard_any", "is_exact_literal",
+        "has_prefilter", "findall_mode", "search_mode", "findall_direct", "search_direct",
+        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat")]
+
+
+class DfaDesc(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_int32) for k in (
+        "n_states", "start_state", "has_start_anchor", "has_end_anchor", "is_pure_literal", "scan_eligible",
+        "required_byte", "is_wildcard_any", "is_exact_literal", "has_anchors_info",
+        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat")] + [
+        ("fixed_sub_offsets", ctypes.c_int32 * 10), ("fixed_sub_widths", ctypes.c_int32 * 10)]
+
+
+EXPORTS = [
+    "mrx_abi_version", "mrx_init", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
+    "mrx_synchronize", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
+    "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
+    "mrx_text_free", "mrx_findall", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
+    "mrx_split", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
+]
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(_SO):
+        raise ImportError(
+            f"{_SO} is missing: build it with `python -m mojo_regex_b200.build` (nvcc, sm_100a). "
+            "mojo_regex_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(_SO)
+    P, c = ctypes.POINTER, ctypes
+    vp, i64, sz = c.c_void_p, c.c_int64, c.c_size_t
+    lib.mrx_abi_version.restype = c.c_int
+    lib.mrx_init.argtypes = [c.c_int]
+    lib.mrx_last_error.restype = c.c_char_p
+    lib.mrx_stream.restype = vp
+    lib.mrx_launch_count.restype = c.c_uint64
+    lib.mrx_compile.argtypes = [c.c_char_p, sz, P(vp)]
+    lib.mrx_dfa_pack.argtypes = [P(DfaDesc), vp, vp, vp, c.c_char_p, sz, c.c_char_p, sz, c.c_char_p, sz, vp, P(sz)]
+    lib.mrx_regex_load.argtypes = [c.c_char_p, sz, P(vp)]
+    lib.mrx_regex_blob.argtypes = [vp, vp, P(sz)]
+    lib.mrx_regex_info.argtypes = [vp, P(Info)]
+    lib.mrx_regex_free.argtypes = [vp]
+    lib.mrx_regex_free.restype = None
+    lib.mrx_text_upload.argtypes = [vp, sz, P(vp)]
+    lib.mrx_text_wrap_device.argtypes = [vp, sz, P(vp)]
+    lib.mrx_text_set_window.argtypes = [vp, sz, sz, i64]
+    lib.mrx_text_len.argtypes = [vp]
+    lib.mrx_text_len.restype = sz
+    lib.mrx_text_free.argtypes = [vp]
+    lib.mrx_text_free.restype = None
+    lib.mrx_findall.argtypes = [vp, vp, c.c_int, P(_Spans)]
+    lib.mrx_search.argtypes = [vp, vp, i64, P(i64)]
+    lib.mrx_match_first.argtypes = [vp, vp, i64, P(i64)]
+    lib.mrx_search_batch.argtypes = [vp, vp, vp, sz, i64, c.c_int, vp]
+    lib.mrx_sub.argtypes = [vp, c.c_char_p, sz, i64, vp, c.c_int, P(_Bytes)]
+    lib.mrx_split.argtypes = [vp, vp, i64, c.c_int, P(_Pieces)]
+    lib.mrx_spans_free.argtypes = [P(_Spans)]
+    lib.mrx_spans_free.restype = None
+    lib.mrx_bytes_free.argtypes = [P(_Bytes)]
+    lib.mrx_bytes_free.restype = None
+    lib.mrx_pieces_free.argtypes = [P(_Pieces)]
+    lib.mrx_pieces_free.restype = None
+    return lib
+
+
+lib = _load()
+_initialised_device: Optional[int] = None
+
+
+def _check(rc: int) -> int:
+    if rc >= 0:
+        return rc
+    msg = (lib.mrx_last_error() or b"").decode("utf-8", "replace")
+    if rc == MRX_E_PARSE:
+        raise RegexError(msg)
+    if rc == MRX_E_UNSUPPORTED:
+        raise UnsupportedPattern(msg)
+    if rc == MRX_E_UNDEFINED:
+        raise UndefinedBehaviour(msg)
+    if rc == MRX_E_INVALID:
+        raise ValueError(msg)
+    raise RegexCudaError(f"[{rc}] {msg}")
+
+
+def init(device: int = 0) -> None:
+    """Select the CUDA device for this process (one process per GPU)."""
+    global _initialised_device
+    _check(lib.mrx_init(device))
+    _initialised_device = device
+
+
+def _ensure_init() -> None:
+    if _initialised_device is None:
+        init(int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def stream_handle() -> int:
+    """cudaStream_t (as int) the library launches on."""
+    _ensure_init()
+    return int(lib.mrx_stream() or 0)
+
+
+def launch_count() -> int:
+    return int(lib.mrx_launch_count())
+
+
+def synchronize() -> None:
+    _check(lib.mrx_synchronize())
+
+
+def _as_bytes(x) -> bytes:
+    if isinstance(x, str):
+        return x.encode("utf-8")
+    return bytes(x)
+
+
+class Text:
+    """A text resident in HBM.  Build from host bytes / numpy uint8, or wrap a CUDA tensor."""
+
+    def __init__(self, data=None, *, device_ptr: int = 0, nbytes: int = 0, keepalive=None):
+        _ensure_init()
+        self._h = ctypes.c_void_p()
+        self._keep = keepalive
+        if data is not None:
+            if isinstance(data, np.ndarray):
+                assert data.dtype == np.uint8
+                arr = np.ascontiguousarray(data)
+                self._n = arr.size
+                _check(lib.mrx_text_upload(arr.ctypes.data, arr.size, ctypes.byref(self._h)))
+                synchronize()  # arr may be temporary
+            else:
+                b = _as_bytes(data)
+                self._n = len(b)
+                buf = ctypes.create_string_buffer(b, len(b)) if b else None
+                _check(lib.mrx_text_upload(ctypes.cast(buf, ctypes.c_void_p) if buf else None, len(b),
+                                           ctypes.byref(self._h)))
+                synchronize()
+        else:
+            self._n = nbytes
+            _check(lib.mrx_text_wrap_device(device_ptr, nbytes, ctypes.byref(self._h)))
+
+    @classmethod
+    def from_tensor(cls, t) -> "Text":
+        """Wrap a contiguous CUDA uint8 torch tensor without copying."""
+        assert t.is_cuda and t.is_contiguous() and t.element_size() == 1
+        return cls(device_ptr=t.data_ptr(), nbytes=t.numel(), keepalive=t)
+
+    @classmethod
+    def from_pinned(cls, ptr: int, nbytes: int) -> "Text":
+        """Upload `nbytes` from a (pinned) host pointer; asynchronous on the library stream."""
+        self = cls.__new__(cls)
+        _ensure_init()
+        self._h = ctypes.c_void_p()
+        self._keep = None
+        self._n = nbytes
+        _check(lib.mrx_text_upload(ptr, nbytes, ctypes.byref(self._h)))
+        return self
+
+    def set_window(self, core_begin: int, core_end: int, global_offset: int = 0) -> None:
+        _check(lib.mrx_text_set_window(self._h, core_begin, core_end, global_offset))
+
+    def __len__(self) -> int:
+        return self._n
+
+    def close(self) -> None:
+        if self._h:
+            lib.mrx_text_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Match:
+    """matching.mojo:5-46 -- group_id 0, byte offsets, end-exclusive."""
+    __slots__ = ("group_id", "start_idx", "end_idx", "_text")
+
+    def __init__(self, start: int, end: int, text: Optional[bytes] = None):
+        self.group_id = 0
+        self.start_idx = int(start)
+        self.end_idx = int(end)
+        self._text = text
+
+    def get_match_text(self) -> bytes:
+        return self._text[self.start_idx:self.end_idx]
+
+    def span(self):
+        return (self.start_idx, self.end_idx)
+
+    def __repr__(self):
+        return f"Match(start_idx={self.start_idx}, end_idx={self.end_idx})"
+
+    def __eq__(self, other):
+        return isinstance(other, Match) and self.span() == other.span()
+
+
+class MatchList:
+    """matching.mojo:49-157 -- spans held as one (n, 2) int64 array (host numpy or CUDA tensor)."""
+
+    def __init__(self, spans, text: Optional[bytes] = None, owner=None):
+        self.spans = spans
+        self._text = text
+        self._owner = owner
+
+    def __len__(self) -> int:
+        return int(self.spans.shape[0])
+
+    def __getitem__(self, i: int) -> Match:
+        s, e = self.spans[i]
+        return Match(int(s), int(e), self._text)
+
+    def __iter__(self):
+        for i in range(len(self)):
+            yield self[i]
+
+    def tolist(self):
+        return [[int(s), int(e)] for s, e in self.spans]
+
+
+def _text_of(text) -> "tuple[Text, Optional[bytes]]":
+    if isinstance(text, Text):
+        return text, None
+    if isinstance(text, np.ndarray):
+        return Text(text), None
+    b = _as_bytes(text)
+    return Text(b), b
+
+
+class CompiledRegex:
+    """matcher.mojo:929-1163."""
+
+    def __init__(self, pattern=None, *, blob: Optional[bytes] = None):
+        self._h = ctypes.c_void_p()
+        if blob is not None:
+            self.pattern = None
+            _check(lib.mrx_regex_load(blob, len(blob), ctypes.byref(self._h)))
+        else:
+            self.pattern = _as_bytes(pattern)
+            _check(lib.mrx_compile(self.pattern, len(self.pattern), ctypes.byref(self._h)))
+
+    # -- introspection
+    def info(self) -> Info:
+        o = Info()
+        _check(lib.mrx_regex_info(self._h, ctypes.byref(o)))
+        return o
+
+    def blob(self) -> bytes:
+        n = ctypes.c_size_t(0)
+        _check(lib.mrx_regex_blob(self._h, None, ctypes.byref(n)))
+        buf = ctypes.create_string_buffer(n.value)
+        _check(lib.mrx_regex_blob(self._h, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(n)))
+        return buf.raw[:n.value]
+
+    def get_stats(self) -> str:
+        i = self.info()
+        return (f"Pattern: {self.pattern!r}, Engine: DFA(cuda), Complexity: SIMPLE, "
+                f"findall={MODE_NAMES[i.findall_mode]}{'/direct' if i.findall_direct else ''}, "
+                f"search={MODE_NAMES[i.search_mode]}")
+
+    # -- CompiledRegex.match_first / match_next / match_all
+    def match_first(self, text, start: int = 0) -> Optional[Match]:
+        t, raw = _text_of(text)
+        out = (ctypes.c_int64 * 2)()
+        rc = _check(lib.mrx_match_first(self._h, t._h, start, out))
+        return Match(out[0], out[1], raw) if rc == 1 else None
+
+    def match_next(self, text, start: int = 0) -> Optional[Match]:
+        t, raw = _text_of(text)
+        out = (ctypes.c_int64 * 2)()
+        rc = _check(lib.mrx_search(self._h, t._h, start, out))
+        return Match(out[0], out[1], raw) if rc == 1 else None
+
+    def match_all(self, text) -> MatchList:
+        t, raw = _text_of(text)
+        sp = _Spans()
+        _check(lib.mrx_findall(self._h, t._h, OUT_HOST, ctypes.byref(sp)))
+        try:
+            if sp.n:
+                arr = np.ctypeslib.as_array(sp.start_end, shape=(sp.n * 2,)).copy().reshape(-1, 2)
+            else:
+                arr = np.zeros((0, 2), dtype=np.int64)
+        finally:
+            lib.mrx_spans_free(ctypes.byref(sp))
+        return MatchList(arr, raw)
+
+    def match_all_device(self, text: Text):
+        """findall with the span array left in HBM: returns (torch int64 tensor view (n,2), keepalive)."""
+        import torch
+
+        sp = _Spans()
+        _check(lib.mrx_findall(self._h, text._h, OUT_DEVICE, ctypes.byref(sp)))
+        return _DeviceSpans(sp)
+
+    def search_batch(self, text, doc_offsets=None, doc_stride: int = 0, n_docs: Optional[int] = None) -> np.ndarray:
+        """One match_next(doc, 0) per document -> (n_docs, 2) int64, (-1,-1) = no match."""
+        t, _ = _text_of(text)
+        if doc_offsets is not None:
+            offs = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+            n_docs = offs.size - 1
+            optr = offs.ctypes.data
+        else:
+            assert doc_stride > 0
+            if n_docs is None:
+                n_docs = (len(t) + doc_stride - 1) // doc_stride
+            optr = None
+        out = np.empty((n_docs, 2), dtype=np.int64)
+        _check(lib.mrx_search_batch(self._h, t._h, optr, n_docs, doc_stride, OUT_HOST, out.ctypes.data))
+        return out
+
+    def sub(self, repl, text, count: int = 0) -> bytes:
+        t, _ = _text_of(text)
+        r = _as_bytes(repl)
+        ob = _Bytes()
+        _check(lib.mrx_sub(self._h, r, len(r), count, t._h, OUT_HOST, ctypes.byref(ob)))
+        try:
+            return ctypes.string_at(ob.bytes, ob.n) if ob.n else b""
+        finally:
+            lib.mrx_bytes_free(ctypes.byref(ob))
+
+    def split_raw(self, text, maxsplit: int = 0):
+        t, _ = _text_of(text)
+        pc = _Pieces()
+        _check(lib.mrx_split(self._h, t._h, maxsplit, OUT_HOST, ctypes.byref(pc)))
+        try:
+            offs = np.ctypeslib.as_array(pc.offsets, shape=(pc.n + 1,)).copy()
+            data = ctypes.string_at(pc.bytes, int(offs[-1])) if offs[-1] else b""
+        finally:
+            lib.mrx_pieces_free(ctypes.byref(pc))
+        return data, offs
+
+    def split(self, text, maxsplit: int = 0) -> List[bytes]:
+        data, offs = self.split_raw(text, maxsplit)
+        return [data[offs[i]:offs[i + 1]] for i in range(len(offs) - 1)]
+
+    def close(self):
+        if self._h:
+            lib.mrx_regex_free(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DeviceSpans:
+    """Span array living in HBM (owned by the library until closed)."""
+
+    def __init__(self, sp: _Spans):
+        self._sp = sp
+        self.n = int(sp.n)
+        self.ptr = ctypes.cast(sp.start_end, ctypes.c_void_p).value or 0
+
+    def to_numpy(self) -> np.ndarray:
+        import torch
+
+        if self.n == 0:
+            return np.zeros((0, 2), dtype=np.int64)
+        out = torch.empty((self.n, 2), dtype=torch.int64, device="cuda")
+        rt = torch.cuda.cudart()
+        rt.cudaMemcpy(out.data_ptr(), self.ptr, self.n * 16, 3)  # cudaMemcpyDeviceToDevice
+        return out.cpu().numpy()
+
+    def close(self):
+        if self._sp is not None:
+            lib.mrx_spans_free(ctypes.byref(self._sp))
+            self._sp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- module-level API with the reference's pattern cache (matcher.mojo:1166-1321) ---------------
+_cache: Dict[bytes, CompiledRegex] = {}
+
+
+def compile_regex(pattern) -> CompiledRegex:
+    key = _as_bytes(pattern)
+    rx = _cache.get(key)
+    if rx is None:
+        rx = CompiledRegex(key)
+        _cache[key] = rx
+    return rx
+
+
+def clear_regex_cache() -> None:
+    _cache.clear()
+
+
+def search(pattern, text) -> Optional[Match]:
+    return compile_regex(pattern).match_next(text, 0)
+
+
+def findall(pattern, text) -> MatchList:
+    return compile_regex(pattern).match_all(text)
+
+
+def match_first(pattern, text) -> Optional[Match]:
+    r = compile_regex(pattern).match_first(text, 0)
+    return r if (r is not None and r.start_idx == 0) else None  # matcher.mojo:1411-1415
+
+
+def sub(pattern, repl, text, count: int = 0) -> bytes:
+    return compile_regex(pattern).sub(repl, text, count)
+
+
+def split(pattern, text, maxsplit: int = 0) -> List[bytes]:
+    return compile_regex(pattern).split(text, maxsplit)

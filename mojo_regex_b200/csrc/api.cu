@@ -1,0 +1,1027 @@
+// C ABI of libmojoregex_cuda.so (see include/mojoregex_cuda.h).  Host orchestration only:
+// every byte of text is touched by the kernels in kernels.cu, never by host code.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "frontend.hpp"
+#include "kernels.cuh"
+#include "program.hpp"
+
+using namespace mrx;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+
+struct Lib {
+  bool inited = false;
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  uint64_t launches = 0;
+  // caching allocators: device blocks and pinned host blocks, bucketed by power-of-two size
+  std::multimap<size_t, void *> dev_free, host_free;
+  std::map<void *, size_t> dev_live, host_live;
+  // small persistent scratch
+  unsigned int *ticket = nullptr;        // 4 tickets
+  unsigned long long *scalars = nullptr; // [0] total, [1] best, [2..4] attempt_one out
+  unsigned long long *h_scalars = nullptr;  // pinned mirror
+};
+Lib g;
+
+#define CUDA_TRY(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) return fail(MRX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+size_t bucket(size_t n) {
+  size_t b = 256;
+  while (b < n) b <<= 1;
+  return b;
+}
+int dev_alloc(size_t n, void **out) {
+  const size_t b = bucket(n ? n : 1);
+  auto it = g.dev_free.find(b);
+  if (it != g.dev_free.end()) {
+    *out = it->second;
+    g.dev_free.erase(it);
+  } else {
+    cudaError_t e = cudaMalloc(out, b);
+    if (e != cudaSuccess) {
+      // drop the cache and retry once
+      for (auto &kv : g.dev_free) cudaFree(kv.second);
+      g.dev_free.clear();
+      e = cudaMalloc(out, b);
+      if (e != cudaSuccess) return fail(MRX_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+  }
+  g.dev_live[*out] = b;
+  return MRX_OK;
+}
+void dev_release(void *p) {
+  if (!p) return;
+  auto it = g.dev_live.find(p);
+  if (it == g.dev_live.end()) return;
+  g.dev_free.emplace(it->second, p);
+  g.dev_live.erase(it);
+}
+int host_alloc(size_t n, void **out) {
+  const size_t b = bucket(n ? n : 1);
+  auto it = g.host_free.find(b);
+  if (it != g.host_free.end()) {
+    *out = it->second;
+    g.host_free.erase(it);
+  } else {
+    cudaError_t e = cudaHostAlloc(out, b, cudaHostAllocDefault);
+    if (e != cudaSuccess) return fail(MRX_E_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+  }
+  g.host_live[*out] = b;
+  return MRX_OK;
+}
+void host_release(void *p) {
+  if (!p) return;
+  auto it = g.host_live.find(p);
+  if (it == g.host_live.end()) return;
+  g.host_free.emplace(it->second, p);
+  g.host_live.erase(it);
+}
+
+// RAII for temporaries taken from the device pool
+struct DevTmp {
+  void *p = nullptr;
+  ~DevTmp() { dev_release(p); }
+  int get(size_t n) { return dev_alloc(n, &p); }
+  template <class T> T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+}  // namespace
+
+struct mrx_regex {
+  Program prog;
+  DevProg *d_findall = nullptr, *d_search = nullptr;
+  bool search_dominated = false;
+};
+
+struct mrx_text {
+  uint8_t *d = nullptr;
+  size_t n = 0;
+  bool owned = false;
+  size_t core_begin = 0, core_end = 0;
+  int64_t global_offset = 0;
+};
+
+namespace {
+
+struct OwnedOut {  // behind the _owner fields
+  void *dev[3] = {nullptr, nullptr, nullptr};
+  void *host[3] = {nullptr, nullptr, nullptr};
+};
+void release_owner(void *o) {
+  if (!o) return;
+  OwnedOut *w = static_cast<OwnedOut *>(o);
+  for (void *p : w->dev) dev_release(p);
+  for (void *p : w->host) host_release(p);
+  delete w;
+}
+
+int require_device() {
+  if (!g.inited) return fail(MRX_E_NO_DEVICE, "mrx_init() has not been called (no CUDA device selected); there is no CPU fallback");
+  return MRX_OK;
+}
+
+Filter make_filter(const Plan &pl) {
+  Filter f{};
+  f.kind = pl.filt;
+  auto splat = [](uint32_t b) { return b * 0x01010101u; };
+  if (pl.filt == FILT_NEEDLES) {
+    f.n_needles = pl.n_needles;
+    f.n0 = splat(pl.needles[0]); f.n1 = splat(pl.needles[1]); f.n2 = splat(pl.needles[2]); f.n3 = splat(pl.needles[3]);
+  } else if (pl.filt == FILT_RANGE) {
+    f.n0 = splat(pl.range_lo);
+    f.hi_is_ff = pl.range_hi == 255;
+    f.n1 = splat((uint32_t)((pl.range_hi + 1) & 255));
+  }
+  return f;
+}
+
+int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
+  if ((size_t)p.n_states * p.n_classes > (size_t)kMaxTrans)
+    return fail(MRX_E_UNSUPPORTED, "automaton too large for the shared-memory table (" + std::to_string(p.n_states) + " states x " +
+                                       std::to_string(p.n_classes) + " classes)");
+  if (pl.literal.size() > (size_t)kMaxLiteral) return fail(MRX_E_UNSUPPORTED, "literal longer than 256 bytes");
+  std::vector<uint8_t> raw(sizeof(DevProg), 0);
+  DevProg *h = reinterpret_cast<DevProg *>(raw.data());
+  h->n_states = p.n_states;
+  h->n_classes = p.n_classes;
+  h->start_state = p.start_state;
+  h->flags = (p.flag(BF_END_ANCHOR) ? DF_END_ANCHOR : 0) | (p.flag(BF_START_ANCHOR) ? DF_START_ANCHOR : 0) |
+             (p.start_accepting() ? DF_START_ACCEPTING : 0) | (pl.shortcut ? DF_SHORTCUT : 0);
+  h->literal_len = (int32_t)pl.literal.size();
+  h->required_byte = p.required_byte;
+  h->trans_len = p.n_states * p.n_classes;
+  std::memcpy(h->byte_class, p.byte_class.data(), 256);
+  std::memcpy(h->lookup, p.lookup.data(), 256);
+  std::memcpy(h->cand, pl.cand.data(), 256);
+  if (!p.accepting.empty()) std::memcpy(h->accepting, p.accepting.data(), p.accepting.size());
+  if (!pl.literal.empty()) std::memcpy(h->literal, pl.literal.data(), pl.literal.size());
+  if (!p.trans.empty()) std::memcpy(h->trans, p.trans.data(), p.trans.size());
+  void *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, sizeof(DevProg)));
+  CUDA_TRY(cudaMemcpyAsync(d, h, sizeof(DevProg), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  *out = static_cast<DevProg *>(d);
+  return MRX_OK;
+}
+
+int ensure_uploaded(mrx_regex *re) {
+  if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
+  if (!re->d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->d_findall); if (rc) return rc; }
+  if (!re->d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->d_search); if (rc) return rc; }
+  return MRX_OK;
+}
+
+int read_scalars(int first, int count) {
+  CUDA_TRY(cudaMemcpyAsync(g.h_scalars + first, g.scalars + first, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return MRX_OK;
+}
+
+// A(p) failing implies A(p+1) failing when both bytes are candidates: after two bytes the younger
+// attempt sits in the state the older one is in ("dominated candidates").
+bool compute_dominated(const Program &p, const Plan &pl) {
+  if (pl.shortcut || p.start_accepting() || p.n_states == 0) return false;
+  if (pl.mode != MRX_MODE_FIRST_CLASS && pl.mode != MRX_MODE_EVERY_POS && pl.mode != MRX_MODE_UNIFORM_RUN) return false;
+  const int nc = p.n_classes, s0 = p.start_state;
+  std::vector<uint8_t> ccls(nc, 0);
+  for (int b = 0; b < 256; ++b) if (pl.cand[b]) ccls[p.byte_class[b]] = 1;
+  // candidates must be exactly class-aligned for the argument below
+  for (int b = 0; b < 256; ++b) if ((pl.cand[b] != 0) != (ccls[p.byte_class[b]] != 0)) return false;
+  for (int a = 0; a < nc; ++a) {
+    if (!ccls[a]) continue;
+    int sa = p.trans[(size_t)s0 * nc + a];
+    for (int b = 0; b < nc; ++b) {
+      if (!ccls[b]) continue;
+      int via = sa == kDead ? kDead : p.trans[(size_t)sa * nc + b];
+      int direct = p.trans[(size_t)s0 * nc + b];
+      if (via != direct) return false;
+      // the younger attempt must not accept where the older one did not: state after `b` is shared,
+      // and the older one's state after `a` alone is irrelevant to the younger.
+    }
+  }
+  return true;
+}
+
+struct DevSpans {
+  int64_t *spans = nullptr;  // pool block
+  int64_t n = 0;
+};
+
+// ---- ordered match list for a plan --------------------------------------------------------------
+struct ListJob {
+  const mrx_regex *re;
+  const mrx_text *t;
+  const Plan *pl;
+  const DevProg *dprog;
+  int64_t key_lo, key_hi;  // buffer coordinates
+  int64_t rebase;
+};
+
+int64_t n_tiles_for(int64_t origin, int64_t hi_inclusive) {
+  if (hi_inclusive < origin) return 0;
+  return (hi_inclusive - origin) / kTile + 1;
+}
+
+int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **keys_out) {
+  const Plan &pl = *job.pl;
+  const int64_t n = (int64_t)job.t->n;
+  const bool at_end = pl.try_at_end && job.re->prog.start_accepting() && job.key_hi >= n;
+  const int64_t origin = job.key_lo & ~15ll;
+  const int64_t last_pos = at_end ? n : job.key_hi - 1;
+  const int64_t tiles = n_tiles_for(origin, last_pos);
+  out.n = 0;
+  if (tiles <= 0) return MRX_OK;
+  if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
+  int64_t cap = std::min<int64_t>((job.key_hi - job.key_lo) / 8 + 1024, 1ll << 26);
+  DevTmp desc;
+  int rc = desc.get(sizeof(unsigned long long) * tiles);
+  if (rc) return rc;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    void *spans = nullptr, *keys = nullptr;
+    rc = dev_alloc(sizeof(int64_t) * 2 * cap, &spans);
+    if (rc) return rc;
+    if (want_keys) { rc = dev_alloc(sizeof(int64_t) * cap, &keys); if (rc) { dev_release(spans); return rc; } }
+    CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+    ScanParams p{};
+    p.text = job.t->d; p.n = n; p.tile_origin = origin; p.key_lo = job.key_lo; p.key_hi = job.key_hi;
+    p.key_hi_inclusive_n = at_end ? 1 : 0; p.try_at_end = at_end ? 1 : 0; p.search_start = job.key_lo;
+    p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS; p.dominated = 0;
+    p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
+    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
+    launch_scan(p, (int)tiles, g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    rc = read_scalars(0, 1);
+    if (rc) { dev_release(spans); dev_release(keys); return rc; }
+    const int64_t total = (int64_t)g.h_scalars[0];
+    if (total <= cap) {
+      out.spans = (int64_t *)spans;
+      out.n = total;
+      if (keys_out) *keys_out = (int64_t *)keys; else dev_release(keys);
+      return MRX_OK;
+    }
+    dev_release(spans);
+    dev_release(keys);
+    cap = total;
+  }
+  return fail(MRX_E_CUDA, "match count did not stabilise");
+}
+
+int run_runs_list(const ListJob &job, DevSpans &out) {
+  const Plan &pl = *job.pl;
+  const int64_t n = (int64_t)job.t->n;
+  const int64_t origin = job.key_lo & ~15ll;
+  const int64_t tiles = n_tiles_for(origin, job.key_hi - 1);
+  out.n = 0;
+  if (tiles <= 0) return MRX_OK;
+  if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
+  DevTmp desc, trail, allf, carry;
+  int rc = desc.get(sizeof(unsigned long long) * tiles);
+  if (rc) return rc;
+  const long long *d_carry = nullptr;
+  if (pl.mode == MRX_MODE_UNIFORM_RUN) {
+    if ((rc = trail.get(sizeof(long long) * tiles))) return rc;
+    if ((rc = allf.get(sizeof(int) * tiles))) return rc;
+    if ((rc = carry.get(sizeof(long long) * tiles))) return rc;
+    // the carry of the first tile is the run length ending just before `origin`: cover it by
+    // starting the trailing-run pass one tile earlier when there is text to the left
+    launch_tile_trailing(job.t->d, n, origin, (int)tiles, job.dprog, trail.as<long long>(), allf.as<int>(), g.stream);
+    launch_carry_scan((int)tiles, trail.as<long long>(), allf.as<int>(), carry.as<long long>(), g.stream);
+    g.launches += 2;
+    d_carry = carry.as<long long>();
+  }
+  int64_t cap = std::min<int64_t>((job.key_hi - job.key_lo) / 8 + 1024, 1ll << 26);
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    void *spans = nullptr;
+    if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &spans))) return rc;
+    CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+    RunsParams p{};
+    p.text = job.t->d; p.n = n; p.tile_origin = origin; p.key_lo = job.key_lo; p.key_hi = job.key_hi;
+    p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max;
+    p.n_tiles = (int)tiles; p.tile_carry = d_carry; p.spans = (int64_t *)spans; p.cap = cap; p.rebase = job.rebase;
+    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
+    launch_runs(p, (int)tiles, g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = read_scalars(0, 1))) { dev_release(spans); return rc; }
+    const int64_t total = (int64_t)g.h_scalars[0];
+    if (total <= cap) { out.spans = (int64_t *)spans; out.n = total; return MRX_OK; }
+    dev_release(spans);
+    cap = total;
+  }
+  return fail(MRX_E_CUDA, "match count did not stabilise");
+}
+
+int select_list(DevSpans &pot, int64_t *keys, DevSpans &out) {
+  const int64_t m = pot.n;
+  out.n = 0;
+  if (m == 0) { out.spans = pot.spans; pot.spans = nullptr; dev_release(keys); return MRX_OK; }
+  const int64_t tiles = (m + kThreads - 1) / kThreads;
+  DevTmp desc, pmax, sel;
+  int rc;
+  if ((rc = desc.get(sizeof(unsigned long long) * tiles))) return rc;
+  if ((rc = pmax.get(sizeof(int64_t) * m))) return rc;
+  if ((rc = sel.get((size_t)m))) return rc;
+  void *outp = nullptr;
+  if ((rc = dev_alloc(sizeof(int64_t) * 2 * m, &outp))) return rc;
+  CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+  CUDA_TRY(cudaMemsetAsync(sel.p, 0, (size_t)m, g.stream));
+  launch_select_prefix_max(pot.spans, m, desc.as<unsigned long long>(), g.ticket, pmax.as<int64_t>(), g.stream);
+  launch_select_walk(pot.spans, keys, pmax.as<int64_t>(), m, sel.as<uint8_t>(), g.stream);
+  CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+  launch_select_compact(pot.spans, sel.as<uint8_t>(), m, desc.as<unsigned long long>(), g.ticket, (int64_t *)outp, g.scalars, g.stream);
+  g.launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = read_scalars(0, 1))) { dev_release(outp); return rc; }
+  out.spans = (int64_t *)outp;
+  out.n = (int64_t)g.h_scalars[0];
+  dev_release(pot.spans);
+  pot.spans = nullptr;
+  dev_release(keys);
+  return MRX_OK;
+}
+
+int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]);
+
+// Final ordered, selected match list for `pl` over the text's core window.
+int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const DevProg *dprog, DevSpans &out) {
+  out = DevSpans();
+  if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  const int64_t n = (int64_t)t->n;
+  ListJob job{re, t, &pl, dprog, (int64_t)t->core_begin, (int64_t)t->core_end, t->global_offset};
+  switch (pl.mode) {
+    case MRX_MODE_WILDCARD_ANY: {  // matcher.mojo:809-813
+      void *p = nullptr;
+      int rc = dev_alloc(16, &p);
+      if (rc) return rc;
+      int64_t h[2] = {t->global_offset, n + t->global_offset};
+      CUDA_TRY(cudaMemcpyAsync(p, h, 16, cudaMemcpyHostToDevice, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      out.spans = (int64_t *)p;
+      out.n = 1;
+      return MRX_OK;
+    }
+    case MRX_MODE_ANCHORED: {  // dfa.mojo:2046-2050: one match_next(text, 0)
+      int64_t se[2];
+      int rc = search_impl(re, t, 0, se);
+      if (rc < 0) return rc;
+      if (rc == 0 || se[0] < (int64_t)t->core_begin || se[0] >= std::max<int64_t>((int64_t)t->core_end, 1)) {
+        if (!(rc == 1 && se[0] == n && (int64_t)t->core_end == n)) return MRX_OK;
+      }
+      void *p = nullptr;
+      if ((rc = dev_alloc(16, &p))) return rc;
+      int64_t h[2] = {se[0] + t->global_offset, se[1] + t->global_offset};
+      CUDA_TRY(cudaMemcpyAsync(p, h, 16, cudaMemcpyHostToDevice, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      out.spans = (int64_t *)p;
+      out.n = 1;
+      return MRX_OK;
+    }
+    case MRX_MODE_CLASS_RUNS:
+    case MRX_MODE_UNIFORM_RUN:
+      return run_runs_list(job, out);
+    default: {
+      if (pl.direct) return run_scan_list(job, false, out, nullptr);
+      DevSpans pot;
+      int64_t *keys = nullptr;
+      const bool want_keys = pl.mode == MRX_MODE_REQUIRED_BYTE;
+      int rc = run_scan_list(job, want_keys, pot, &keys);
+      if (rc) return rc;
+      return select_list(pot, keys, out);
+    }
+  }
+}
+
+int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]) {
+  const Plan &pl = re->prog.search;
+  const int64_t n = (int64_t)t->n;
+  if (start < 0) start = 0;
+  if (pl.mode == MRX_MODE_WILDCARD_ANY) {  // matcher.mojo:762-766
+    if (start <= n) { out[0] = start; out[1] = n; return 1; }
+    return 0;
+  }
+  if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  ScanParams p{};
+  p.text = t->d; p.n = n; p.prog = re->d_search; p.filt = make_filter(pl); p.mode = pl.mode;
+  p.search_start = start; p.rebase = 0;
+  if (pl.mode == MRX_MODE_ANCHORED) {  // dfa.mojo:1888-1892
+    if (start != 0) return 0;
+    p.mode = MRX_MODE_EVERY_POS;
+    launch_attempt_one(p, 0, (int64_t *)(g.scalars + 2), g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    int rc = read_scalars(2, 3);
+    if (rc) return rc;
+    if (!g.h_scalars[4]) return 0;
+    out[0] = (int64_t)g.h_scalars[2]; out[1] = (int64_t)g.h_scalars[3];
+    return 1;
+  }
+  if (pl.mode == MRX_MODE_EXACT_LITERAL && start >= n) return 0;  // matcher.mojo:773-774
+  const bool at_end = pl.try_at_end && re->prog.start_accepting();
+  if (start > n || (start == n && !at_end)) return 0;
+  const int64_t origin = start & ~15ll;
+  const int64_t last_pos = at_end ? n : n - 1;
+  const int64_t tiles = n_tiles_for(origin, last_pos);
+  if (tiles <= 0) return 0;
+  p.key_lo = start; p.key_hi = n; p.key_hi_inclusive_n = at_end; p.try_at_end = at_end;
+  p.out_kind = OUT_FIRST; p.best = g.scalars + 1;
+  p.dominated = (re->search_dominated || pl.mode == MRX_MODE_CLASS_RUNS) ? 1 : 0;
+  launch_fill_u64(g.scalars + 1, 1, ~0ull, g.stream);
+  ++g.launches;
+  // windows of growing size so that an early match does not pay for the whole text
+  int64_t done = 0, win = 64;
+  while (done < tiles) {
+    const int64_t cnt = std::min(win, tiles - done);
+    p.tile_origin = origin + done * kTile;
+    p.n_tiles = (int)cnt;
+    launch_scan(p, (int)cnt, g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    int rc = read_scalars(1, 1);
+    if (rc) return rc;
+    if (g.h_scalars[1] != ~0ull) break;
+    done += cnt;
+    win *= 4;
+  }
+  if (g.h_scalars[1] == ~0ull) return 0;
+  const int64_t pos = (int64_t)g.h_scalars[1];
+  launch_attempt_one(p, pos, (int64_t *)(g.scalars + 2), g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  int rc = read_scalars(2, 3);
+  if (rc) return rc;
+  if (!g.h_scalars[4]) return fail(MRX_E_CUDA, "internal: first-match candidate did not re-verify");
+  out[0] = (int64_t)g.h_scalars[2]; out[1] = (int64_t)g.h_scalars[3];
+  return 1;
+}
+
+int finish_spans(DevSpans &ds, int location, mrx_spans *out) {
+  out->n = (size_t)ds.n;
+  out->location = location;
+  OwnedOut *own = new OwnedOut();
+  out->_owner = own;
+  if (location == MRX_OUT_DEVICE) {
+    own->dev[0] = ds.spans;
+    out->start_end = ds.spans;
+    return MRX_OK;
+  }
+  void *h = nullptr;
+  int rc = host_alloc(sizeof(int64_t) * 2 * std::max<int64_t>(ds.n, 1), &h);
+  if (rc) { dev_release(ds.spans); delete own; out->_owner = nullptr; return rc; }
+  own->host[0] = h;
+  if (ds.n > 0) {
+    CUDA_TRY(cudaMemcpyAsync(h, ds.spans, sizeof(int64_t) * 2 * ds.n, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+  }
+  dev_release(ds.spans);
+  out->start_end = (int64_t *)h;
+  return MRX_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int mrx_abi_version(void) { return MRX_ABI_VERSION; }
+const char *mrx_last_error(void) { return g_err.c_str(); }
+
+int mrx_init(int device) {
+  if (g.inited && g.device == device) return MRX_OK;
+  if (g.inited) mrx_shutdown();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(MRX_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count) return fail(MRX_E_INVALID, "device index out of range");
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&g.ticket, 64));
+  CUDA_TRY(cudaMalloc(&g.scalars, 64 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaHostAlloc(&g.h_scalars, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
+  g.device = device;
+  g.inited = true;
+  g.launches = 0;
+  return MRX_OK;
+}
+
+int mrx_shutdown(void) {
+  if (!g.inited) return MRX_OK;
+  cudaStreamSynchronize(g.stream);
+  for (auto &kv : g.dev_free) cudaFree(kv.second);
+  for (auto &kv : g.host_free) cudaFreeHost(kv.second);
+  g.dev_free.clear();
+  g.host_free.clear();
+  cudaFree(g.ticket);
+  cudaFree(g.scalars);
+  cudaFreeHost(g.h_scalars);
+  cudaStreamDestroy(g.stream);
+  g = Lib();
+  return MRX_OK;
+}
+
+void *mrx_stream(void) { return g.stream; }
+uint64_t mrx_launch_count(void) { return g.launches; }
+int mrx_synchronize(void) {
+  int rc = require_device();
+  if (rc) return rc;
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return MRX_OK;
+}
+
+// ---- front end ---------------------------------------------------------------------------------
+static int regex_from_blob(const std::string &blob, mrx_regex **out) {
+  mrx_regex *re = new mrx_regex();
+  std::string err;
+  if (!load_program((const uint8_t *)blob.data(), blob.size(), re->prog, err)) {
+    delete re;
+    return fail(MRX_E_INVALID, err);
+  }
+  re->search_dominated = compute_dominated(re->prog, re->prog.search);
+  *out = re;
+  return MRX_OK;
+}
+
+int mrx_compile(const uint8_t *pattern, size_t n, mrx_regex **out) {
+  if (!out || (!pattern && n)) return fail(MRX_E_INVALID, "null argument");
+  *out = nullptr;
+  RawDfa dfa;
+  RegexMeta meta;
+  std::string err;
+  int rc = compile_frontend(std::string((const char *)pattern, n), dfa, meta, err);
+  if (rc != MRX_OK) return fail(rc, err);
+  std::string blob;
+  if (!pack_blob(dfa, meta, blob, err)) return fail(MRX_E_UNSUPPORTED, err);
+  return regex_from_blob(blob, out);
+}
+
+int mrx_dfa_pack(const mrx_dfa_desc *desc, const int32_t *transitions, const uint8_t *accepting,
+                 const uint8_t *matcher_lookup, const uint8_t *literal, size_t literal_len,
+                 const uint8_t *exact_literal, size_t exact_len, const uint8_t *prefilter, size_t prefilter_len,
+                 uint8_t *blob, size_t *blob_len) {
+  if (!desc || !blob_len || desc->n_states < 0 || (desc->n_states > 0 && (!transitions || !accepting)))
+    return fail(MRX_E_INVALID, "null argument");
+  RawDfa d;
+  d.trans.resize(desc->n_states);
+  d.accepting.resize(desc->n_states);
+  for (int s = 0; s < desc->n_states; ++s) {
+    std::memcpy(d.trans[s].data(), transitions + (size_t)s * 256, 256 * sizeof(int32_t));
+    d.accepting[s] = accepting[s] ? 1 : 0;
+  }
+  d.start_state = desc->start_state;
+  d.has_start_anchor = desc->has_start_anchor;
+  d.has_end_anchor = desc->has_end_anchor;
+  d.is_pure_literal = desc->is_pure_literal;
+  d.scan_eligible = desc->scan_eligible;
+  if (literal_len) d.literal.assign((const char *)literal, literal_len);
+  if (matcher_lookup) { d.has_matcher = true; std::memcpy(d.lookup.data(), matcher_lookup, 256); }
+  RegexMeta m;
+  m.is_wildcard_any = desc->is_wildcard_any;
+  m.is_exact_literal = desc->is_exact_literal;
+  m.has_anchors_info = desc->has_anchors_info;
+  if (exact_len) m.exact_literal.assign((const char *)exact_literal, exact_len);
+  if (prefilter_len) m.prefilter.assign((const char *)prefilter, prefilter_len);
+  m.required_byte = desc->required_byte;
+  m.fixed_total_width = desc->fixed_sub_total_width;
+  m.fixed_num_groups = desc->fixed_sub_num_groups;
+  m.fixed_concat = desc->fixed_sub_concat;
+  std::memcpy(m.fixed_offsets, desc->fixed_sub_offsets, sizeof m.fixed_offsets);
+  std::memcpy(m.fixed_widths, desc->fixed_sub_widths, sizeof m.fixed_widths);
+  std::string out, err;
+  if (!pack_blob(d, m, out, err)) return fail(MRX_E_UNSUPPORTED, err);
+  if (!blob) { *blob_len = out.size(); return MRX_OK; }
+  if (*blob_len < out.size()) { *blob_len = out.size(); return fail(MRX_E_INVALID, "blob buffer too small"); }
+  std::memcpy(blob, out.data(), out.size());
+  *blob_len = out.size();
+  return MRX_OK;
+}
+
+int mrx_regex_load(const uint8_t *blob, size_t n, mrx_regex **out) {
+  if (!blob || !out) return fail(MRX_E_INVALID, "null argument");
+  *out = nullptr;
+  return regex_from_blob(std::string((const char *)blob, n), out);
+}
+
+int mrx_regex_blob(const mrx_regex *re, uint8_t *buf, size_t *len) {
+  if (!re || !len) return fail(MRX_E_INVALID, "null argument");
+  const std::string &b = re->prog.blob;
+  if (!buf) { *len = b.size(); return MRX_OK; }
+  if (*len < b.size()) { *len = b.size(); return fail(MRX_E_INVALID, "buffer too small"); }
+  std::memcpy(buf, b.data(), b.size());
+  *len = b.size();
+  return MRX_OK;
+}
+
+int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
+  if (!re || !o) return fail(MRX_E_INVALID, "null argument");
+  const Program &p = re->prog;
+  std::memset(o, 0, sizeof *o);
+  o->n_states = p.n_states; o->n_classes = p.n_classes; o->start_state = p.start_state;
+  o->has_start_anchor = p.flag(BF_START_ANCHOR); o->has_end_anchor = p.flag(BF_END_ANCHOR);
+  o->is_pure_literal = p.flag(BF_PURE_LITERAL); o->has_matcher = p.flag(BF_HAS_MATCHER);
+  o->scan_eligible = p.flag(BF_SCAN_ELIGIBLE); o->required_byte = p.required_byte;
+  o->is_wildcard_any = p.flag(BF_WILDCARD_ANY); o->is_exact_literal = p.flag(BF_EXACT_LITERAL);
+  o->has_prefilter = p.flag(BF_HAS_PREFILTER);
+  o->findall_mode = p.findall.unsupported ? -1 : p.findall.mode;
+  o->search_mode = p.search.unsupported ? -1 : p.search.mode;
+  o->findall_direct = p.findall.direct; o->search_direct = p.search.direct;
+  o->fixed_sub_total_width = p.fixed_total_width; o->fixed_sub_num_groups = p.fixed_num_groups;
+  o->fixed_sub_concat = p.fixed_concat;
+  return MRX_OK;
+}
+
+void mrx_regex_free(mrx_regex *re) {
+  if (!re) return;
+  if (re->d_findall) cudaFree(re->d_findall);
+  if (re->d_search) cudaFree(re->d_search);
+  delete re;
+}
+
+// ---- texts ---------------------------------------------------------------------------------------
+int mrx_text_upload(const uint8_t *host, size_t n, mrx_text **out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!out || (!host && n)) return fail(MRX_E_INVALID, "null argument");
+  mrx_text *t = new mrx_text();
+  void *d = nullptr;
+  rc = dev_alloc(n + 512, &d);  // slack so that 16-byte vector reads past the end stay in bounds
+  if (rc) { delete t; return rc; }
+  t->d = (uint8_t *)d;
+  t->n = n;
+  t->owned = true;
+  t->core_begin = 0;
+  t->core_end = n;
+  if (n) CUDA_TRY(cudaMemcpyAsync(d, host, n, cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaMemsetAsync((uint8_t *)d + n, 0, 512, g.stream));
+  *out = t;
+  return MRX_OK;
+}
+
+int mrx_text_wrap_device(const void *dptr, size_t n, mrx_text **out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!out || (!dptr && n)) return fail(MRX_E_INVALID, "null argument");
+  mrx_text *t = new mrx_text();
+  t->d = (uint8_t *)dptr;
+  t->n = n;
+  t->owned = false;
+  t->core_begin = 0;
+  t->core_end = n;
+  *out = t;
+  return MRX_OK;
+}
+
+int mrx_text_set_window(mrx_text *t, size_t core_begin, size_t core_end, int64_t global_offset) {
+  if (!t || core_begin > core_end || core_end > t->n) return fail(MRX_E_INVALID, "bad window");
+  t->core_begin = core_begin;
+  t->core_end = core_end;
+  t->global_offset = global_offset;
+  return MRX_OK;
+}
+
+size_t mrx_text_len(const mrx_text *t) { return t ? t->n : 0; }
+
+void mrx_text_free(mrx_text *t) {
+  if (!t) return;
+  if (t->owned) dev_release(t->d);
+  delete t;
+}
+
+// ---- matching ------------------------------------------------------------------------------------
+int mrx_findall(const mrx_regex *re_c, const mrx_text *t, int location, mrx_spans *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  if ((rc = ensure_uploaded(re))) return rc;
+  DevSpans ds;
+  if ((rc = match_list(re, t, re->prog.findall, re->d_findall, ds))) return rc;
+  return finish_spans(ds, location, out);
+}
+
+int mrx_search(const mrx_regex *re_c, const mrx_text *t, int64_t start, int64_t out[2]) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  if ((rc = ensure_uploaded(re))) return rc;
+  return search_impl(re, t, start, out);
+}
+
+int mrx_match_first(const mrx_regex *re_c, const mrx_text *t, int64_t start, int64_t out[2]) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  const Program &p = re->prog;
+  const int64_t n = (int64_t)t->n;
+  if (p.flag(BF_WILDCARD_ANY)) {  // matcher.mojo:741-745
+    if (start <= n) { out[0] = start; out[1] = n; return 1; }
+    return 0;
+  }
+  if ((rc = ensure_uploaded(re))) return rc;
+  if (p.flag(BF_START_ANCHOR) && start > 0) return 0;  // dfa.mojo:1866-1867
+  if (start > n || start < 0) return 0;
+  // _try_match_at_position(require_exact_position=True): literal verify or one attempt
+  Plan one = p.findall;  // only the attempt semantics matter here
+  ScanParams sp{};
+  sp.text = t->d; sp.n = n; sp.rebase = 0;
+  DevTmp tmpprog;
+  if (p.flag(BF_PURE_LITERAL)) {
+    sp.mode = MRX_MODE_LITERAL;
+    sp.prog = (p.findall.mode == MRX_MODE_LITERAL) ? re->d_findall : re->d_search;
+    if (p.findall.mode != MRX_MODE_LITERAL && p.search.mode != MRX_MODE_LITERAL)
+      return fail(MRX_E_UNSUPPORTED, "match_first on a literal routed through the exact-literal path");
+  } else {
+    sp.mode = MRX_MODE_EVERY_POS;
+    // any uploaded program of this regex carries the same automaton and shortcut flag semantics,
+    // except that the shortcut depends only on the engine -> take the findall program
+    sp.prog = re->d_findall;
+    (void)one;
+  }
+  launch_attempt_one(sp, start, (int64_t *)(g.scalars + 2), g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = read_scalars(2, 3))) return rc;
+  if (!g.h_scalars[4]) return 0;
+  out[0] = (int64_t)g.h_scalars[2];
+  out[1] = (int64_t)g.h_scalars[3];
+  return 1;
+}
+
+int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *doc_offsets, size_t n_docs,
+                     int64_t doc_stride, int location, int64_t *out_start_end) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out_start_end || (!doc_offsets && doc_stride <= 0)) return fail(MRX_E_INVALID, "bad argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  if ((rc = ensure_uploaded(re))) return rc;
+  const Plan &pl = re->prog.search;
+  if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  if (n_docs == 0) return MRX_OK;
+  const int64_t n = (int64_t)t->n;
+  if (pl.mode == MRX_MODE_WILDCARD_ANY || pl.mode == MRX_MODE_ANCHORED)
+    return fail(MRX_E_UNSUPPORTED, "batch search for `.*` / anchored patterns is not built yet");
+  // offsets / results on the device
+  DevTmp d_offs, d_best, d_out;
+  const int64_t *offs_dev = nullptr;
+  if (doc_offsets) {
+    if (location == MRX_OUT_HOST) {
+      if ((rc = d_offs.get(sizeof(int64_t) * (n_docs + 1)))) return rc;
+      CUDA_TRY(cudaMemcpyAsync(d_offs.p, doc_offsets, sizeof(int64_t) * (n_docs + 1), cudaMemcpyHostToDevice, g.stream));
+      offs_dev = d_offs.as<int64_t>();
+    } else {
+      offs_dev = doc_offsets;
+    }
+  }
+  if ((rc = d_best.get(sizeof(unsigned long long) * n_docs))) return rc;
+  launch_fill_u64(d_best.as<unsigned long long>(), (int64_t)n_docs, ~0ull, g.stream);
+  ++g.launches;
+  ScanParams p{};
+  p.text = t->d; p.n = n; p.prog = re->d_search; p.filt = make_filter(pl); p.mode = pl.mode;
+  p.tile_origin = 0; p.key_lo = 0; p.key_hi = n; p.search_start = -1;
+  p.out_kind = OUT_BATCH; p.doc_offsets = offs_dev; p.doc_stride = doc_stride; p.n_docs = (int64_t)n_docs;
+  p.doc_best = d_best.as<unsigned long long>();
+  p.dominated = (re->search_dominated || pl.mode == MRX_MODE_CLASS_RUNS) ? 1 : 0;
+  const int64_t tiles = n_tiles_for(0, n - 1);
+  if (tiles > 0) {
+    p.n_tiles = (int)tiles;
+    launch_scan(p, (int)tiles, g.stream);
+    ++g.launches;
+  }
+  int64_t *outp = out_start_end;
+  if (location == MRX_OUT_HOST) {
+    if ((rc = d_out.get(sizeof(int64_t) * 2 * n_docs))) return rc;
+    outp = d_out.as<int64_t>();
+  }
+  launch_batch_finalize(d_best.as<unsigned long long>(), (int64_t)n_docs, offs_dev, doc_stride, n,
+                        (pl.try_at_end && re->prog.start_accepting()) ? 1 : 0, outp, g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  if (location == MRX_OUT_HOST) {
+    CUDA_TRY(cudaMemcpyAsync(out_start_end, outp, sizeof(int64_t) * 2 * n_docs, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return MRX_OK;
+}
+
+// replacement template: matcher.mojo:1437-1482 (_parse_repl_template, _has_group_refs)
+static bool repl_has_group_refs(const uint8_t *r, size_t n) {
+  for (size_t i = 0; i + 1 < n; ++i)
+    if (r[i] == '\\' && r[i + 1] >= '1' && r[i + 1] <= '9') return true;
+  return false;
+}
+
+int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const mrx_text *t,
+            int location, mrx_bytes *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out || (!repl && repl_n)) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  out->location = location;
+  const Program &p = re->prog;
+  const int64_t n = (int64_t)t->n;
+  if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "sub on a windowed text: assemble per shard on whole buffers");
+  // template
+  SubTemplate tpl{};
+  int64_t repl_len = 0;
+  const bool use_groups = repl_has_group_refs(repl, repl_n);
+  if (use_groups) {
+    if (p.fixed_total_width < 0)
+      return fail(MRX_E_UNSUPPORTED, "capture-group references need the reference's NFA group engine (matcher.mojo:1783-1821)");
+    size_t i = 0, lit_start = 0;
+    auto push_lit = [&](size_t a, size_t b) -> bool {
+      if (b <= a) return true;
+      if (tpl.n_segs >= kMaxTplSegs) return false;
+      tpl.group_off[tpl.n_segs] = -1; tpl.lit_off[tpl.n_segs] = (int32_t)a; tpl.len[tpl.n_segs] = (int32_t)(b - a);
+      ++tpl.n_segs;
+      return true;
+    };
+    while (i < repl_n) {
+      if (repl[i] == '\\' && i + 1 < repl_n && repl[i + 1] >= '1' && repl[i + 1] <= '9') {
+        if (!push_lit(lit_start, i)) return fail(MRX_E_UNSUPPORTED, "replacement template has too many segments");
+        const int gref = repl[i + 1] - '0';
+        if (gref <= p.fixed_num_groups) {  // refs past the last group expand to nothing (matcher.mojo:1613-1620)
+          if (tpl.n_segs >= kMaxTplSegs) return fail(MRX_E_UNSUPPORTED, "replacement template has too many segments");
+          tpl.group_off[tpl.n_segs] = p.fixed_offsets[gref]; tpl.lit_off[tpl.n_segs] = 0; tpl.len[tpl.n_segs] = p.fixed_widths[gref];
+          ++tpl.n_segs;
+        }
+        i += 2;
+        lit_start = i;
+        continue;
+      }
+      ++i;
+    }
+    if (!push_lit(lit_start, repl_n)) return fail(MRX_E_UNSUPPORTED, "replacement template has too many segments");
+  } else if (repl_n) {
+    tpl.n_segs = 1; tpl.group_off[0] = -1; tpl.lit_off[0] = 0; tpl.len[0] = (int32_t)repl_n;
+  }
+  for (int k = 0; k < tpl.n_segs; ++k) repl_len += tpl.len[k];
+  OwnedOut *own = new OwnedOut();
+  out->_owner = own;
+  auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
+  if (n == 0) {  // matcher.mojo:1697-1698
+    out->n = 0;
+    out->bytes = nullptr;
+    return MRX_OK;
+  }
+  if ((rc = ensure_uploaded(re))) return bail(rc);
+  DevSpans ms;
+  if ((rc = match_list(re, t, p.search, re->d_search, ms))) return bail(rc);
+  int64_t M = ms.n;
+  if (count > 0 && M > count) M = count;
+  DevTmp d_repl, d_offs, d_desc, d_bad;
+  struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
+  if ((rc = d_repl.get(repl_n + 16))) return bail(rc);
+  if (repl_n) CUDA_TRY(cudaMemcpyAsync(d_repl.p, repl, repl_n, cudaMemcpyHostToDevice, g.stream));
+  tpl.literal = d_repl.as<uint8_t>();
+  const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
+  if ((rc = d_offs.get(sizeof(int64_t) * (M + 2)))) return bail(rc);
+  if ((rc = d_desc.get(sizeof(unsigned long long) * seg_tiles))) return bail(rc);
+  if ((rc = d_bad.get(16))) return bail(rc);
+  CUDA_TRY(cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long) * seg_tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+  CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 16, g.stream));
+  launch_seg_lengths(ms.spans, M, n, SEG_SUB, repl_len, d_desc.as<unsigned long long>(), g.ticket, d_offs.as<int64_t>(),
+                     d_bad.as<int>(), g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  int64_t total = 0;
+  CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 8, d_offs.as<int64_t>() + (M + 1), 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  total = (int64_t)g.h_scalars[8];
+  void *d_out = nullptr;
+  if ((rc = dev_alloc((size_t)total + 16, &d_out))) return bail(rc);
+  own->dev[0] = d_out;
+  launch_seg_repl(t->d, n, ms.spans, M, d_offs.as<int64_t>(), tpl, (uint8_t *)d_out, g.stream);
+  launch_seg_gaps(t->d, n, ms.spans, M, d_offs.as<int64_t>(), SEG_SUB, (uint8_t *)d_out, g.stream);
+  g.launches += (M > 0 ? 1 : 0) + 1;
+  CUDA_TRY(cudaGetLastError());
+  out->n = (size_t)total;
+  if (location == MRX_OUT_DEVICE) {
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    out->bytes = (uint8_t *)d_out;
+    return MRX_OK;
+  }
+  void *h = nullptr;
+  if ((rc = host_alloc((size_t)total + 1, &h))) return bail(rc);
+  own->host[0] = h;
+  if (total) CUDA_TRY(cudaMemcpyAsync(h, d_out, (size_t)total, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  dev_release(d_out);
+  own->dev[0] = nullptr;
+  out->bytes = (uint8_t *)h;
+  return MRX_OK;
+}
+
+int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int location, mrx_pieces *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  out->location = location;
+  const int64_t n = (int64_t)t->n;
+  if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "split on a windowed text: assemble per shard on whole buffers");
+  if ((rc = ensure_uploaded(re))) return rc;
+  DevSpans ms;
+  if ((rc = match_list(re, t, re->prog.findall, re->d_findall, ms))) return rc;
+  struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
+  int64_t M = ms.n;
+  if (maxsplit < 0) M = 0;  // matcher.mojo:1386-1387 with splits_done(0) >= maxsplit
+  else if (maxsplit > 0 && M > maxsplit) M = maxsplit;
+  OwnedOut *own = new OwnedOut();
+  out->_owner = own;
+  auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
+  DevTmp d_desc, d_bad;
+  const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
+  void *d_offs = nullptr;
+  if ((rc = dev_alloc(sizeof(int64_t) * (M + 2), &d_offs))) return bail(rc);
+  own->dev[1] = d_offs;
+  if ((rc = d_desc.get(sizeof(unsigned long long) * seg_tiles))) return bail(rc);
+  if ((rc = d_bad.get(16))) return bail(rc);
+  CUDA_TRY(cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long) * seg_tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+  CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 16, g.stream));
+  launch_seg_lengths(ms.spans, M, n, SEG_SPLIT, 0, d_desc.as<unsigned long long>(), g.ticket, (int64_t *)d_offs,
+                     d_bad.as<int>(), g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 8, (int64_t *)d_offs + (M + 1), 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 9, d_bad.p, 4, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if ((int)(g.h_scalars[9] & 0xffffffffu) != 0)
+    return bail(fail(MRX_E_UNDEFINED, "separator spans overlap (text[prev_end:start] with prev_end > start): the reference's "
+                                      "behaviour is undefined here (matcher.mojo:1389)"));
+  const int64_t total = (int64_t)g.h_scalars[8];
+  void *d_bytes = nullptr;
+  if ((rc = dev_alloc((size_t)total + 16, &d_bytes))) return bail(rc);
+  own->dev[0] = d_bytes;
+  launch_seg_gaps(t->d, n, ms.spans, M, (int64_t *)d_offs, SEG_SPLIT, (uint8_t *)d_bytes, g.stream);
+  ++g.launches;
+  CUDA_TRY(cudaGetLastError());
+  out->n = (size_t)(M + 1);
+  if (location == MRX_OUT_DEVICE) {
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    out->bytes = (uint8_t *)d_bytes;
+    out->offsets = (int64_t *)d_offs;
+    return MRX_OK;
+  }
+  void *hb = nullptr, *ho = nullptr;
+  if ((rc = host_alloc((size_t)total + 1, &hb))) return bail(rc);
+  own->host[0] = hb;
+  if ((rc = host_alloc(sizeof(int64_t) * (M + 2), &ho))) return bail(rc);
+  own->host[1] = ho;
+  if (total) CUDA_TRY(cudaMemcpyAsync(hb, d_bytes, (size_t)total, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaMemcpyAsync(ho, d_offs, sizeof(int64_t) * (M + 2), cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  dev_release(d_bytes); own->dev[0] = nullptr;
+  dev_release(d_offs); own->dev[1] = nullptr;
+  out->bytes = (uint8_t *)hb;
+  out->offsets = (int64_t *)ho;
+  return MRX_OK;
+}
+
+void mrx_spans_free(mrx_spans *s) {
+  if (!s) return;
+  release_owner(s->_owner);
+  std::memset(s, 0, sizeof *s);
+}
+void mrx_bytes_free(mrx_bytes *b) {
+  if (!b) return;
+  release_owner(b->_owner);
+  std::memset(b, 0, sizeof *b);
+}
+void mrx_pieces_free(mrx_pieces *p) {
+  if (!p) return;
+  release_owner(p->_owner);
+  std::memset(p, 0, sizeof *p);
+}
+
+}  // extern "C"

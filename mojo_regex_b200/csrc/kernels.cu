@@ -1,0 +1,956 @@
+// Hand-written sm_100a kernels of the matching hot path.
+//
+//  k_scan<FILT>      candidate filter (SWAR, 16-B shared-memory vectors) + per-candidate attempt
+//                    (dense DFA walk from a shared-memory table / literal compare / required-byte
+//                    back-scan), ordered single-pass compaction by decoupled look-back.  Serves
+//                    findall (direct or potential list), search (global first match) and batch
+//                    search (per-document first match).
+//  k_runs<FILT>      maximal class runs (CLASS_RUNS) and closed-form chunking of runs for chain
+//                    automata over one class (UNIFORM_RUN), ordered compaction as above.
+//  k_tile_trailing / k_carry_scan   run-length carry across tiles for UNIFORM_RUN.
+//  k_select_*        greedy non-overlap selection over a potential-match list.
+//  k_seg_*           output assembly for sub / split.
+//
+// Text tiles are staged into shared memory with the TMA 1-D bulk copy (cp.async.bulk, mbarrier
+// completion); each thread then owns 144 contiguous bytes (9 x LDS.128, bank-conflict free).
+#include "kernels.cuh"
+
+namespace mrx {
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory layout helpers
+struct TextView {
+  const uint8_t *g;   // whole buffer in HBM
+  const uint8_t *s;   // staged window in shared memory
+  int64_t s_begin, s_end;
+  __device__ __forceinline__ uint8_t at(int64_t q) const {
+    return (q >= s_begin && q < s_end) ? s[q - s_begin] : g[q];
+  }
+};
+
+__device__ __forceinline__ void load_prog(DevProg *dst, const DevProg *src) {
+  // header + the four 256-byte tables + literal, then only the live part of the transition table
+  const int fixed = offsetof(DevProg, trans);
+  const int total = fixed + ((src->trans_len + 15) & ~15);
+  const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+  uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+  for (int i = threadIdx.x; i < total / 16; i += blockDim.x) d4[i] = s4[i];
+}
+
+// Stage text[begin, begin+bytes) into shared memory.  TMA bulk copy when the global address is
+// 16-byte aligned (always true for library-owned texts), plain loads otherwise.
+__device__ __forceinline__ void stage_tile(uint8_t *sm, const uint8_t *g, int64_t begin, int bytes, uint64_t *bar) {
+  const bool aligned = ((reinterpret_cast<uintptr_t>(g + begin) & 15) == 0);
+  const int bulk = aligned ? (bytes & ~15) : 0;
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (bulk > 0) {
+      mbar_expect_tx(bar, (uint32_t)bulk);
+      tma_bulk_g2s(sm, g + begin, (uint32_t)bulk, bar);
+    }
+  }
+  for (int i = bulk + threadIdx.x; i < bytes; i += blockDim.x) sm[i] = g[begin + i];
+  if (bulk > 0) mbar_wait(bar, 0);
+  __syncthreads();
+}
+
+template <int FILT>
+__device__ __forceinline__ uint32_t filter_word(uint32_t x, const Filter &f, const uint8_t *cand) {
+  if (FILT == FILT_NEEDLES) {
+    // inexact-but-never-missing zero-byte test; candidates are re-checked against cand[]
+    uint32_t t0 = x ^ f.n0, r = (t0 - kL) & ~t0;
+    if (f.n_needles > 1) { uint32_t t = x ^ f.n1; r |= (t - kL) & ~t; }
+    if (f.n_needles > 2) { uint32_t t = x ^ f.n2; r |= (t - kL) & ~t; }
+    if (f.n_needles > 3) { uint32_t t = x ^ f.n3; r |= (t - kL) & ~t; }
+    return r & kH;
+  } else if (FILT == FILT_RANGE) {
+    return swar_range(x, f.n0, f.n1, f.hi_is_ff != 0);
+  } else if (FILT == FILT_LUT) {
+    uint32_t r = 0;
+    r |= cand[x & 255] ? 0x80u : 0;
+    r |= cand[(x >> 8) & 255] ? 0x8000u : 0;
+    r |= cand[(x >> 16) & 255] ? 0x800000u : 0;
+    r |= cand[x >> 24] ? 0x80000000u : 0;
+    return r;
+  } else {
+    return kH;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attempts: DFAEngine._try_match_at_position (dfa.mojo:1905-2026) on the packed table
+struct Attempt {
+  const DevProg *p;
+  TextView tv;
+  int64_t lo, n;  // the text the reference would see is [lo, n)
+
+  // _try_match_simd (dfa.mojo:2132-2197); returns end or -1 (fall through to the DFA walk)
+  __device__ __forceinline__ int64_t simd_shortcut(int64_t start) const {
+    int64_t q = start;
+    while (q < n && p->lookup[tv.at(q)]) ++q;
+    if (q == start && !(p->flags & DF_START_ACCEPTING)) return -1;
+    if ((p->flags & DF_END_ANCHOR) && q != n) return -1;
+    return q;
+  }
+  __device__ __forceinline__ int64_t dfa(int64_t start) const {
+    if (p->flags & DF_SHORTCUT) {
+      int64_t e = simd_shortcut(start);
+      if (e >= 0) return e;
+    }
+    int state = p->start_state;
+    int64_t last = (p->flags & DF_START_ACCEPTING) ? start : -1;
+    int64_t q = start;
+    const int nc = p->n_classes;
+    while (q < n) {
+      const int nx = p->trans[state * nc + p->byte_class[tv.at(q)]];
+      if (nx == 0xFF) break;
+      state = nx;
+      ++q;
+      if (p->accepting[state]) last = q;
+    }
+    if (last >= 0 && (p->flags & DF_END_ANCHOR) && last != n) return -1;
+    return last;
+  }
+  __device__ __forceinline__ bool literal_at(int64_t pos) const {
+    const int m = p->literal_len;
+    if (pos + m > n) return false;
+    for (int i = 0; i < m; ++i)
+      if (tv.at(pos + i) != p->literal[i]) return false;
+    return true;
+  }
+};
+
+struct Hit {
+  int64_t key, s, e;
+};
+
+// One candidate position -> at most one potential match.
+__device__ __forceinline__ bool try_candidate(const ScanParams &prm, const Attempt &at, int64_t pos, Hit &h) {
+  switch (prm.mode) {
+    case MRX_MODE_LITERAL:
+    case MRX_MODE_EXACT_LITERAL:
+      if (!at.literal_at(pos)) return false;
+      h.key = h.s = pos;
+      h.e = pos + at.p->literal_len;
+      return true;
+    case MRX_MODE_REQUIRED_BYTE: {  // matcher.mojo:876-897
+      int64_t start = pos;
+      while (start > at.lo && at.p->lookup[at.tv.at(start - 1)]) --start;
+      if ((at.p->flags & DF_START_ANCHOR) && start > at.lo) return false;  // match_first, dfa.mojo:1866-1867
+      int64_t e = at.dfa(start);
+      if (e < 0 || e <= pos) return false;
+      h.key = pos; h.s = start; h.e = e;
+      return true;
+    }
+    default: {
+      int64_t e = at.dfa(pos);
+      if (e < 0) return false;
+      h.key = h.s = pos;
+      h.e = e;
+      return true;
+    }
+  }
+}
+
+__device__ __forceinline__ int64_t doc_of(const ScanParams &prm, int64_t pos) {
+  if (prm.doc_offsets == nullptr) return pos / prm.doc_stride;
+  int64_t lo = 0, hi = prm.n_docs;  // last d with doc_offsets[d] <= pos
+  while (hi - lo > 1) {
+    int64_t mid = (lo + hi) >> 1;
+    if (prm.doc_offsets[mid] <= pos) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+struct ScanShared {
+  DevProg prog;
+  alignas(16) uint8_t text[kTile + kHalo];
+  alignas(8) uint64_t bar;
+  int scan_ws[kThreads / 32 + 2];
+  int tile;
+  int overflow;
+  unsigned long long base;
+  uint32_t slot_s[kThreads * kSlots];  // start relative to tile_start - kBack (fits 32 bits)
+  uint32_t slot_l[kThreads * kSlots];  // length
+  uint32_t slot_k[kThreads * kSlots];  // key - start (required-byte potentials)
+};
+
+template <int FILT>
+__global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  ScanShared &sh = *reinterpret_cast<ScanShared *>(smem_raw);
+  const int tid = threadIdx.x;
+
+  if (tid == 0) {
+    sh.tile = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
+    sh.overflow = 0;
+    // early exit for search: a match left of this tile is already known (block-uniform decision)
+    sh.base = (prm.out_kind == OUT_FIRST) ? ld_volatile_u64(prm.best) : ~0ull;
+  }
+  load_prog(&sh.prog, prm.prog);
+  __syncthreads();
+  const int tile = sh.tile;
+  const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
+  if (prm.out_kind == OUT_FIRST && sh.base < (unsigned long long)tile_start) return;
+  int stage_bytes = kTile + kHalo;
+  if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
+  stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
+
+  Attempt at;
+  at.p = &sh.prog;
+  at.tv.g = prm.text;
+  at.tv.s = sh.text;
+  at.tv.s_begin = tile_start;
+  at.tv.s_end = tile_start + stage_bytes;
+  at.lo = 0;
+  at.n = prm.n;
+
+  const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
+  const int64_t key_lo = prm.key_lo, key_hi = prm.key_hi;  // candidate positions in [key_lo, key_hi)
+  const uint8_t *cand = sh.prog.cand;
+
+  int cnt = 0;
+  unsigned long long out_idx = 0;
+
+  // PASS 0: count (+ buffer up to kSlots per thread);  PASS 1 (only after overflow): emit directly
+  for (int pass = 0; pass < 2; ++pass) {
+    if (pass == 1) cnt = 0;
+    int64_t cur_doc = -1, doc_lo = 0, doc_hi = 0;
+    for (int v = 0; v < kVecs; ++v) {
+      const int64_t pos0 = chunk0 + 16 * v;
+      if (pos0 >= key_hi || pos0 + 16 <= key_lo) continue;
+      const uint4 w = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
+      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        uint32_t f = filter_word<FILT>(ws[wi], prm.filt, cand);
+        while (f) {
+          const int b = (__ffs(f) - 1) >> 3;
+          f &= f - 1;
+          const int64_t pos = pos0 + 4 * wi + b;
+          if (pos < key_lo || pos >= key_hi) continue;
+          const uint8_t byte = (uint8_t)(ws[wi] >> (8 * b));
+          if (FILT != FILT_ALL && !cand[byte]) continue;
+          if (prm.out_kind == OUT_BATCH) {
+            if (pos >= doc_hi || pos < doc_lo) {
+              cur_doc = doc_of(prm, pos);
+              doc_lo = prm.doc_offsets ? prm.doc_offsets[cur_doc] : cur_doc * prm.doc_stride;
+              doc_hi = prm.doc_offsets ? prm.doc_offsets[cur_doc + 1] : min(doc_lo + prm.doc_stride, prm.n);
+            }
+            at.lo = doc_lo;
+            at.n = doc_hi;
+          }
+          if (prm.dominated && pos > at.lo && pos > prm.search_start && cand[at.tv.at(pos - 1)]) continue;
+          Hit h;
+          if (!try_candidate(prm, at, pos, h)) continue;
+          if (prm.out_kind == OUT_FIRST) {
+            atomicMin(prm.best, (unsigned long long)h.key);
+          } else if (prm.out_kind == OUT_BATCH) {
+            const unsigned long long packed = ((unsigned long long)(h.s - doc_lo) << 32) | (unsigned long long)(h.e - doc_lo);
+            atomicMin(prm.doc_best + cur_doc, packed);
+          } else if (pass == 0) {
+            if (cnt < kSlots) {
+              const int64_t rel = h.s - (tile_start - kBackSlack);
+              sh.slot_s[tid * kSlots + cnt] = (uint32_t)rel;
+              sh.slot_l[tid * kSlots + cnt] = (uint32_t)(h.e - h.s);
+              sh.slot_k[tid * kSlots + cnt] = (uint32_t)(h.key - h.s);
+              if (rel < 0 || rel > 0xffffffffll || h.e - h.s > 0xffffffffll) sh.overflow = 1;
+            } else {
+              sh.overflow = 1;
+            }
+            ++cnt;
+          } else {
+            const unsigned long long o = out_idx + cnt;
+            if (o < (unsigned long long)prm.cap) {
+              st_span(prm.spans + 2 * o, h.s + prm.rebase, h.e + prm.rebase);
+              if (prm.keys) prm.keys[o] = h.key + prm.rebase;
+            }
+            ++cnt;
+          }
+        }
+      }
+    }
+    // position n itself (empty match at end of text, dfa.mojo:1970-1977 / :2118)
+    if (prm.try_at_end && prm.out_kind != OUT_BATCH && prm.n >= chunk0 && prm.n < chunk0 + kChunk &&
+        prm.n >= key_lo && prm.n <= key_hi && prm.key_hi_inclusive_n) {
+      Hit h;
+      if (try_candidate(prm, at, prm.n, h)) {
+        if (prm.out_kind == OUT_FIRST) {
+          atomicMin(prm.best, (unsigned long long)h.key);
+        } else if (pass == 0) {
+          if (cnt < kSlots) {
+            sh.slot_s[tid * kSlots + cnt] = (uint32_t)(h.s - (tile_start - kBackSlack));
+            sh.slot_l[tid * kSlots + cnt] = 0;
+            sh.slot_k[tid * kSlots + cnt] = 0;
+          } else {
+            sh.overflow = 1;
+          }
+          ++cnt;
+        } else {
+          const unsigned long long o = out_idx + cnt;
+          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, h.s + prm.rebase, h.e + prm.rebase);
+          ++cnt;
+        }
+      }
+    }
+    if (prm.out_kind != OUT_SPANS) return;
+
+    if (pass == 0) {
+      int total;
+      const int rank = block_exclusive_scan(cnt, sh.scan_ws, &total);
+      if (tid < 32) {
+        const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
+        if (tid == 0) {
+          sh.base = b;
+          if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+        }
+      }
+      __syncthreads();
+      out_idx = sh.base + (unsigned long long)rank;
+      if (!sh.overflow) {
+        for (int i = 0; i < cnt; ++i) {
+          const unsigned long long o = out_idx + i;
+          if (o < (unsigned long long)prm.cap) {
+            const int64_t s = (int64_t)sh.slot_s[tid * kSlots + i] + (tile_start - kBackSlack);
+            const int64_t e = s + sh.slot_l[tid * kSlots + i];
+            st_span(prm.spans + 2 * o, s + prm.rebase, e + prm.rebase);
+            if (prm.keys) prm.keys[o] = s + sh.slot_k[tid * kSlots + i] + prm.rebase;
+          }
+        }
+        return;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// class runs
+struct RunsShared {
+  DevProg prog;
+  alignas(16) uint8_t text[kTile + kHalo];
+  alignas(8) uint64_t bar;
+  int scan_ws[kThreads / 32 + 2];
+  int tile;
+  unsigned long long base;
+  long long warp_len[kThreads / 32];
+  int warp_all[kThreads / 32];
+};
+
+// membership bits of 16 bytes
+template <int FILT>
+__device__ __forceinline__ uint32_t class_bits16(const uint4 &w, const Filter &f, const uint8_t *cand) {
+  uint32_t m = 0;
+  const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint32_t fl;
+    if (FILT == FILT_NEEDLES) {
+      fl = swar_eq(ws[i], f.n0);
+      if (f.n_needles > 1) fl |= swar_eq(ws[i], f.n1);
+      if (f.n_needles > 2) fl |= swar_eq(ws[i], f.n2);
+      if (f.n_needles > 3) fl |= swar_eq(ws[i], f.n3);
+    } else {
+      fl = filter_word<FILT>(ws[i], f, cand);
+    }
+    m |= flags_to_nibble(fl) << (4 * i);
+  }
+  return m;
+}
+
+// 144 membership bits of one thread's chunk
+struct ChunkBits {
+  uint32_t w[5];  // bit i of w[i/32] = byte i of the chunk (bits 144..159 of w[4] are zero)
+  __device__ __forceinline__ bool get(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+};
+
+template <int FILT>
+__global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  RunsShared &sh = *reinterpret_cast<RunsShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  if (tid == 0) sh.tile = (int)atomicAdd(prm.ticket, 1u);
+  load_prog(&sh.prog, prm.prog);
+  __syncthreads();
+  const int tile = sh.tile;
+  const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
+  int stage_bytes = kTile + kHalo;
+  if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
+  stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
+  const uint8_t *lut = sh.prog.cand;
+  TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
+
+  const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
+  // membership bits.  CLASS_RUNS treats the key window as the whole text (runs are clipped to it;
+  // shards are stitched by the caller); UNIFORM_RUN needs the real run structure of the buffer.
+  const int64_t vis_lo = prm.mode == MRX_MODE_CLASS_RUNS ? prm.key_lo : 0;
+  const int64_t vis_hi = prm.mode == MRX_MODE_CLASS_RUNS ? prm.key_hi : prm.n;
+  ChunkBits cb;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) cb.w[i] = 0;
+#pragma unroll
+  for (int v = 0; v < kVecs; ++v) {
+    const int64_t pos0 = chunk0 + 16 * v;
+    uint32_t m = 0;
+    if (pos0 < vis_hi && pos0 + 16 > vis_lo) {
+      const uint4 w = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
+      m = class_bits16<FILT>(w, prm.filt, lut);
+      if (pos0 + 16 > vis_hi) m &= (1u << (int)(vis_hi - pos0)) - 1u;
+      if (pos0 < vis_lo) m &= ~((1u << (int)(vis_lo - pos0)) - 1u);
+    }
+    cb.w[v >> 1] |= m << (16 * (v & 1));
+  }
+  const bool prev_in = chunk0 > vis_lo && chunk0 <= vis_hi && lut[tv.at(chunk0 - 1)];
+  const bool next_in = (chunk0 + kChunk < vis_hi) && chunk0 + kChunk >= vis_lo && lut[tv.at(chunk0 + kChunk)];
+
+  if (prm.mode == MRX_MODE_CLASS_RUNS) {
+    // starts: in-class byte whose predecessor is not; ends: in-class byte whose successor is not.
+    // The k-th start pairs with the k-th end globally, so starts and ends are ranked independently
+    // and #ends-before-tile = #starts-before-tile - (a run is open across the tile start).
+    uint32_t st[5], en[5];
+    int ns = 0, ne = 0;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t carry_in = (i == 0) ? (prev_in ? 1u : 0u) : (cb.w[i - 1] >> 31);
+      const uint32_t nxt = (i == 4) ? (next_in ? (1u << 16) : 0u) : 0u;
+      const uint32_t up = (i < 4) ? (cb.w[i + 1] << 31) : 0u;
+      st[i] = cb.w[i] & ~((cb.w[i] << 1) | carry_in);
+      en[i] = cb.w[i] & ~((cb.w[i] >> 1) | up | (i == 4 ? (nxt >> 1) : 0u));
+      ns += __popc(st[i]);
+      ne += __popc(en[i]);
+    }
+    int total_s;
+    const int rank_s = block_exclusive_scan(ns, sh.scan_ws, &total_s);
+    int total_e;
+    const int rank_e = block_exclusive_scan(ne, sh.scan_ws, &total_e);
+    if (tid < 32) {
+      const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total_s);
+      if (tid == 0) {
+        sh.base = b;
+        if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total_s;
+      }
+    }
+    __syncthreads();
+    const bool open_at_tile = tile_start > vis_lo && tile_start < vis_hi && lut[tv.at(tile_start - 1)] && lut[tv.at(tile_start)];
+    unsigned long long os = sh.base + rank_s;
+    unsigned long long oe = sh.base - (open_at_tile ? 1ull : 0ull) + rank_e;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      uint32_t f = st[i];
+      while (f) {
+        const int b = __ffs(f) - 1;
+        f &= f - 1;
+        if (os < (unsigned long long)prm.cap) prm.spans[2 * os] = chunk0 + 32 * i + b + prm.rebase;
+        ++os;
+      }
+      f = en[i];
+      while (f) {
+        const int b = __ffs(f) - 1;
+        f &= f - 1;
+        if (oe < (unsigned long long)prm.cap) prm.spans[2 * oe + 1] = chunk0 + 32 * i + b + 1 + prm.rebase;
+        ++oe;
+      }
+    }
+    return;
+  }
+
+  // ---- UNIFORM_RUN: chain automaton over one class, accepting depths [mn, K] -------------------
+  // distance from the run start at the first byte of this chunk
+  int lead = 0;
+  {
+    bool all = true;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t full = (i == 4) ? 0xffffu : 0xffffffffu;
+      if (all) {
+        if (cb.w[i] == full) lead += (i == 4) ? 16 : 32;
+        else { lead += __ffs(~cb.w[i]) - 1; all = false; }
+      }
+    }
+  }
+  const bool all_in = lead == kChunk;
+  int trail = 0;
+  if (!all_in) {
+    bool go = true;
+#pragma unroll
+    for (int i = 4; i >= 0; --i) {
+      const int bits = (i == 4) ? 16 : 32;
+      const uint32_t full = (i == 4) ? 0xffffu : 0xffffffffu;
+      if (go) {
+        if (cb.w[i] == full) trail += bits;
+        else { trail += __clz(~(cb.w[i] << (32 - bits))); go = false; }
+      }
+    }
+  }
+  // inclusive scan of (all, len) with (a1,l1)*(a2,l2) = (a1&a2, a2 ? l1+l2 : l2)
+  long long len = all_in ? kChunk : trail;
+  int allf = all_in ? 1 : 0;
+  const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long pl = __shfl_up_sync(0xffffffffu, len, o);
+    const int pa = __shfl_up_sync(0xffffffffu, allf, o);
+    if (lane >= o) {
+      if (allf) len += pl;
+      allf &= pa;
+    }
+  }
+  if (lane == 31) { sh.warp_len[warp] = len; sh.warp_all[warp] = allf; }
+  __syncthreads();
+  // carry entering this thread = combine(tile carry, warps before, lanes before)
+  long long carry = prm.tile_carry ? prm.tile_carry[tile] : 0;  // distance at tile start (0 if not in a run)
+  for (int w = 0; w < warp; ++w) carry = sh.warp_all[w] ? carry + sh.warp_len[w] : sh.warp_len[w];
+  {
+    const long long pl = __shfl_up_sync(0xffffffffu, len, 1);
+    const int pa = __shfl_up_sync(0xffffffffu, allf, 1);
+    if (lane > 0) carry = pa ? carry + pl : pl;
+  }
+  // `carry` = number of consecutive in-class bytes immediately before this chunk
+  const int K = prm.run_max, MN = prm.run_min;
+
+  int cnt = 0;
+  unsigned long long out_idx = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    cnt = 0;
+    int i = 0;
+    while (i < kChunk) {
+      // find next run segment [i0, i1) inside the chunk
+      int i0 = i;
+      while (i0 < kChunk && !cb.get(i0)) ++i0;
+      if (i0 >= kChunk) break;
+      int i1 = i0;
+      while (i1 < kChunk && cb.get(i1)) ++i1;
+      const long long d0 = (i0 == 0) ? carry : 0;  // distance of byte i0 from its run start
+      int ext = 0;                                 // in-class bytes following the chunk, capped at K
+      if (i1 == kChunk) {
+        int64_t q = chunk0 + kChunk;
+        while (ext < K && q < prm.n && lut[tv.at(q)]) { ++ext; ++q; }
+      }
+      int first = i0 + (int)((K - (d0 % K)) % K);
+      for (int s = first; s < i1; s += K) {
+        const int rem = (i1 - s) + ext;  // exact when < K
+        const int L = rem >= K ? K : rem;
+        if (L < MN) continue;
+        const int64_t pos = chunk0 + s;
+        if (pos < prm.key_lo || pos >= prm.key_hi) continue;
+        if (pass == 1) {
+          const unsigned long long o = out_idx + cnt;
+          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, pos + prm.rebase, pos + L + prm.rebase);
+        }
+        ++cnt;
+      }
+      i = i1;
+    }
+    if (pass == 0) {
+      int total;
+      const int rank = block_exclusive_scan(cnt, sh.scan_ws, &total);
+      if (tid < 32) {
+        const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
+        if (tid == 0) {
+          sh.base = b;
+          if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+        }
+      }
+      __syncthreads();
+      out_idx = sh.base + (unsigned long long)rank;
+    }
+  }
+}
+
+// trailing in-class run length of every tile (and whether the whole tile is in class)
+__global__ void k_tile_trailing(const uint8_t *text, int64_t n, int64_t tile_origin, int n_tiles, const DevProg *prog,
+                                long long *trail, int *all) {
+  const int tile = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  if (tile >= n_tiles) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t begin = tile_origin + (int64_t)tile * kTile;
+  int64_t end = begin + kTile;
+  if (end > n) end = n;
+  // walk backwards 32 bytes at a time
+  long long t = 0;
+  bool stop = false;
+  for (int64_t hi = end; hi > begin && !stop; hi -= 32) {
+    const int64_t q = hi - 1 - lane;
+    const bool in = (q >= begin) && prog->cand[text[q]];
+    const unsigned m = __ballot_sync(0xffffffffu, in);
+    const int width = (int)min((int64_t)32, hi - begin);
+    const unsigned fullm = width == 32 ? 0xffffffffu : ((1u << width) - 1u);
+    if ((m & fullm) == fullm) t += width;
+    else { t += __ffs(~m) - 1; stop = true; }
+  }
+  if (lane == 0) {
+    trail[tile] = t;
+    all[tile] = (!stop && end - begin == kTile) ? 1 : 0;
+    if (!stop && end - begin < kTile) all[tile] = 0;
+  }
+}
+
+// carry[tile] = in-class bytes immediately before the tile start (sequential over tiles; n_tiles is
+// text/36 KB, so this is microseconds)
+__global__ void k_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long c = 0;
+  for (int t = 0; t < n_tiles; ++t) {
+    carry[t] = c;
+    c = all[t] ? c + trail[t] : trail[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// search helpers
+__global__ void k_attempt_one(const ScanParams prm, int64_t pos, int64_t *out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Attempt at;
+  at.p = prm.prog;
+  at.tv.g = prm.text;
+  at.tv.s = nullptr;
+  at.tv.s_begin = at.tv.s_end = 0;
+  at.lo = 0;
+  at.n = prm.n;
+  Hit h;
+  if (try_candidate(prm, at, pos, h)) { out[0] = h.s; out[1] = h.e; out[2] = 1; }
+  else { out[0] = out[1] = -1; out[2] = 0; }
+}
+
+// first class run at or after `start` (dfa.mojo:2222-2239): OUT_FIRST found the first in-class byte
+__global__ void k_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t q = pos;
+  while (q < n && prog->lookup[text[q]]) ++q;
+  out[0] = pos; out[1] = q; out[2] = q > pos ? 1 : 0;
+}
+
+__global__ void k_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
+                                 int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= n_docs) return;
+  const unsigned long long v = doc_best[d];
+  if (v == ~0ull) {
+    if (empty_at_end) {
+      const int64_t lo = doc_offsets ? doc_offsets[d] : d * doc_stride;
+      const int64_t hi = doc_offsets ? doc_offsets[d + 1] : min(lo + doc_stride, n);
+      out[2 * d] = hi - lo; out[2 * d + 1] = hi - lo;
+    } else {
+      out[2 * d] = -1; out[2 * d + 1] = -1;
+    }
+  } else {
+    out[2 * d] = (int64_t)(v >> 32);
+    out[2 * d + 1] = (int64_t)(v & 0xffffffffull);
+  }
+}
+
+__global__ void k_fill_u64(unsigned long long *p, int64_t n, unsigned long long v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// greedy selection over a potential list sorted by key (= the reference's `pos = end` restart
+// loops, dfa.mojo:2078-2128 / matcher.mojo:876-897, applied to precomputed attempts).
+//   sync node: key >= every earlier end  => no earlier match can cover it => always visited.
+//   clusters between sync nodes are resolved by one thread each (typically 1-3 entries).
+__global__ void k_select_prefix_max(const int64_t *spans, int64_t m, unsigned long long *desc, unsigned int *ticket,
+                                    int64_t *pmax /* exclusive prefix max of ends */) {
+  __shared__ int s_tile;
+  __shared__ long long s_warp[kThreads / 32];
+  __shared__ long long s_base;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t i = (int64_t)tile * kThreads + threadIdx.x;
+  const long long NEG = -1;
+  long long v = (i < m) ? (long long)spans[2 * i + 1] : NEG;
+  long long inc = v;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc = max(inc, t);
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  long long before = NEG;
+  for (int w = 0; w < warp; ++w) before = max(before, s_warp[w]);
+  long long block_max = NEG;
+  for (int w = 0; w < kThreads / 32; ++w) block_max = max(block_max, s_warp[w]);
+  // look-back with max: reuse the sum look-back on (value+1) is not valid for max; do a max look-back
+  if (threadIdx.x < 32) {
+    unsigned long long agg = (unsigned long long)(block_max + 1);  // >= 0
+    long long excl = 0;
+    if (tile == 0) {
+      if (lane == 0) st_volatile_u64(desc, kFlagPre | agg);
+    } else {
+      if (lane == 0) st_volatile_u64(desc + tile, kFlagAgg | agg);
+      int idx = tile - 1;
+      unsigned long long run = 0;
+      while (true) {
+        const int my = idx - lane;
+        unsigned long long d = kFlagPre;
+        if (my >= 0) { do { d = ld_volatile_u64(desc + my); } while ((d >> 62) == 0); }
+        const unsigned pre_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+        const int first_pre = pre_mask ? (__ffs(pre_mask) - 1) : 32;
+        unsigned long long x = (lane <= first_pre) ? (d & kValMask) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) x = max(x, __shfl_xor_sync(0xffffffffu, x, o));
+        run = max(run, x);
+        if (pre_mask) break;
+        idx -= 32;
+      }
+      excl = (long long)run;
+      if (lane == 0) st_volatile_u64(desc + tile, kFlagPre | max(run, agg));
+    }
+    if (lane == 0) s_base = excl - 1;  // back to the "end" domain (-1 = none)
+  }
+  __syncthreads();
+  long long ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = NEG;
+  ex = max(ex, before);
+  ex = max(ex, s_base);
+  if (i < m) pmax[i] = ex;
+}
+
+__global__ void k_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int64_t key_i = keys ? keys[i] : spans[2 * i];
+  if (key_i < pmax[i]) return;  // not a sync node: some earlier potential match may cover it
+  // resolve the cluster that starts here
+  int64_t cover = key_i;
+  for (int64_t j = i; j < m; ++j) {
+    const int64_t kj = keys ? keys[j] : spans[2 * j];
+    if (j > i && kj >= pmax[j]) break;  // next sync node
+    if (kj >= cover) {
+      sel[j] = 1;
+      const int64_t s = spans[2 * j], e = spans[2 * j + 1];
+      cover = (e > kj && e > s) ? e : kj + 1;  // `pos = end`, or `pos += 1` for an empty match
+      if (e <= kj) cover = kj + 1;
+    } else {
+      sel[j] = 0;
+    }
+  }
+}
+
+__global__ void k_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
+                                 unsigned int *ticket, int64_t *out, unsigned long long *total, int n_tiles) {
+  __shared__ int s_tile;
+  __shared__ int ws[kThreads / 32 + 2];
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t i = (int64_t)tile * kThreads + threadIdx.x;
+  const int v = (i < m && sel[i]) ? 1 : 0;
+  int tot;
+  const int rank = block_exclusive_scan(v, ws, &tot);
+  if (threadIdx.x < 32) {
+    const unsigned long long b = lookback_exclusive(desc, tile, (unsigned long long)tot);
+    if (threadIdx.x == 0) {
+      s_base = b;
+      if (tile == n_tiles - 1) *total = b + (unsigned long long)tot;
+    }
+  }
+  __syncthreads();
+  if (v) {
+    const unsigned long long o = s_base + rank;
+    st_span(out + 2 * o, spans[2 * i], spans[2 * i + 1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sub / split assembly.
+// Segment j (0 <= j <= M): gap [pos_j, s_j) copied to out[O_j ...], then (j < M) the replacement
+// (template of literal pieces and fixed-offset group slices), then for a zero-width match the
+// byte text[pos_j] (matcher.mojo:1771-1778).  pos_0 = 0, pos_{j+1} = e_j (or e_j + 1 after a
+// zero-width match); the tail gap j = M runs to n.
+__device__ __forceinline__ int64_t seg_pos(const int64_t *spans, int64_t j, int mode) {
+  if (j == 0) return 0;
+  const int64_t s = spans[2 * (j - 1)], e = spans[2 * (j - 1) + 1];
+  if (mode == SEG_SPLIT) return e;
+  return e == s ? e + 1 : e;
+}
+
+__global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
+                              unsigned long long *desc, unsigned int *ticket, int64_t *offs /* M+2 */,
+                              int *bad, int n_tiles) {
+  __shared__ int s_tile;
+  __shared__ long long s_warp[kThreads / 32];
+  __shared__ unsigned long long s_base;
+  if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
+  __syncthreads();
+  const int tile = s_tile;
+  const int64_t j = (int64_t)tile * kThreads + threadIdx.x;  // 0..M (M = tail gap)
+  long long len = 0;
+  if (j <= M) {
+    const int64_t pos = seg_pos(spans, j, mode);
+    const int64_t gap_end = (j < M) ? spans[2 * j] : n;
+    long long gap = gap_end - pos;
+    if (j == M && gap < 0) gap = 0;  // pos may be n + 1 after a zero-width match at n
+    if (gap < 0) { if (mode == SEG_SPLIT) *bad = 1; gap = 0; }
+    len = gap;
+    if (j < M && mode == SEG_SUB) {
+      len += repl_len;
+      if (spans[2 * j] == spans[2 * j + 1] && pos < n) len += 1;
+    }
+  }
+  long long inc = len;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  long long before = 0, tot = 0;
+  for (int w = 0; w < kThreads / 32; ++w) { if (w < warp) before += s_warp[w]; tot += s_warp[w]; }
+  if (threadIdx.x < 32) {
+    const unsigned long long b = lookback_exclusive(desc, tile, (unsigned long long)tot);
+    if (threadIdx.x == 0) {
+      s_base = b;
+      if (tile == n_tiles - 1) offs[M + 1] = (int64_t)(b + (unsigned long long)tot);
+    }
+  }
+  __syncthreads();
+  if (j <= M) offs[j] = (int64_t)(s_base + before + inc - len);
+}
+
+// one thread per match: replacement bytes (and the zero-width extra byte)
+__global__ void k_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
+                           const SubTemplate tpl, uint8_t *out) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= M) return;
+  const int64_t s = spans[2 * j], e = spans[2 * j + 1];
+  const int64_t pos = seg_pos(spans, j, SEG_SUB);
+  int64_t o = offs[j] + (s - pos);
+  for (int k = 0; k < tpl.n_segs; ++k) {
+    if (tpl.group_off[k] >= 0) {
+      const uint8_t *src = text + s + tpl.group_off[k];
+      for (int i = 0; i < tpl.len[k]; ++i) out[o++] = src[i];
+    } else {
+      const uint8_t *src = tpl.literal + tpl.lit_off[k];
+      for (int i = 0; i < tpl.len[k]; ++i) out[o++] = src[i];
+    }
+  }
+  if (e == s && pos < n) out[o] = text[pos];
+}
+
+// gap copy: grid over input tiles; every thread copies the gap bytes among its 16 input bytes
+__global__ void __launch_bounds__(kThreads) k_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans,
+                                                       int64_t M, const int64_t *offs, int mode, uint8_t *out) {
+  const int64_t x0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
+  if (x0 >= n) return;
+  // j = number of matches with start <= x0  (segment index whose gap could contain x0 is j, if x0 >= pos_j)
+  int64_t lo = 0, hi = M;  // first index with spans[2*idx] > x0
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (spans[2 * mid] > x0) hi = mid; else lo = mid + 1;
+  }
+  int64_t j = lo;  // gap j = [pos_j, s_j) with s_j > x0 (or tail when j == M)
+  int64_t pos = seg_pos(spans, j, mode);
+  int64_t gend = (j < M) ? spans[2 * j] : n;
+  int64_t o = offs[j];
+  const int64_t x1 = min(x0 + 16, n);
+  for (int64_t x = x0; x < x1; ++x) {
+    while (x >= gend && j < M) {
+      ++j;
+      pos = seg_pos(spans, j, mode);
+      gend = (j < M) ? spans[2 * j] : n;
+      o = offs[j];
+    }
+    if (x >= pos && x < gend) out[o + (x - pos)] = text[x];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side launchers
+template <int FILT>
+static void launch_scan_t(const ScanParams &p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_scan<FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanShared));
+    attr_set = true;
+  }
+  k_scan<FILT><<<grid, kThreads, sizeof(ScanShared), st>>>(p);
+}
+void launch_scan(const ScanParams &p, int grid, cudaStream_t st) {
+  switch (p.filt.kind) {
+    case FILT_NEEDLES: launch_scan_t<FILT_NEEDLES>(p, grid, st); break;
+    case FILT_RANGE: launch_scan_t<FILT_RANGE>(p, grid, st); break;
+    case FILT_ALL: launch_scan_t<FILT_ALL>(p, grid, st); break;
+    default: launch_scan_t<FILT_LUT>(p, grid, st); break;
+  }
+}
+template <int FILT>
+static void launch_runs_t(const RunsParams &p, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_runs<FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RunsShared));
+    attr_set = true;
+  }
+  k_runs<FILT><<<grid, kThreads, sizeof(RunsShared), st>>>(p);
+}
+void launch_runs(const RunsParams &p, int grid, cudaStream_t st) {
+  switch (p.filt.kind) {
+    case FILT_NEEDLES: launch_runs_t<FILT_NEEDLES>(p, grid, st); break;
+    case FILT_RANGE: launch_runs_t<FILT_RANGE>(p, grid, st); break;
+    case FILT_ALL: launch_runs_t<FILT_ALL>(p, grid, st); break;
+    default: launch_runs_t<FILT_LUT>(p, grid, st); break;
+  }
+}
+void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
+                          long long *trail, int *all, cudaStream_t st) {
+  const int warps_per_block = 8;
+  k_tile_trailing<<<(n_tiles + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+      text, n, origin, n_tiles, prog, trail, all);
+}
+void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st) {
+  k_carry_scan<<<1, 32, 0, st>>>(n_tiles, trail, all, carry);
+}
+void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st) {
+  k_attempt_one<<<1, 32, 0, st>>>(p, pos, out);
+}
+void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out, cudaStream_t st) {
+  k_run_extent<<<1, 32, 0, st>>>(text, n, prog, pos, out);
+}
+void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
+                           int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st) {
+  k_batch_finalize<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(doc_best, n_docs, doc_offsets, doc_stride, n,
+                                                                     empty_at_end, out);
+}
+void launch_fill_u64(unsigned long long *p, int64_t n, unsigned long long v, cudaStream_t st) {
+  k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
+}
+void launch_select_prefix_max(const int64_t *spans, int64_t m, unsigned long long *desc, unsigned int *ticket,
+                              int64_t *pmax, cudaStream_t st) {
+  k_select_prefix_max<<<(unsigned)((m + kThreads - 1) / kThreads), kThreads, 0, st>>>(spans, m, desc, ticket, pmax);
+}
+void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel,
+                        cudaStream_t st) {
+  k_select_walk<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(spans, keys, pmax, m, sel);
+}
+void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
+                           unsigned int *ticket, int64_t *out, unsigned long long *total, cudaStream_t st) {
+  const int tiles = (int)((m + kThreads - 1) / kThreads);
+  k_select_compact<<<tiles, kThreads, 0, st>>>(spans, sel, m, desc, ticket, out, total, tiles);
+}
+void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
+                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, cudaStream_t st) {
+  const int tiles = (int)((M + 1 + kThreads - 1) / kThreads);
+  k_seg_lengths<<<tiles, kThreads, 0, st>>>(spans, M, n, mode, repl_len, desc, ticket, offs, bad, tiles);
+}
+void launch_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
+                     const SubTemplate &tpl, uint8_t *out, cudaStream_t st) {
+  if (M <= 0) return;
+  k_seg_repl<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(text, n, spans, M, offs, tpl, out);
+}
+void launch_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs, int mode,
+                     uint8_t *out, cudaStream_t st) {
+  if (n <= 0) return;
+  const int64_t threads = (n + 15) / 16;
+  k_seg_gaps<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(text, n, spans, M, offs, mode, out);
+}
+
+}  // namespace mrx

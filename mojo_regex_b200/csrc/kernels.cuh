@@ -1,0 +1,101 @@
+// Kernel parameter blocks and host-side launchers (definitions in kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/mojoregex_cuda.h"
+#include "device.cuh"
+#include "program.hpp"
+
+namespace mrx {
+
+constexpr int64_t kBackSlack = 1 << 20;  // buffered match starts may precede the tile by this much
+
+enum OutKind : int32_t {
+  OUT_SPANS = 0,  // ordered (start,end) list through look-back compaction
+  OUT_FIRST = 1,  // global minimum key (search)
+  OUT_BATCH = 2,  // per-document minimum (batch search)
+};
+
+struct ScanParams {
+  const uint8_t *text;
+  int64_t n;            // bytes in the buffer; the reference sees text[0, n)
+  int64_t tile_origin;  // first tile starts here (16-byte aligned position)
+  int64_t key_lo, key_hi;  // candidate positions reported: [key_lo, key_hi)
+  int32_t key_hi_inclusive_n;  // position n itself is a candidate (empty match at end of text)
+  int32_t try_at_end;
+  int64_t search_start;
+  const DevProg *prog;
+  Filter filt;
+  int32_t mode;
+  int32_t out_kind;
+  int32_t dominated;
+  int32_t n_tiles;
+  int64_t *spans;
+  int64_t *keys;
+  int64_t cap;
+  int64_t rebase;
+  unsigned long long *desc;
+  unsigned int *ticket;
+  unsigned long long *total;
+  unsigned long long *best;
+  const int64_t *doc_offsets;
+  int64_t doc_stride;
+  int64_t n_docs;
+  unsigned long long *doc_best;
+};
+
+struct RunsParams {
+  const uint8_t *text;
+  int64_t n;
+  int64_t tile_origin;
+  int64_t key_lo, key_hi;
+  const DevProg *prog;
+  Filter filt;
+  int32_t mode;  // MRX_MODE_CLASS_RUNS or MRX_MODE_UNIFORM_RUN
+  int32_t run_min, run_max;
+  int32_t n_tiles;
+  const long long *tile_carry;
+  int64_t *spans;
+  int64_t cap;
+  int64_t rebase;
+  unsigned long long *desc;
+  unsigned int *ticket;
+  unsigned long long *total;
+};
+
+enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };
+
+constexpr int kMaxTplSegs = 32;
+struct SubTemplate {
+  int32_t n_segs;
+  int32_t group_off[kMaxTplSegs];  // >= 0: copy `len` bytes from match_start + group_off; < 0: literal
+  int32_t lit_off[kMaxTplSegs];
+  int32_t len[kMaxTplSegs];
+  const uint8_t *literal;  // replacement string in device memory
+};
+
+void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
+void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
+void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
+                          long long *trail, int *all, cudaStream_t st);
+void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st);
+void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st);
+void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out, cudaStream_t st);
+void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
+                           int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st);
+void launch_fill_u64(unsigned long long *p, int64_t n, unsigned long long v, cudaStream_t st);
+void launch_select_prefix_max(const int64_t *spans, int64_t m, unsigned long long *desc, unsigned int *ticket,
+                              int64_t *pmax, cudaStream_t st);
+void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel,
+                        cudaStream_t st);
+void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
+                           unsigned int *ticket, int64_t *out, unsigned long long *total, cudaStream_t st);
+void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
+                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, cudaStream_t st);
+void launch_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
+                     const SubTemplate &tpl, uint8_t *out, cudaStream_t st);
+void launch_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs, int mode,
+                     uint8_t *out, cudaStream_t st);
+
+}  // namespace mrx

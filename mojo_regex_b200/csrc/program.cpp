@@ -1,0 +1,417 @@
+// Blob pack / load and the scan planner.  Host only.
+#include "program.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <queue>
+
+#include "../../include/mojoregex_cuda.h"
+
+namespace mrx {
+
+bool pack_blob(const RawDfa &dfa, const RegexMeta &meta, std::string &blob, std::string &err) {
+  const int ns = (int)dfa.trans.size();
+  if (ns > kMaxStates) {
+    err = "automaton has " + std::to_string(ns) + " states; the packed format holds " + std::to_string(kMaxStates);
+    return false;
+  }
+  // byte classes: two bytes share a class iff every state sends them to the same target
+  std::array<uint8_t, 256> cls{};
+  int ncls = 0;
+  {
+    std::map<std::vector<int32_t>, int> seen;
+    for (int b = 0; b < 256; ++b) {
+      std::vector<int32_t> col(ns);
+      for (int s = 0; s < ns; ++s) col[s] = dfa.trans[s][b];
+      auto it = seen.find(col);
+      if (it == seen.end()) it = seen.emplace(col, ncls++).first;
+      cls[b] = (uint8_t)it->second;
+    }
+  }
+  if (ns == 0) ncls = 0;
+  BlobHeader h{};
+  h.magic = kBlobMagic;
+  h.version = kBlobVersion;
+  h.flags = (dfa.has_start_anchor ? BF_START_ANCHOR : 0) | (dfa.has_end_anchor ? BF_END_ANCHOR : 0) |
+            (dfa.is_pure_literal ? BF_PURE_LITERAL : 0) | (dfa.has_matcher ? BF_HAS_MATCHER : 0) |
+            (dfa.scan_eligible ? BF_SCAN_ELIGIBLE : 0) | (meta.is_wildcard_any ? BF_WILDCARD_ANY : 0) |
+            (meta.is_exact_literal ? BF_EXACT_LITERAL : 0) | (meta.has_anchors_info ? BF_HAS_ANCHORS_INFO : 0) |
+            (!meta.prefilter.empty() ? BF_HAS_PREFILTER : 0);
+  h.n_states = ns;
+  h.n_classes = ncls;
+  h.start_state = dfa.start_state;
+  h.required_byte = meta.required_byte;
+  h.fixed_total_width = meta.fixed_total_width;
+  h.fixed_num_groups = meta.fixed_num_groups;
+  h.fixed_concat = meta.fixed_concat ? 1 : 0;
+  std::memcpy(h.fixed_offsets, meta.fixed_offsets, sizeof h.fixed_offsets);
+  std::memcpy(h.fixed_widths, meta.fixed_widths, sizeof h.fixed_widths);
+  h.literal_len = (uint32_t)dfa.literal.size();
+  h.exact_len = (uint32_t)meta.exact_literal.size();
+  h.prefilter_len = (uint32_t)meta.prefilter.size();
+  blob.assign((const char *)&h, sizeof h);
+  blob.append((const char *)cls.data(), 256);
+  blob.append((const char *)dfa.lookup.data(), 256);
+  blob.append((const char *)dfa.accepting.data(), ns);
+  std::string tr((size_t)ns * ncls, (char)kDead);
+  for (int s = 0; s < ns; ++s)
+    for (int b = 0; b < 256; ++b) {
+      int32_t t = dfa.trans[s][b];
+      if (t < -1 || t >= ns) { err = "transition target out of range"; return false; }
+      tr[(size_t)s * ncls + cls[b]] = (char)(t < 0 ? kDead : t);
+    }
+  blob += tr;
+  blob += dfa.literal;
+  blob += meta.exact_literal;
+  blob += meta.prefilter;
+  uint32_t total = (uint32_t)blob.size();
+  std::memcpy(&blob[offsetof(BlobHeader, total_len)], &total, 4);
+  return true;
+}
+
+namespace {
+
+// ---- planner helpers ------------------------------------------------------------------------
+void choose_filter(Plan &pl) {
+  int cnt = 0, lo = -1, hi = -1, ranges = 0;
+  bool in = false;
+  for (int b = 0; b < 256; ++b) {
+    if (pl.cand[b]) {
+      ++cnt;
+      if (!in) { ++ranges; in = true; if (lo < 0) lo = b; }
+      hi = b;
+    } else {
+      in = false;
+    }
+  }
+  if (cnt == 256) { pl.filt = FILT_ALL; return; }
+  if (cnt >= 1 && cnt <= 4) {
+    pl.filt = FILT_NEEDLES;
+    pl.n_needles = 0;
+    for (int b = 0; b < 256; ++b) if (pl.cand[b]) pl.needles[pl.n_needles++] = (uint8_t)b;
+    for (int i = pl.n_needles; i < 4; ++i) pl.needles[i] = pl.needles[0];
+    return;
+  }
+  if (ranges == 1) { pl.filt = FILT_RANGE; pl.range_lo = (uint8_t)lo; pl.range_hi = (uint8_t)hi; return; }
+  pl.filt = FILT_LUT;
+}
+
+std::vector<uint8_t> can_reach_accept(const Program &p) {
+  std::vector<uint8_t> ok(p.n_states, 0);
+  for (int s = 0; s < p.n_states; ++s) ok[s] = p.accepting[s];
+  bool changed = true;
+  while (changed) {
+    changed = false;
+    for (int s = 0; s < p.n_states; ++s) {
+      if (ok[s]) continue;
+      for (int c = 0; c < p.n_classes; ++c) {
+        int t = p.trans[(size_t)s * p.n_classes + c];
+        if (t != kDead && ok[t]) { ok[s] = 1; changed = true; break; }
+      }
+    }
+  }
+  return ok;
+}
+
+// Can two successful attempts overlap (p < p' < A(p), both succeed)?  Conservative product search
+// over (older thread state, younger thread state, older accepted after p', younger accepted).
+bool attempts_can_overlap(const Program &p, const Plan &pl) {
+  const int ns = p.n_states, nc = p.n_classes, D = ns;  // D = dead
+  if (ns == 0) return false;
+  std::vector<int> cls_rep(nc, -1);  // class -> is there a candidate byte in it
+  std::vector<uint8_t> cls_cand(nc, 0);
+  for (int b = 0; b < 256; ++b) if (pl.cand[b]) cls_cand[p.byte_class[b]] = 1;
+  auto step = [&](int s, int c) { return s == D ? D : (p.trans[(size_t)s * nc + c] == kDead ? D : (int)p.trans[(size_t)s * nc + c]); };
+  // R1: states reachable from start by >= 1 byte
+  std::vector<uint8_t> r1(ns, 0);
+  {
+    std::queue<int> q;
+    for (int c = 0; c < nc; ++c) { int t = step(p.start_state, c); if (t != D && !r1[t]) { r1[t] = 1; q.push(t); } }
+    while (!q.empty()) {
+      int s = q.front(); q.pop();
+      for (int c = 0; c < nc; ++c) { int t = step(s, c); if (t != D && !r1[t]) { r1[t] = 1; q.push(t); } }
+    }
+  }
+  auto idx = [&](int o, int y, int oa, int ya) { return ((o * (ns + 1) + y) * 2 + oa) * 2 + ya; };
+  std::vector<uint8_t> seen((size_t)(ns + 1) * (ns + 1) * 4, 0);
+  std::queue<std::array<int, 4>> q;
+  auto push = [&](int o, int y, int oa, int ya) -> bool {
+    if (o != D && p.accepting[o]) oa = 1;
+    if (y != D && p.accepting[y]) ya = 1;
+    if (oa && ya) return true;
+    if (o == D && y == D) return false;
+    if (o == D && !oa) return false;  // older died without accepting after p': cannot overlap
+    if (y == D && !ya) return false;  // younger failed
+    int k = idx(o, y, oa, ya);
+    if (!seen[k]) { seen[k] = 1; q.push({o, y, oa, ya}); }
+    return false;
+  };
+  for (int s = 0; s < ns; ++s) {
+    if (!r1[s]) continue;
+    for (int c = 0; c < nc; ++c) {
+      if (!cls_cand[c]) continue;
+      int y = step(p.start_state, c), o = step(s, c);
+      if (y == D || o == D) continue;
+      if (push(o, y, 0, 0)) return true;
+    }
+  }
+  while (!q.empty()) {
+    auto st = q.front(); q.pop();
+    for (int c = 0; c < nc; ++c)
+      if (push(step(st[0], c), step(st[1], c), st[2], st[3])) return true;
+  }
+  return false;
+}
+
+// REQUIRED_BYTE: can an accepted string contain a second needle after its first one?
+bool second_needle_possible(const Program &p, int needle) {
+  const int ns = p.n_states, nc = p.n_classes;
+  const int ncl = p.byte_class[needle];
+  // is the needle alone in its class?  if not, the class edge also covers other bytes; still
+  // conservative to treat any edge on that class as a needle edge.
+  std::vector<uint8_t> reach_ok = can_reach_accept(p);
+  // phase 0: before first needle, phase 1: after first needle
+  std::vector<uint8_t> seen(ns * 2, 0);
+  std::queue<std::pair<int, int>> q;
+  seen[p.start_state * 2] = 1;
+  q.push({p.start_state, 0});
+  while (!q.empty()) {
+    auto [s, ph] = q.front(); q.pop();
+    for (int c = 0; c < nc; ++c) {
+      int t = p.trans[(size_t)s * nc + c];
+      if (t == kDead) continue;
+      int nph = ph;
+      if (c == ncl) {
+        if (ph == 1) { if (reach_ok[t]) return true; continue; }
+        nph = 1;
+      }
+      if (!seen[t * 2 + nph]) { seen[t * 2 + nph] = 1; q.push({t, nph}); }
+    }
+  }
+  return false;
+}
+
+bool literal_has_border(const std::string &s) {
+  for (size_t k = 1; k < s.size(); ++k)
+    if (s.compare(0, s.size() - k, s, k, s.size() - k) == 0) return true;
+  return false;
+}
+
+// CharacterClassSIMD candidate set of find_first_nibble_match's vector body
+// (simd_ops.mojo:62-86, 364-401, 565-648).
+void simd_candidates(const std::array<uint8_t, 256> &lookup, std::array<uint8_t, 256> &cand) {
+  int ranges = 0;
+  bool in = false;
+  for (int b = 0; b < 256; ++b) {
+    if (lookup[b]) { if (!in) { ++ranges; in = true; } } else in = false;
+  }
+  if (ranges >= 1 && ranges <= 3) { cand = lookup; return; }
+  uint8_t lo[16] = {0}, hi[16] = {0};
+  int bucket = 0;
+  for (int b = 0; b < 256; ++b)
+    if (lookup[b]) {
+      uint8_t bit = (uint8_t)(1u << (bucket & 7));
+      lo[b & 15] |= bit;
+      hi[b >> 4] |= bit;
+      ++bucket;
+    }
+  for (int b = 0; b < 256; ++b) cand[b] = (lo[b & 15] & hi[b >> 4]) ? 1 : 0;
+}
+
+// Chain automaton over a single byte set with a contiguous accepting tail -> closed-form runs.
+bool detect_uniform_run(const Program &p, const Plan &pl, int &mn, int &mx) {
+  if (pl.shortcut || p.n_states < 2 || p.start_accepting()) return false;
+  const int nc = p.n_classes;
+  std::vector<uint8_t> xcls(nc, 0);
+  for (int c = 0; c < nc; ++c) xcls[c] = p.trans[(size_t)p.start_state * nc + c] != kDead;
+  for (int b = 0; b < 256; ++b)
+    if ((pl.cand[b] != 0) != (xcls[p.byte_class[b]] != 0)) return false;  // candidates == live set
+  int s = p.start_state, depth = 0, first_acc = -1;
+  std::vector<uint8_t> visited(p.n_states, 0);
+  while (true) {
+    visited[s] = 1;
+    int target = -1, live = 0, nx = 0;
+    for (int c = 0; c < nc; ++c) {
+      int t = p.trans[(size_t)s * nc + c];
+      nx += xcls[c];
+      if (t == kDead) continue;
+      if (!xcls[c]) return false;  // edge on a byte outside the run class
+      if (target != -1 && target != t) return false;
+      target = t;
+      ++live;
+    }
+    if (live == 0) break;          // terminal state: no outgoing edges at all
+    if (live != nx) return false;  // only part of the class continues
+    if (visited[target]) return false;  // loop
+    s = target;
+    ++depth;
+    if (p.accepting[s]) { if (first_acc < 0) first_acc = depth; }
+    else if (first_acc >= 0) return false;  // accepting set must be a contiguous tail
+  }
+  if (first_acc < 0 || depth < 1) return false;
+  mn = first_acc;
+  mx = depth;
+  return true;
+}
+
+void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
+  pl.shortcut = p.flag(BF_HAS_MATCHER) && p.n_states > 0 && (p.flag(BF_SCAN_ELIGIBLE) || p.start_accepting());
+  if (first_class) {
+    pl.mode = MRX_MODE_FIRST_CLASS;
+    pl.cand = p.lookup;
+    pl.try_at_end = false;
+    std::array<uint8_t, 256> simd{};
+    simd_candidates(p.lookup, simd);
+    for (int b = 0; b < 256; ++b) {
+      if (simd[b] && !p.lookup[b]) {
+        bool alive = p.n_states > 0 && p.next(p.start_state, b) != kDead;
+        if (alive || p.start_accepting()) {
+          pl.unsupported = true;
+          pl.why = "first-class nibble filter has false positives that reach the automaton; the reference's "
+                   "result then depends on the host SIMD width (simd_ops.mojo:117-133)";
+          return;
+        }
+      }
+    }
+  } else {
+    pl.mode = MRX_MODE_EVERY_POS;
+    pl.try_at_end = true;
+    for (int b = 0; b < 256; ++b)
+      pl.cand[b] = (p.start_accepting() || p.flag(BF_END_ANCHOR) || pl.shortcut ||
+                    (p.n_states > 0 && p.next(p.start_state, b) != kDead)) ? 1 : 0;
+  }
+  int mn, mx;
+  if (!p.flag(BF_START_ANCHOR) && !p.flag(BF_END_ANCHOR) && detect_uniform_run(p, pl, mn, mx)) {
+    pl.mode = MRX_MODE_UNIFORM_RUN;
+    pl.run_min = mn;
+    pl.run_max = mx;
+    pl.direct = true;
+    choose_filter(pl);
+    return;
+  }
+  pl.direct = !pl.shortcut && !p.start_accepting() && !p.flag(BF_END_ANCHOR) && !attempts_can_overlap(p, pl);
+  choose_filter(pl);
+}
+
+void make_plans(Program &p) {
+  Plan &fa = p.findall, &se = p.search;
+  // _try_match_at_position consults _try_match_simd first whenever the engine has a matcher and
+  // (scan-eligible or accepting start state) -- an engine property, identical for every plan.
+  fa.shortcut = se.shortcut =
+      p.flag(BF_HAS_MATCHER) && p.n_states > 0 && (p.flag(BF_SCAN_ELIGIBLE) || p.start_accepting());
+  // ---- match_all: matcher.mojo:804-862 then dfa.mojo:2028-2130
+  if (p.flag(BF_WILDCARD_ANY)) {
+    fa.mode = se.mode = MRX_MODE_WILDCARD_ANY;
+    fa.direct = se.direct = true;
+    return;
+  }
+  if (p.flag(BF_EXACT_LITERAL) && !p.flag(BF_HAS_ANCHORS_INFO)) {
+    fa.mode = MRX_MODE_EXACT_LITERAL;
+    fa.literal = p.exact;
+    fa.direct = true;  // start = pos + 1: every occurrence is reported (matcher.mojo:843)
+    if (!p.exact.empty()) fa.cand[(uint8_t)p.exact[0]] = 1;
+    choose_filter(fa);
+  } else if (p.required_byte >= 0) {
+    fa.mode = MRX_MODE_REQUIRED_BYTE;
+    fa.cand[p.required_byte] = 1;
+    fa.direct = !fa.shortcut && !p.flag(BF_PURE_LITERAL) && !second_needle_possible(p, p.required_byte);
+    choose_filter(fa);
+  } else if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) {
+    fa.mode = MRX_MODE_ANCHORED;
+    fa.direct = true;
+  } else if (p.flag(BF_PURE_LITERAL)) {
+    fa.mode = MRX_MODE_LITERAL;
+    fa.literal = p.literal;
+    fa.cand[(uint8_t)p.literal[0]] = 1;
+    fa.direct = !literal_has_border(p.literal);
+    choose_filter(fa);
+  } else if (p.flag(BF_HAS_MATCHER) && p.n_states > 0 && p.flag(BF_SCAN_ELIGIBLE)) {
+    fa.mode = MRX_MODE_CLASS_RUNS;
+    fa.cand = p.lookup;
+    fa.direct = true;
+    choose_filter(fa);
+  } else if (p.flag(BF_HAS_MATCHER) && p.n_states > 0) {
+    plan_attempt_mode(p, fa, true);
+  } else {
+    plan_attempt_mode(p, fa, false);
+  }
+  // ---- match_next: matcher.mojo:755-802 then dfa.mojo:1874-1903
+  if (p.flag(BF_EXACT_LITERAL) && !p.flag(BF_HAS_ANCHORS_INFO) && !p.exact.empty()) {
+    se.mode = MRX_MODE_EXACT_LITERAL;
+    se.literal = p.exact;
+    se.cand[(uint8_t)p.exact[0]] = 1;
+    se.direct = !literal_has_border(p.exact);
+    choose_filter(se);
+  } else if (p.flag(BF_HAS_PREFILTER) && !p.flag(BF_HAS_ANCHORS_INFO)) {
+    se.mode = MRX_MODE_FIRST_CLASS;
+    se.unsupported = true;
+    se.why = "match_next goes through the MemchrPrefilter literal path (matcher.mojo:784-796), not built yet";
+  } else if (p.flag(BF_START_ANCHOR)) {
+    se.mode = MRX_MODE_ANCHORED;
+    se.direct = true;
+  } else if (p.flag(BF_HAS_MATCHER) && !p.flag(BF_END_ANCHOR)) {
+    if (p.flag(BF_SCAN_ELIGIBLE)) {
+      se.mode = MRX_MODE_CLASS_RUNS;
+      se.cand = p.lookup;
+      se.direct = true;
+      choose_filter(se);
+    } else {
+      plan_attempt_mode(p, se, true);
+    }
+  } else if (p.flag(BF_PURE_LITERAL)) {
+    se.mode = MRX_MODE_LITERAL;
+    se.literal = p.literal;
+    se.cand[(uint8_t)p.literal[0]] = 1;
+    se.direct = !literal_has_border(p.literal);
+    choose_filter(se);
+  } else {
+    plan_attempt_mode(p, se, false);
+  }
+}
+
+}  // namespace
+
+bool load_program(const uint8_t *blob, size_t n, Program &p, std::string &err) {
+  if (!blob || n < sizeof(BlobHeader)) { err = "blob too short"; return false; }
+  BlobHeader h;
+  std::memcpy(&h, blob, sizeof h);
+  if (h.magic != kBlobMagic || h.version != kBlobVersion) { err = "bad blob magic/version"; return false; }
+  if (h.total_len != n) { err = "blob length mismatch"; return false; }
+  if (h.n_states < 0 || h.n_states > kMaxStates || h.n_classes < 0 || h.n_classes > 256) { err = "bad state/class count"; return false; }
+  size_t need = sizeof h + 512 + (size_t)h.n_states + (size_t)h.n_states * h.n_classes + h.literal_len + h.exact_len + h.prefilter_len;
+  if (need != n) { err = "blob sections do not add up"; return false; }
+  if (h.n_states > 0 && (h.start_state < 0 || h.start_state >= h.n_states)) { err = "bad start state"; return false; }
+  if (h.required_byte < -1 || h.required_byte > 255) { err = "bad required byte"; return false; }
+  p = Program();
+  p.flags = h.flags;
+  p.n_states = h.n_states;
+  p.n_classes = h.n_classes;
+  p.start_state = h.start_state;
+  p.required_byte = h.required_byte;
+  p.fixed_total_width = h.fixed_total_width;
+  p.fixed_num_groups = h.fixed_num_groups;
+  p.fixed_concat = h.fixed_concat;
+  std::memcpy(p.fixed_offsets, h.fixed_offsets, sizeof p.fixed_offsets);
+  std::memcpy(p.fixed_widths, h.fixed_widths, sizeof p.fixed_widths);
+  if (p.fixed_num_groups < 0 || p.fixed_num_groups > 9) { err = "bad fixed-sub group count"; return false; }
+  const uint8_t *q = blob + sizeof h;
+  std::memcpy(p.byte_class.data(), q, 256); q += 256;
+  std::memcpy(p.lookup.data(), q, 256); q += 256;
+  p.accepting.assign(q, q + h.n_states); q += h.n_states;
+  p.trans.assign(q, q + (size_t)h.n_states * h.n_classes); q += (size_t)h.n_states * h.n_classes;
+  p.literal.assign((const char *)q, h.literal_len); q += h.literal_len;
+  p.exact.assign((const char *)q, h.exact_len); q += h.exact_len;
+  p.prefilter.assign((const char *)q, h.prefilter_len);
+  for (int b = 0; b < 256; ++b)
+    if (h.n_states > 0 && p.byte_class[b] >= h.n_classes) { err = "byte class out of range"; return false; }
+  for (uint8_t t : p.trans)
+    if (t != kDead && t >= h.n_states) { err = "transition target out of range"; return false; }
+  if (p.flag(BF_PURE_LITERAL) && p.literal.empty()) { err = "pure literal without literal bytes"; return false; }
+  if (!p.flag(BF_WILDCARD_ANY) && h.n_states == 0) { err = "empty automaton"; return false; }
+  p.blob.assign((const char *)blob, n);
+  make_plans(p);
+  return true;
+}
+
+}  // namespace mrx

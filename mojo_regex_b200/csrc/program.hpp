@@ -1,0 +1,87 @@
+// Packed regex program: the blob format shared by the C++ front end and the Mojo-side
+// serializer (mrx_dfa_pack), its decoder, and the planner that picks a scan mode and
+// proves (or fails to prove) that potential matches cannot overlap.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "frontend.hpp"
+
+namespace mrx {
+
+constexpr uint32_t kBlobMagic = 0x4258524du;  // "MRXB"
+constexpr uint32_t kBlobVersion = 1;
+constexpr int kDead = 0xFF;
+constexpr int kMaxStates = 254;
+
+enum BlobFlags : uint32_t {
+  BF_START_ANCHOR = 1u << 0,
+  BF_END_ANCHOR = 1u << 1,
+  BF_PURE_LITERAL = 1u << 2,
+  BF_HAS_MATCHER = 1u << 3,
+  BF_SCAN_ELIGIBLE = 1u << 4,
+  BF_WILDCARD_ANY = 1u << 5,
+  BF_EXACT_LITERAL = 1u << 6,
+  BF_HAS_ANCHORS_INFO = 1u << 7,
+  BF_HAS_PREFILTER = 1u << 8,
+};
+
+#pragma pack(push, 1)
+struct BlobHeader {
+  uint32_t magic, version, total_len, flags;
+  int32_t n_states, n_classes, start_state, required_byte;
+  int32_t fixed_total_width, fixed_num_groups, fixed_concat;
+  int32_t fixed_offsets[10], fixed_widths[10];
+  uint32_t literal_len, exact_len, prefilter_len, reserved;
+  // followed by: byte_class[256] | lookup[256] | accepting[n_states] |
+  //              trans[n_states*n_classes] (0xFF = dead) | literal | exact | prefilter
+};
+#pragma pack(pop)
+
+enum FilterKind : int32_t {
+  FILT_NEEDLES = 0,  // candidate byte in a set of <= 4 values: SWAR equality
+  FILT_RANGE = 1,    // candidate byte in one contiguous range: SWAR range test
+  FILT_LUT = 2,      // 256-entry table in shared memory
+  FILT_ALL = 3,      // every position
+};
+
+struct Plan {
+  int32_t mode = -1;  // MRX_MODE_*
+  bool direct = false;        // potential matches provably never overlap: emit them as final
+  bool unsupported = false;   // plan cannot be executed faithfully
+  std::string why;
+  int32_t filt = FILT_LUT;
+  int32_t n_needles = 0;
+  uint8_t needles[4] = {0, 0, 0, 0};
+  uint8_t range_lo = 0, range_hi = 0;
+  std::array<uint8_t, 256> cand{};  // candidate predicate K(p) on the byte at p
+  bool shortcut = false;            // _try_match_simd fires inside attempts (dfa.mojo:1956-1968)
+  bool try_at_end = false;          // loop also attempts p == n (dfa.mojo:2118, 1899)
+  int32_t run_min = 0, run_max = 0; // UNIFORM_RUN
+  std::string literal;              // LITERAL / EXACT_LITERAL needle
+};
+
+struct Program {
+  uint32_t flags = 0;
+  int32_t n_states = 0, n_classes = 0, start_state = 0, required_byte = -1;
+  std::array<uint8_t, 256> byte_class{}, lookup{};
+  std::vector<uint8_t> accepting, trans;
+  std::string literal, exact, prefilter;
+  int32_t fixed_total_width = -1, fixed_num_groups = 0, fixed_concat = 0;
+  int32_t fixed_offsets[10] = {0}, fixed_widths[10] = {0};
+  std::string blob;
+  Plan findall, search;
+
+  bool flag(uint32_t f) const { return (flags & f) != 0; }
+  bool start_accepting() const { return n_states > 0 && accepting[start_state]; }
+  int next(int s, int byte) const { return trans[(size_t)s * n_classes + byte_class[byte]]; }
+};
+
+// RawDfa (+meta) -> blob.  Returns false (with err) when the automaton does not fit the format.
+bool pack_blob(const RawDfa &dfa, const RegexMeta &meta, std::string &blob, std::string &err);
+// blob -> Program (validates every length and index); then plans.
+bool load_program(const uint8_t *blob, size_t n, Program &p, std::string &err);
+
+}  // namespace mrx

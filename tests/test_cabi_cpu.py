@@ -1,0 +1,176 @@
+"""CPU-side checks of the C ABI: the library loads, exports every symbol the header declares,
+compiles patterns without a GPU, refuses to match without one, and its front end builds the
+same automata as the oracle's independent restatement."""
+import ctypes
+import os
+import re
+import struct
+
+import numpy as np
+import pytest
+
+import mojo_regex_b200 as mr
+import oracle
+from _golden import load_vectors
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "mojoregex_cuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mrx_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    syms = header_symbols()
+    assert len(syms) >= 25
+    for s in syms:
+        assert hasattr(mr.lib, s), s
+    assert sorted(mr.EXPORTS) == syms
+    assert mr.lib.mrx_abi_version() == 1
+
+
+def decode_blob(blob: bytes):
+    hdr = struct.unpack_from("<4I4i3i10i10i4I", blob, 0)
+    magic, version, total, flags, ns, nc, start, req = hdr[:8]
+    assert magic == 0x4258524D and version == 1 and total == len(blob)
+    ftw, fng, fcc = hdr[8:11]
+    foff, fwid = hdr[11:21], hdr[21:31]
+    llen, elen, plen, _ = hdr[31:35]
+    off = struct.calcsize("<4I4i3i10i10i4I")
+    cls = np.frombuffer(blob, np.uint8, 256, off); off += 256
+    lookup = np.frombuffer(blob, np.uint8, 256, off); off += 256
+    acc = np.frombuffer(blob, np.uint8, ns, off); off += ns
+    tr = np.frombuffer(blob, np.uint8, ns * nc, off).reshape(ns, nc) if ns else np.zeros((0, 0), np.uint8)
+    off += ns * nc
+    lit = blob[off:off + llen]; off += llen
+    exact = blob[off:off + elen]; off += elen
+    pref = blob[off:off + plen]
+    full = np.full((ns, 256), -1, dtype=np.int32)
+    for s in range(ns):
+        row = tr[s][cls].astype(np.int32)
+        row[row == 255] = -1
+        full[s] = row
+    return dict(flags=flags, start=start, req=req, trans=full, acc=acc.astype(bool).tolist(), lookup=lookup,
+                literal=lit, exact=exact, prefilter=pref, fixed=(ftw, fng, fcc, list(foff), list(fwid)))
+
+
+PATTERNS = sorted({v["pattern"] for v in load_vectors()["vectors"]} | {
+    r"(hello|world|foo)", r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}", r"(\d{3})(\d{3})(\d{4})",
+    r"\s*,\s*", r"(hello|help|helicopter)", r"(a|b)*", r"(cat|dog)+", r"(ab)?", r"(abc)+", r"(abc)*",
+    r"a*", r"ab+", r"x?", r".+", r".?", r".", r"[0-9]+\.?[0-9]*", r"^[0-9]+\.?[0-9]*$", r"(?:00|33|44)[0-9]{2}",
+    r"ab[0-9]{2}[a-z]{3}", r"\w+\s\w+", r"(\w+) (\w+)", r"[+]*\d+[-]*\d+", r"[abc]+", r"[^x]", r"a{2}b{3}",
+    r".*", r"", r"^", r"$", r"^$", r"\t", r"a|b|c", r"(a|b)|(c|d)", r"[a-f0-9]{8}-[a-f0-9]{4}", r"\d{1,3}\.\d{1,3}",
+})
+
+
+@pytest.mark.parametrize("pattern", PATTERNS, ids=lambda p: p or "<empty>")
+def test_product_front_end_matches_oracle_tables(pattern):
+    try:
+        oc = oracle.frontend.compile_regex(pattern.encode())
+    except oracle.Unsupported:
+        with pytest.raises(mr.UnsupportedPattern):
+            mr.CompiledRegex(pattern)
+        return
+    except oracle.RegexError:
+        with pytest.raises(mr.RegexError):
+            mr.CompiledRegex(pattern)
+        return
+    rx = mr.CompiledRegex(pattern)
+    b = decode_blob(rx.blob())
+    if oc.is_wildcard_match_any:
+        assert b["flags"] & (1 << 5)
+        return
+    d = oc.dfa
+    assert b["trans"].tolist() == d.trans
+    assert b["acc"] == [bool(x) for x in d.accepting]
+    assert b["start"] == d.start_state
+    assert bool(b["flags"] & 1) == d.has_start_anchor and bool(b["flags"] & 2) == d.has_end_anchor
+    assert bool(b["flags"] & 4) == d.is_pure_literal
+    assert bool(b["flags"] & 8) == (d.matcher is not None)
+    assert bool(b["flags"] & 16) == d.simd_scan_eligible
+    assert bool(b["flags"] & 64) == oc.is_exact_literal
+    assert bool(b["flags"] & 128) == oc.has_anchors_info
+    assert bool(b["flags"] & 256) == (oc.prefilter_literal is not None)
+    assert b["literal"] == d.literal_pattern
+    assert b["req"] == oc.required_byte
+    if d.matcher is not None:
+        assert b["lookup"].tolist() == d.matcher.lookup
+    if oc.prefilter_literal is not None:
+        assert b["prefilter"] == oc.prefilter_literal
+    assert b["fixed"][0] == oc.fixed_sub_total_width and b["fixed"][1] == oc.fixed_sub_num_groups
+    assert bool(b["fixed"][2]) == oc.fixed_sub_concat
+    if oc.fixed_sub_total_width >= 0:
+        assert b["fixed"][3] == oc.fixed_sub_offsets and b["fixed"][4] == oc.fixed_sub_widths
+
+
+def test_plans_for_the_five_configs():
+    names = mr.MODE_NAMES
+    i = mr.CompiledRegex(r"\d+").info()
+    assert names[i.findall_mode] == "CLASS_RUNS" and i.findall_direct
+    i = mr.CompiledRegex(r"(hello|world|foo)").info()
+    assert names[i.findall_mode] == "EVERY_POS" and i.findall_direct and (i.n_states, i.n_classes) == (12, 9)
+    i = mr.CompiledRegex(r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}").info()
+    assert names[i.search_mode] == "FIRST_CLASS" and names[i.findall_mode] == "REQUIRED_BYTE" and i.findall_direct
+    i = mr.CompiledRegex(r"(\d{3})(\d{3})(\d{4})").info()
+    assert names[i.search_mode] == "UNIFORM_RUN" and i.fixed_sub_total_width == 10
+    i = mr.CompiledRegex(r"\s*,\s*").info()
+    assert names[i.findall_mode] == "REQUIRED_BYTE" and i.findall_direct and i.required_byte == ord(",")
+    # overlapping candidates -> selection pass needed
+    assert not mr.CompiledRegex("aa").info().findall_direct
+    assert mr.CompiledRegex("ab").info().findall_direct
+    assert not mr.CompiledRegex(r"[a-z]+[0-9]+").info().findall_direct
+
+
+def test_blob_roundtrip_and_dfa_pack():
+    rx = mr.CompiledRegex(r"[a-z]+[0-9]+")
+    blob = rx.blob()
+    rx2 = mr.CompiledRegex(blob=blob)
+    assert rx2.blob() == blob
+    # the Mojo-side serializer entry: raw 256 x int32 tables -> identical blob
+    oc = oracle.frontend.compile_regex(rb"[a-z]+[0-9]+")
+    d = oc.dfa
+    desc = mr.DfaDesc()
+    desc.n_states = len(d.trans)
+    desc.start_state = d.start_state
+    desc.scan_eligible = int(d.simd_scan_eligible)
+    desc.required_byte = oc.required_byte
+    desc.fixed_sub_total_width = oc.fixed_sub_total_width
+    trans = np.asarray(d.trans, dtype=np.int32)
+    acc = np.asarray(d.accepting, dtype=np.uint8)
+    lookup = np.asarray(d.matcher.lookup, dtype=np.uint8)
+    n = ctypes.c_size_t(0)
+    assert mr.lib.mrx_dfa_pack(ctypes.byref(desc), trans.ctypes.data, acc.ctypes.data, lookup.ctypes.data,
+                               None, 0, None, 0, None, 0, None, ctypes.byref(n)) == 0
+    buf = ctypes.create_string_buffer(n.value)
+    assert mr.lib.mrx_dfa_pack(ctypes.byref(desc), trans.ctypes.data, acc.ctypes.data, lookup.ctypes.data,
+                               None, 0, None, 0, None, 0, ctypes.cast(buf, ctypes.c_void_p), ctypes.byref(n)) == 0
+    assert buf.raw[:n.value] == blob
+    # corrupt blobs are rejected
+    with pytest.raises(ValueError):
+        mr.CompiledRegex(blob=blob[:-1])
+    bad = bytearray(blob)
+    bad[0] ^= 0xFF
+    with pytest.raises(ValueError):
+        mr.CompiledRegex(blob=bytes(bad))
+
+
+def test_parse_errors_and_nfa_patterns_are_reported():
+    for p in ["(abc", "abc)", "[abc", "a]", "a{x}"]:
+        with pytest.raises(mr.RegexError):
+            mr.CompiledRegex(p)
+        with pytest.raises(oracle.RegexError):
+            oracle.compile(p)
+    for v in load_vectors()["nfa_routed"]:
+        with pytest.raises(mr.UnsupportedPattern):
+            mr.CompiledRegex(v["pattern"])
+
+
+def test_matching_without_a_device_fails_loudly():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(mr.RegexCudaError):
+        mr.findall(r"\d+", b"abc123")
