@@ -109,6 +109,10 @@ void *mrx_stream(void);
 /* Number of kernels this library has launched since mrx_init (bench.py's gpu_launches). */
 uint64_t mrx_launch_count(void);
 int mrx_synchronize(void);
+/* Measurement aid: when enabled, the dominant kernel of each matching call (k_scan / k_runs) is
+ * bracketed by CUDA events on the library stream; mrx_last_kernel_ms() returns its duration. */
+int mrx_set_profiling(int enabled);
+double mrx_last_kernel_ms(void);
 
 /* ---- front end ------------------------------------------------------------------------ */
 /* Replaces compile_regex()/CompiledRegex(pattern) (matcher.mojo:964-978, 1292-1315) for

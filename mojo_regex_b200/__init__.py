@@ -80,7 +80,7 @@ class DfaDesc(ctypes.Structure):
 
 EXPORTS = [
     "mrx_abi_version", "mrx_init", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
-    "mrx_synchronize", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
+    "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
     "mrx_text_free", "mrx_findall", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
     "mrx_split", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
@@ -100,6 +100,8 @@ def _load() -> ctypes.CDLL:
     lib.mrx_last_error.restype = c.c_char_p
     lib.mrx_stream.restype = vp
     lib.mrx_launch_count.restype = c.c_uint64
+    lib.mrx_set_profiling.argtypes = [c.c_int]
+    lib.mrx_last_kernel_ms.restype = c.c_double
     lib.mrx_compile.argtypes = [c.c_char_p, sz, P(vp)]
     lib.mrx_dfa_pack.argtypes = [P(DfaDesc), vp, vp, vp, c.c_char_p, sz, c.c_char_p, sz, c.c_char_p, sz, vp, P(sz)]
     lib.mrx_regex_load.argtypes = [c.c_char_p, sz, P(vp)]
@@ -168,6 +170,14 @@ def stream_handle() -> int:
 
 def launch_count() -> int:
     return int(lib.mrx_launch_count())
+
+
+def set_profiling(enabled: bool) -> None:
+    lib.mrx_set_profiling(int(enabled))
+
+
+def last_kernel_ms() -> float:
+    return float(lib.mrx_last_kernel_ms())
 
 
 def synchronize() -> None:
@@ -421,15 +431,20 @@ class _DeviceSpans:
         self.n = int(sp.n)
         self.ptr = ctypes.cast(sp.start_end, ctypes.c_void_p).value or 0
 
-    def to_numpy(self) -> np.ndarray:
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n, 2), "typestr": "<i8", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def tensor(self):
+        """Zero-copy torch view (n, 2) int64 of the spans in HBM (valid until close())."""
         import torch
 
         if self.n == 0:
-            return np.zeros((0, 2), dtype=np.int64)
-        out = torch.empty((self.n, 2), dtype=torch.int64, device="cuda")
-        rt = torch.cuda.cudart()
-        rt.cudaMemcpy(out.data_ptr(), self.ptr, self.n * 16, 3)  # cudaMemcpyDeviceToDevice
-        return out.cpu().numpy()
+            return torch.zeros((0, 2), dtype=torch.int64, device="cuda")
+        return torch.as_tensor(self, device="cuda")
+
+    def to_numpy(self) -> np.ndarray:
+        return self.tensor().cpu().numpy()
 
     def close(self):
         if self._sp is not None:

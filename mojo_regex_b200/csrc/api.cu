@@ -34,6 +34,9 @@ struct Lib {
   unsigned int *ticket = nullptr;        // 4 tickets
   unsigned long long *scalars = nullptr; // [0] total, [1] best, [2..4] attempt_one out
   unsigned long long *h_scalars = nullptr;  // pinned mirror
+  bool profiling = false;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool ev_valid = false;
 };
 Lib g;
 
@@ -268,7 +271,9 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS; p.dominated = 0;
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
+    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
     launch_scan(p, (int)tiles, g.stream);
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     rc = read_scalars(0, 1);
@@ -322,7 +327,9 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max;
     p.n_tiles = (int)tiles; p.tile_carry = d_carry; p.spans = (int64_t *)spans; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
+    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
     launch_runs(p, (int)tiles, g.stream);
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     if ((rc = read_scalars(0, 1))) { dev_release(spans); return rc; }
@@ -523,6 +530,8 @@ int mrx_init(int device) {
   CUDA_TRY(cudaMalloc(&g.ticket, 64));
   CUDA_TRY(cudaMalloc(&g.scalars, 64 * sizeof(unsigned long long)));
   CUDA_TRY(cudaHostAlloc(&g.h_scalars, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
+  CUDA_TRY(cudaEventCreate(&g.ev0));
+  CUDA_TRY(cudaEventCreate(&g.ev1));
   g.device = device;
   g.inited = true;
   g.launches = 0;
@@ -539,6 +548,8 @@ int mrx_shutdown(void) {
   cudaFree(g.ticket);
   cudaFree(g.scalars);
   cudaFreeHost(g.h_scalars);
+  cudaEventDestroy(g.ev0);
+  cudaEventDestroy(g.ev1);
   cudaStreamDestroy(g.stream);
   g = Lib();
   return MRX_OK;
@@ -546,6 +557,18 @@ int mrx_shutdown(void) {
 
 void *mrx_stream(void) { return g.stream; }
 uint64_t mrx_launch_count(void) { return g.launches; }
+int mrx_set_profiling(int enabled) {
+  g.profiling = enabled != 0;
+  g.ev_valid = false;
+  return MRX_OK;
+}
+double mrx_last_kernel_ms(void) {
+  if (!g.inited || !g.ev_valid) return -1.0;
+  if (cudaEventSynchronize(g.ev1) != cudaSuccess) return -1.0;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, g.ev0, g.ev1) != cudaSuccess) return -1.0;
+  return (double)ms;
+}
 int mrx_synchronize(void) {
   int rc = require_device();
   if (rc) return rc;
@@ -811,7 +834,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   const int64_t tiles = n_tiles_for(0, n - 1);
   if (tiles > 0) {
     p.n_tiles = (int)tiles;
+    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
     launch_scan(p, (int)tiles, g.stream);
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
   }
   int64_t *outp = out_start_end;

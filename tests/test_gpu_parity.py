@@ -1,0 +1,255 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (ctypes), against the oracle.
+
+Bit-exact bar: spans, sub output bytes and split pieces must be identical.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import mojo_regex_b200 as mr
+import oracle
+from _golden import check_vector, load_vectors
+from mojo_regex_b200 import corpora
+
+pytestmark = pytest.mark.gpu
+
+DATA = load_vectors()
+TILE = 36864
+
+
+class _Impl:
+    """Adapter so tests/_golden.check_vector can drive the product."""
+
+    class _Rx:
+        def __init__(self, p):
+            self.rx = mr.compile_regex(p)
+
+        def findall(self, text):
+            return self.rx.match_all(text).spans
+
+        def search(self, text):
+            m = self.rx.match_next(text, 0)
+            return m.span() if m else None
+
+        def match_first(self, text):
+            m = self.rx.match_first(text, 0)
+            return m.span() if (m and m.start_idx == 0) else None
+
+        def sub(self, repl, text, count=0):
+            return self.rx.sub(repl, text, count)
+
+        def split(self, text, maxsplit=0):
+            return self.rx.split(text, maxsplit)
+
+    def compile(self, p):
+        return self._Rx(p)
+
+
+@pytest.mark.parametrize("v", DATA["vectors"], ids=lambda v: "%s:%s" % (v["op"], v["src"].split("/")[-1]))
+def test_reference_vector_on_gpu(v):
+    check_vector(_Impl(), v)
+
+
+def _compare_all_ops(pattern, text, repl=None):
+    orx = oracle.compile(pattern)
+    grx = mr.compile_regex(pattern)
+    want = orx.findall(text).tolist()
+    got = grx.match_all(text).tolist()
+    assert got == want, (pattern, text[:200], got[:10], want[:10])
+    info = grx.info()
+    if info.search_mode != -1:
+        for start in (0, 1, len(text) // 2, len(text)):
+            w = orx.match_next(text, start)
+            m = grx.match_next(text, start)
+            assert (m.span() if m else None) == w, (pattern, start, text[:200])
+        for start in (0, 3, len(text)):
+            w = orx.match_first_at(text, start)
+            m = grx.match_first(text, start)
+            assert (m.span() if m else None) == w, (pattern, start, text[:200])
+        for r in ([b"<>", b""] if repl is None else [repl]):
+            try:
+                w = orx.sub(r, text)
+            except oracle.Unsupported:
+                with pytest.raises(mr.UnsupportedPattern):
+                    grx.sub(r, text)
+                continue
+            assert grx.sub(r, text) == w, (pattern, r, text[:200])
+            assert grx.sub(r, text, 2) == orx.sub(r, text, 2)
+    try:
+        w = orx.split(text)
+    except oracle.Unsupported:
+        with pytest.raises(mr.UndefinedBehaviour):
+            grx.split(text)
+    else:
+        assert grx.split(text) == w
+        assert grx.split(text, 3) == orx.split(text, 3)
+
+
+FUZZ = [
+    (r"\d+", "0123456789ab xyz"),
+    (r"[a-c]*", "abcx "),
+    (r"\d{2,4}", "0123456789ab "),
+    (r"[^ab]+", "abc d"),
+    (r"(hello|world|foo)", "helowrdf "),
+    (r"(hello|help|helicopter)", "helpicotr "),
+    (r"aa", "ab"),
+    (r"aba", "ab"),
+    (r"abc", "abc "),
+    (r"a|ab|abc", "abc "),
+    (r"(a|b)*", "abc"),
+    (r"(ab|cd)+", "abcd "),
+    (r"(abc)+", "abc "),
+    (r"(ab)?", "abc"),
+    (r"ab*", "abc"),
+    (r"a+", "ab"),
+    (r".", "ab\n"),
+    (r".+", "ab\n\x80"),
+    (r".?", "ab\n"),
+    (r"[a-z]+[0-9]+", "abz019 A"),
+    (r"[a-z]*[0-9]+", "abz019 A"),
+    (r"[a-z]*[0-9]*", "abz019 A"),
+    (r"[0-9]+\.?[0-9]*", "0129. a"),
+    (r"(\d{3})(\d{3})(\d{4})", "0123456789 a"),
+    (r"(\d{2})-(\d{2})", "0123456789- a"),
+    (r"[A-Z]{2}-[0-9]{3}", "ABZ-019 "),
+    (r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}", "abAB09._%+-@ "),
+    (r"\s*,\s*", "ab, \t\n\x0b"),
+    (r"\s*;\s*x", "ab; \tx"),
+    (r"[a-z]+@[a-z]+", "ab@ "),
+    (r"(?:00|33|44)[0-9]{2}[a-z]+", "0345ab "),
+    (r"^ab", "ab "),
+    (r"ab$", "ab "),
+    (r"^", "ab"),
+    (r"$", "ab"),
+    (r"^$", "ab"),
+    (r"", "ab"),
+    (r"\w+\s\w+", "ab_9 \t"),
+    (r"[+]*\d+[-]*\d+", "+-019 "),
+]
+
+
+@pytest.mark.parametrize("pattern,alphabet", FUZZ, ids=[p or "<empty>" for p, _ in FUZZ])
+def test_fuzz_small_texts_against_oracle(pattern, alphabet):
+    rng = random.Random(hash(pattern) & 0xFFFFF)
+    sizes = [0, 1, 2, 3, 7, 15, 16, 17, 31, 33, 64, 100, 143, 144, 145, 300, 1000]
+    for n in sizes + [rng.randrange(0, 400) for _ in range(12)]:
+        text = bytes(ord(rng.choice(alphabet)) for _ in range(n))
+        _compare_all_ops(pattern, text)
+
+
+@pytest.mark.parametrize("pattern,alphabet", [(p, a) for p, a in FUZZ if p in (
+    r"\d+", r"(hello|world|foo)", r"aa", r"[a-z]+[0-9]+", r"(\d{3})(\d{3})(\d{4})", r"\s*,\s*", r"\d{2,4}",
+    r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}", r"a|ab|abc", r"(ab|cd)+", r"[a-c]*")],
+    ids=lambda x: x if isinstance(x, str) and len(x) > 3 else None)
+def test_fuzz_tile_boundaries_against_oracle(pattern, alphabet):
+    rng = random.Random(hash(pattern) & 0xFFFF)
+    for n in (TILE - 1, TILE, TILE + 1, 2 * TILE + 17, 5 * TILE - 3):
+        text = bytes(ord(rng.choice(alphabet)) for _ in range(n))
+        _compare_all_ops(pattern, text)
+
+
+@pytest.mark.parametrize("kind", ["all_digits", "no_digits", "straddle"])
+def test_c1_edge_variants(kind):
+    n = 3 * TILE + 100
+    if kind == "all_digits":
+        text = b"7" * n
+    elif kind == "no_digits":
+        text = b"x" * n
+    else:
+        text = bytearray(b"x" * n)
+        for k in range(1, 4):
+            text[k * TILE - 3:k * TILE + 4] = b"1234567"
+        text = bytes(text)
+    for pat in (r"\d+", r"(\d{3})(\d{3})(\d{4})", r"\d{2,4}", r"\d"):
+        _compare_all_ops(pat, text, repl=rb"[\1]" if "(" in pat else b"#")
+
+
+def _corpus(config, size):
+    return corpora.make(config, size).numpy()
+
+
+def test_config1_findall_digits():
+    text = _corpus("c1", 4 << 20)
+    want = oracle.compile(r"\d+").findall(text)
+    got = mr.compile_regex(r"\d+").match_all(text).spans
+    assert np.array_equal(got, want)
+    assert len(got) > 200_000
+
+
+def test_config2_findall_alternation():
+    text = _corpus("c2", 8 << 20)
+    want = oracle.compile(r"(hello|world|foo)").findall(text)
+    got = mr.compile_regex(r"(hello|world|foo)").match_all(text).spans
+    assert np.array_equal(got, want)
+    assert len(got) > 100_000
+
+
+def test_config3_batch_search_email():
+    pat = corpora.CONFIGS["c3"]["pattern"]
+    n_lines = 200_000
+    text = _corpus("c3", n_lines)
+    orx = oracle.compile(pat)
+    want = np.full((n_lines, 2), -1, dtype=np.int64)
+    for i in range(n_lines):
+        r = orx.search(text[i * 128:(i + 1) * 128])
+        if r:
+            want[i] = r
+    grx = mr.compile_regex(pat)
+    got = grx.search_batch(text, doc_stride=128)
+    assert np.array_equal(got, want)
+    assert (want[:, 0] >= 0).sum() > 10_000
+    # ragged documents through explicit offsets
+    rng = np.random.default_rng(3)
+    cuts = np.unique(np.concatenate([[0, text.size], rng.integers(0, text.size, 5000)]))
+    got2 = grx.search_batch(text, doc_offsets=cuts)
+    for k in rng.integers(0, cuts.size - 1, 400):
+        r = orx.search(text[cuts[k]:cuts[k + 1]])
+        assert tuple(got2[k]) == (r if r else (-1, -1))
+
+
+def test_config4_sub_phone_numbers():
+    cfg = corpora.CONFIGS["c4"]
+    text = _corpus("c4", 4 << 20)
+    want = oracle.compile(cfg["pattern"]).sub(cfg["repl"].encode(), text)
+    got = mr.compile_regex(cfg["pattern"]).sub(cfg["repl"], text)
+    assert got == want
+    assert len(got) > len(text)
+
+
+def test_config5_split_csv():
+    text = _corpus("c5", 4 << 20)
+    wd, wo = oracle.compile(r"\s*,\s*").split_raw(text)
+    gd, go = mr.compile_regex(r"\s*,\s*").split_raw(text)
+    assert np.array_equal(go, wo)
+    assert gd == wd
+    assert len(go) > 400_000
+
+
+def test_device_resident_text_and_results():
+    text = corpora.make("c2", 2 << 20)
+    dev = text.cuda()
+    t = mr.Text.from_tensor(dev)
+    rx = mr.compile_regex(r"(hello|world|foo)")
+    ds = rx.match_all_device(t)
+    want = oracle.compile(r"(hello|world|foo)").findall(text.numpy())
+    assert ds.n == len(want)
+    assert np.array_equal(ds.to_numpy(), want)
+    ds.close()
+    # unaligned device pointer -> non-TMA staging path
+    t2 = mr.Text.from_tensor(dev[5:])
+    want2 = oracle.compile(r"(hello|world|foo)").findall(text.numpy()[5:])
+    assert np.array_equal(rx.match_all(t2).spans, want2)
+
+
+def test_windowed_text_reports_only_core_keys():
+    text = corpora.make("c2", 1 << 20).numpy()
+    rx = mr.compile_regex(r"(hello|world|foo)")
+    want = oracle.compile(r"(hello|world|foo)").findall(text)
+    t = mr.Text(text)
+    lo, hi = 300_001, 700_003
+    t.set_window(lo, hi, 1000)
+    got = rx.match_all(t).spans
+    sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)] + 1000
+    assert np.array_equal(got, sel)
