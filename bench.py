@@ -1,0 +1,324 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the matching hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--config c2] [--impl reference]
+
+A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload
+is BASELINE.json configs[1]: findall("(hello|world|foo)") over a 1 GiB single-buffer corpus.
+With N>1 (torchrun, one rank per GPU) every rank scans its own 1 GiB shard (+ halo) of an
+N GiB corpus and the ranks all-gather their match counts over NCCL (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = input GB/s with the corpus already resident in HBM
+(device time, CUDA events on the library stream, max over ranks); `e2e` = the same metric
+through the public API with host buffers (pinned), H2D and D2H copies inside the timed region.
+`--impl reference` times the CPU restatement of the reference's own path (oracle/) on the
+host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GiB = 1 << 30
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.path = tempfile.mktemp(prefix="clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock over the samples taken inside [t_begin, t_end] (wall clock); when the timed
+        region is shorter than the sampling period, the samples closest to it are used."""
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        try:
+            import datetime
+
+            rows = [r.strip().split(",") for r in open(self.path) if r.strip()]
+            rows = [r for r in rows if len(r) >= 9]
+            if t_begin is not None and rows:
+                def ts(r):
+                    return datetime.datetime.strptime(r[0].strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                inside = [r for r in rows if t_begin - 0.05 <= ts(r) <= t_end + 0.05]
+                if not inside:
+                    inside = sorted(rows, key=lambda r: abs(ts(r) - t_begin))[:2]
+                rows = inside
+            sm = sorted(float(r[1]) for r in rows)
+            if sm:
+                out["sm_mhz"] = sm[len(sm) // 2]
+                out["sm_max_mhz"] = float(rows[0][2])
+                out["samples"] = len(sm)
+                reasons = set()
+                names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+                for r in rows:
+                    for k, nm in enumerate(names):
+                        if r[5 + k].strip().lower().startswith("active"):
+                            reasons.add(nm)
+                out["reasons"] = sorted(reasons)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        return out
+
+
+CONFIG_DESCR = {
+    "c1": 'findall("\\\\d+") over synthetic ASCII text',
+    "c2": 'findall("(hello|world|foo)") over a single-buffer synthetic corpus',
+    "c3": "search(e-mail pattern) over synthetic 128-byte log lines (batch API)",
+    "c4": 'sub("(\\\\d{3})(\\\\d{3})(\\\\d{4})", "\\\\1-\\\\2-\\\\3") over synthetic phone-number text',
+    "c5": 'split("\\\\s*,\\\\s*") over a synthetic CSV corpus',
+}
+
+
+def default_size(config: str) -> int:
+    # largest single-GPU-friendly size per config (bytes; c3: lines)
+    return {"c1": 64 << 20, "c2": 1 << 30, "c3": 10_000_000, "c4": 4 << 30, "c5": 4 << 30}[config]
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    """CPU arm: the oracle port of the reference's path on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import numpy as np
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+
+    import oracle
+    from mojo_regex_b200 import corpora
+
+    cfg = corpora.CONFIGS[args.config]
+    cores = len(os.sched_getaffinity(0))
+    # bounded sample of the same corpus: 32 MiB per host thread, at most 1 GiB
+    if args.config == "c3":
+        sample_units = min(default_size("c3"), 250_000 * cores)
+        text = corpora.make("c3", sample_units).numpy()
+        sample_bytes = text.size
+    else:
+        sample_bytes = min(args.size or default_size(args.config), (32 << 20) * cores, GiB)
+        text = corpora.make(args.config, sample_bytes).numpy()
+    # one contiguous shard per thread, cut at a byte that no match can straddle
+    cut_byte = 10 if args.config in ("c3", "c5") else 32
+    bounds = [0]
+    for k in range(1, cores):
+        p = int(sample_bytes * k / cores)
+        while p < sample_bytes and text[p] != cut_byte:
+            p += 1
+        bounds.append(min(p + 1, sample_bytes))
+    bounds.append(sample_bytes)
+    shards = [text[bounds[i]:bounds[i + 1]] for i in range(cores) if bounds[i + 1] > bounds[i]]
+    regs = [oracle.compile(cfg["pattern"]) for _ in shards]
+
+    def work(i):
+        rx, sh = regs[i], shards[i]
+        if cfg["op"] == "findall":
+            return len(rx.findall(sh))
+        if cfg["op"] == "sub":
+            return len(rx.sub(cfg["repl"].encode(), sh))
+        if cfg["op"] == "split":
+            return len(rx.split_raw(sh)[1])
+        n = 0
+        for j in range(0, sh.size, 128):
+            n += rx.search(sh[j:j + 128]) is not None
+        return n
+
+    pool = ThreadPoolExecutor(max_workers=len(shards))
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        list(pool.map(work, range(len(shards))))
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    gbs = sample_bytes * len(times) / total / 1e9
+    line = {
+        "impl": "reference", "metric": "input GB/s scanned", "value": gbs, "unit": "GB/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": CONFIG_DESCR[args.config], "config": args.config, "bytes_per_step": int(sample_bytes)},
+        "cpu_baseline": {"value": gbs, "unit": "GB/s", "cores": len(shards), "kind": "port",
+                         "sample": "%d MiB prefix of the %s corpus, one contiguous shard per host thread; "
+                                   "restated reference (oracle/), not Mojo" % (sample_bytes >> 20, args.config)},
+        "e2e": {"value": gbs, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import mojo_regex_b200 as mr
+    from mojo_regex_b200 import corpora
+    from mojo_regex_b200 import distributed as mrd
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local_rank)
+    mr.init(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    cfg = corpora.CONFIGS[args.config]
+    size = args.size or default_size(args.config)
+    rx = mr.compile_regex(cfg["pattern"])
+    peak, peak_src = load_peaks()
+
+    # ---- this rank's shard, resident in HBM (weak scaling: `size` units per GPU) ----------------
+    shard = mrd.make_shard(args.config, size, rank, world, dev)
+    n_bytes = shard.core_bytes
+    lib_stream = torch.cuda.ExternalStream(mr.stream_handle(), device=dev)
+
+    def step_device():
+        return mrd.run_op_device(rx, cfg, shard)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        mr.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    clocks = ClockSampler(local_rank)
+    for _ in range(args.warmup):
+        res = step_device()
+        res.close()
+    mr.set_profiling(True)
+    sync_all()
+    launches0 = mr.launch_count()
+    t_begin = time.time()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    units = 0
+    alg_bytes = 0
+    with torch.cuda.stream(lib_stream):
+        ev0.record(lib_stream)
+        for _ in range(args.steps):
+            res = step_device()
+            kernel_ms.append(mr.last_kernel_ms())
+            units = res.units
+            alg_bytes = res.algorithmic_bytes
+            res.close()
+        ev1.record(lib_stream)
+    sync_all()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = mr.launch_count() - launches0
+    t_end = time.time()
+    clk = clocks.stop(t_begin, t_end)
+    mr.set_profiling(False)
+
+    # ---- end to end through the public API with host buffers ---------------------------------
+    host = torch.empty(shard.buffer.numel(), dtype=torch.uint8, pin_memory=True)
+    host.copy_(shard.buffer)
+    torch.cuda.synchronize()
+    e2e_steps = max(1, min(args.steps, 3))
+    mrd.run_op_host(rx, cfg, shard, host)  # warm the pools
+    sync_all()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(e2e_steps):
+        d2h = mrd.run_op_host(rx, cfg, shard, host)
+    mr.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks ----------------------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_bytes), float(units), float(launches)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max, k_ms = [float(x) for x in t.tolist()]
+    total_bytes, total_units, total_launches = [float(x) for x in tot.tolist()]
+
+    # ---- CPU baseline on rank 0 (bounded sample, single thread: the reference is single-threaded)
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        cpu = mrd.cpu_baseline(args.config, cfg, shard, seconds=10.0)
+
+    if rank == 0:
+        value = total_bytes * args.steps / (dev_ms_max / 1e3) / 1e9
+        achieved = alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
+        line = {
+            "metric": "input GB/s scanned", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+            "config": {"workload": CONFIG_DESCR[args.config], "config": args.config,
+                       "bytes_per_gpu": int(n_bytes), "units_per_step": int(total_units),
+                       "l2": "input (%.0f MiB per GPU) is larger than the 126 MB L2; no flush needed" % (n_bytes / 2**20)
+                       if n_bytes > 256 << 20 else "input re-read every step; smaller than 2x L2",
+                       "sharding": "byte ranges + halo, count all-gather over NCCL" if world > 1 else "single GPU"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": args.traffic,
+                         "kernel": res.kernel, "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "kernel_ms": k_ms, "peak_source": peak_src},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total_bytes * e2e_steps / (e2e_ms_max / 1e3) / 1e9, "unit": "GB/s",
+                    "h2d_bytes_per_step": int(shard.buffer.numel()), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(total_launches),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--size", type=int, default=0, help="bytes per GPU (c3: lines); default = BASELINE size")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--traffic", type=float, default=None,
+                    help="dram bytes per launch of the dominant kernel from an ncu --set full capture")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -386,13 +386,29 @@ class CompiledRegex:
         _check(lib.mrx_search_batch(self._h, t._h, optr, n_docs, doc_stride, OUT_HOST, out.ctypes.data))
         return out
 
+    def search_batch_device(self, text: "Text", out_ptr: int, n_docs: int, doc_stride: int = 0,
+                            doc_offsets_ptr: int = 0) -> None:
+        """Batch search with offsets / results already in HBM (out: n_docs x 2 int64)."""
+        _check(lib.mrx_search_batch(self._h, text._h, doc_offsets_ptr or None, n_docs, doc_stride, OUT_DEVICE, out_ptr))
+
+    def sub_device(self, repl, text: "Text", count: int = 0) -> "_DeviceBytes":
+        r = _as_bytes(repl)
+        ob = _Bytes()
+        _check(lib.mrx_sub(self._h, r, len(r), count, text._h, OUT_DEVICE, ctypes.byref(ob)))
+        return _DeviceBytes(ob)
+
+    def split_device(self, text: "Text", maxsplit: int = 0) -> "_DevicePieces":
+        pc = _Pieces()
+        _check(lib.mrx_split(self._h, text._h, maxsplit, OUT_DEVICE, ctypes.byref(pc)))
+        return _DevicePieces(pc)
+
     def sub(self, repl, text, count: int = 0) -> bytes:
         t, _ = _text_of(text)
         r = _as_bytes(repl)
         ob = _Bytes()
         _check(lib.mrx_sub(self._h, r, len(r), count, t._h, OUT_HOST, ctypes.byref(ob)))
         try:
-            return ctypes.string_at(ob.bytes, ob.n) if ob.n else b""
+            return np.ctypeslib.as_array(ob.bytes, shape=(ob.n,)).tobytes() if ob.n else b""
         finally:
             lib.mrx_bytes_free(ctypes.byref(ob))
 
@@ -402,7 +418,7 @@ class CompiledRegex:
         _check(lib.mrx_split(self._h, t._h, maxsplit, OUT_HOST, ctypes.byref(pc)))
         try:
             offs = np.ctypeslib.as_array(pc.offsets, shape=(pc.n + 1,)).copy()
-            data = ctypes.string_at(pc.bytes, int(offs[-1])) if offs[-1] else b""
+            data = np.ctypeslib.as_array(pc.bytes, shape=(int(offs[-1]),)).tobytes() if offs[-1] else b""
         finally:
             lib.mrx_pieces_free(ctypes.byref(pc))
         return data, offs
@@ -450,6 +466,69 @@ class _DeviceSpans:
         if self._sp is not None:
             lib.mrx_spans_free(ctypes.byref(self._sp))
             self._sp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DeviceBytes:
+    """sub() output left in HBM."""
+
+    def __init__(self, ob: _Bytes):
+        self._ob = ob
+        self.n = int(ob.n)
+        self.ptr = ctypes.cast(ob.bytes, ctypes.c_void_p).value or 0
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.n,), "typestr": "|u1", "data": (self.ptr, False), "version": 3, "strides": None}
+
+    def tensor(self):
+        import torch
+
+        if self.n == 0:
+            return torch.zeros((0,), dtype=torch.uint8, device="cuda")
+        return torch.as_tensor(self, device="cuda")
+
+    def close(self):
+        if self._ob is not None:
+            lib.mrx_bytes_free(ctypes.byref(self._ob))
+            self._ob = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _DevicePieces:
+    """split() output left in HBM: n pieces, bytes + (n+1) int64 offsets."""
+
+    def __init__(self, pc: _Pieces):
+        self._pc = pc
+        self.n = int(pc.n)
+        self.bytes_ptr = ctypes.cast(pc.bytes, ctypes.c_void_p).value or 0
+        self.offsets_ptr = ctypes.cast(pc.offsets, ctypes.c_void_p).value or 0
+
+    def offsets_tensor(self):
+        import torch
+
+        class _V:
+            pass
+
+        v = _V()
+        v.__cuda_array_interface__ = {"shape": (self.n + 1,), "typestr": "<i8", "data": (self.offsets_ptr, False),
+                                      "version": 3, "strides": None}
+        return torch.as_tensor(v, device="cuda")
+
+    def close(self):
+        if self._pc is not None:
+            lib.mrx_pieces_free(ctypes.byref(self._pc))
+            self._pc = None
 
     def __del__(self):
         try:

@@ -166,6 +166,18 @@ __device__ __forceinline__ int64_t doc_of(const ScanParams &prm, int64_t pos) {
   return lo;
 }
 
+// Layout of one CTA tile (kTile bytes): warp w owns the contiguous region [w*kWarpBytes, +kWarpBytes);
+// in step v its lane t reads the 16-byte vector at w*kWarpBytes + 512*v + 16*t (coalesced, conflict
+// free).  Candidate positions of a step are compacted into a per-warp queue (position order = lane
+// order), then processed 32 at a time with every lane busy; matches are appended, still in position
+// order, to a per-warp list that is flushed to HBM with coalesced 16-byte stores once the tile's
+// global rank is known (decoupled look-back).
+constexpr int kWarps = kThreads / 32;
+constexpr int kWarpBytes = kTile / kWarps;  // 4608
+constexpr int kSteps = kWarpBytes / 512;    // 9
+constexpr int kQCap = 512;                  // candidates of one step: at most 32 lanes x 16 bytes
+constexpr int kListCap = 224;               // buffered matches per warp and tile before the recompute path
+
 struct ScanShared {
   DevProg prog;
   alignas(16) uint8_t text[kTile + kHalo];
@@ -174,16 +186,16 @@ struct ScanShared {
   int tile;
   int overflow;
   unsigned long long base;
-  uint32_t slot_s[kThreads * kSlots];  // start relative to tile_start - kBack (fits 32 bits)
-  uint32_t slot_l[kThreads * kSlots];  // length
-  uint32_t slot_k[kThreads * kSlots];  // key - start (required-byte potentials)
+  uint16_t q_pos[kWarps][kQCap];      // candidate position relative to the tile start
+  uint32_t list_kb[kWarps][kListCap];  // (key - tile_start) | (key - start) << 16
+  uint32_t list_len[kWarps][kListCap];
 };
 
 template <int FILT>
 __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   ScanShared &sh = *reinterpret_cast<ScanShared *>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
   if (tid == 0) {
     sh.tile = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
@@ -209,120 +221,125 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
   at.lo = 0;
   at.n = prm.n;
 
-  const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
   const int64_t key_lo = prm.key_lo, key_hi = prm.key_hi;  // candidate positions in [key_lo, key_hi)
   const uint8_t *cand = sh.prog.cand;
+  uint16_t *q = sh.q_pos[warp];
+  const int warp_rel0 = warp * kWarpBytes;
 
-  int cnt = 0;
-  unsigned long long out_idx = 0;
+  int list_n = 0;                    // warp-uniform: matches found by this warp so far
+  unsigned long long out_idx = 0;    // pass 1: global index of this warp's next match
 
-  // PASS 0: count (+ buffer up to kSlots per thread);  PASS 1 (only after overflow): emit directly
+  // PASS 0: find matches, buffer them per warp;  PASS 1 (only after an overflow): recompute, emit directly
   for (int pass = 0; pass < 2; ++pass) {
-    if (pass == 1) cnt = 0;
-    int64_t cur_doc = -1, doc_lo = 0, doc_hi = 0;
-    for (int v = 0; v < kVecs; ++v) {
-      const int64_t pos0 = chunk0 + 16 * v;
-      if (pos0 >= key_hi || pos0 + 16 <= key_lo) continue;
-      const uint4 w = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
-      const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+    list_n = 0;
+    for (int v = 0; v < kSteps; ++v) {
+      const int rel0 = warp_rel0 + 512 * v + 16 * lane;
+      const int64_t pos0 = tile_start + rel0;
+      // ---- 1. candidate mask of this lane's 16 bytes
+      uint32_t m = 0;
+      if (pos0 < key_hi && pos0 + 16 > key_lo) {
+        const uint4 w = *reinterpret_cast<const uint4 *>(sh.text + rel0);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-      for (int wi = 0; wi < 4; ++wi) {
-        uint32_t f = filter_word<FILT>(ws[wi], prm.filt, cand);
-        while (f) {
-          const int b = (__ffs(f) - 1) >> 3;
-          f &= f - 1;
-          const int64_t pos = pos0 + 4 * wi + b;
-          if (pos < key_lo || pos >= key_hi) continue;
-          const uint8_t byte = (uint8_t)(ws[wi] >> (8 * b));
-          if (FILT != FILT_ALL && !cand[byte]) continue;
-          if (prm.out_kind == OUT_BATCH) {
-            if (pos >= doc_hi || pos < doc_lo) {
-              cur_doc = doc_of(prm, pos);
-              doc_lo = prm.doc_offsets ? prm.doc_offsets[cur_doc] : cur_doc * prm.doc_stride;
-              doc_hi = prm.doc_offsets ? prm.doc_offsets[cur_doc + 1] : min(doc_lo + prm.doc_stride, prm.n);
-            }
+        for (int wi = 0; wi < 4; ++wi) m |= flags_to_nibble(filter_word<FILT>(ws[wi], prm.filt, cand)) << (4 * wi);
+        if (pos0 + 16 > key_hi) m &= (1u << (int)(key_hi - pos0)) - 1u;
+        if (pos0 < key_lo) m &= ~((1u << (int)(key_lo - pos0)) - 1u);
+      }
+      if (prm.key_hi_inclusive_n && prm.n >= pos0 && prm.n < pos0 + 16) m |= 1u << (int)(prm.n - pos0);
+      // ---- 2. compaction: exclusive scan of popcounts, lanes append their positions in order
+      const int c = __popc(m);
+      int off = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, off, o);
+        if (lane >= o) off += t;
+      }
+      const int total = __shfl_sync(0xffffffffu, off, 31);
+      off -= c;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        q[off++] = (uint16_t)(rel0 + b);
+      }
+      __syncwarp();
+      // ---- 3. attempts, 32 candidates at a time
+      for (int j0 = 0; j0 < total; j0 += 32) {
+        const int j = j0 + lane;
+        bool hit = false;
+        Hit h;
+        h.key = h.s = h.e = 0;
+        int64_t doc_lo = 0;
+        int64_t cur_doc = 0;
+        if (j < total) {
+          const int64_t pos = tile_start + q[j];
+          bool ok = true;
+          if (FILT != FILT_ALL && pos < prm.n && !cand[sh.text[q[j]]]) ok = false;  // SWAR filter is a superset
+          if (ok && prm.out_kind == OUT_BATCH) {
+            cur_doc = doc_of(prm, pos);
+            doc_lo = prm.doc_offsets ? prm.doc_offsets[cur_doc] : cur_doc * prm.doc_stride;
             at.lo = doc_lo;
-            at.n = doc_hi;
+            at.n = prm.doc_offsets ? prm.doc_offsets[cur_doc + 1] : min(doc_lo + prm.doc_stride, prm.n);
           }
-          if (prm.dominated && pos > at.lo && pos > prm.search_start && cand[at.tv.at(pos - 1)]) continue;
-          Hit h;
-          if (!try_candidate(prm, at, pos, h)) continue;
-          if (prm.out_kind == OUT_FIRST) {
-            atomicMin(prm.best, (unsigned long long)h.key);
-          } else if (prm.out_kind == OUT_BATCH) {
-            const unsigned long long packed = ((unsigned long long)(h.s - doc_lo) << 32) | (unsigned long long)(h.e - doc_lo);
-            atomicMin(prm.doc_best + cur_doc, packed);
-          } else if (pass == 0) {
-            if (cnt < kSlots) {
-              const int64_t rel = h.s - (tile_start - kBackSlack);
-              sh.slot_s[tid * kSlots + cnt] = (uint32_t)rel;
-              sh.slot_l[tid * kSlots + cnt] = (uint32_t)(h.e - h.s);
-              sh.slot_k[tid * kSlots + cnt] = (uint32_t)(h.key - h.s);
-              if (rel < 0 || rel > 0xffffffffll || h.e - h.s > 0xffffffffll) sh.overflow = 1;
+          if (ok && prm.dominated && pos > at.lo && pos > prm.search_start && pos < prm.n && cand[at.tv.at(pos - 1)]) ok = false;
+          if (ok) hit = try_candidate(prm, at, pos, h);
+        }
+        if (prm.out_kind == OUT_FIRST) {
+          if (hit) atomicMin(prm.best, (unsigned long long)h.key);
+          continue;
+        }
+        if (prm.out_kind == OUT_BATCH) {
+          if (hit) atomicMin(prm.doc_best + cur_doc, ((unsigned long long)(h.s - doc_lo) << 32) | (unsigned long long)(h.e - doc_lo));
+          continue;
+        }
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        const int r = list_n + __popc(hm & ((1u << lane) - 1u));
+        if (hit) {
+          if (pass == 0) {
+            const int64_t back = h.key - h.s, len = h.e - h.s;
+            if (r < kListCap && back <= 0xffff && len <= 0xffffffffll) {
+              sh.list_kb[warp][r] = (uint32_t)(h.key - tile_start) | ((uint32_t)back << 16);
+              sh.list_len[warp][r] = (uint32_t)len;
             } else {
               sh.overflow = 1;
             }
-            ++cnt;
           } else {
-            const unsigned long long o = out_idx + cnt;
+            const unsigned long long o = out_idx + r;
             if (o < (unsigned long long)prm.cap) {
               st_span(prm.spans + 2 * o, h.s + prm.rebase, h.e + prm.rebase);
               if (prm.keys) prm.keys[o] = h.key + prm.rebase;
             }
-            ++cnt;
           }
         }
+        list_n += __popc(hm);
       }
+      __syncwarp();
     }
-    // position n itself (empty match at end of text, dfa.mojo:1970-1977 / :2118)
-    if (prm.try_at_end && prm.out_kind != OUT_BATCH && prm.n >= chunk0 && prm.n < chunk0 + kChunk &&
-        prm.n >= key_lo && prm.n <= key_hi && prm.key_hi_inclusive_n) {
-      Hit h;
-      if (try_candidate(prm, at, prm.n, h)) {
-        if (prm.out_kind == OUT_FIRST) {
-          atomicMin(prm.best, (unsigned long long)h.key);
-        } else if (pass == 0) {
-          if (cnt < kSlots) {
-            sh.slot_s[tid * kSlots + cnt] = (uint32_t)(h.s - (tile_start - kBackSlack));
-            sh.slot_l[tid * kSlots + cnt] = 0;
-            sh.slot_k[tid * kSlots + cnt] = 0;
-          } else {
-            sh.overflow = 1;
-          }
-          ++cnt;
-        } else {
-          const unsigned long long o = out_idx + cnt;
-          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, h.s + prm.rebase, h.e + prm.rebase);
-          ++cnt;
-        }
-      }
-    }
-    if (prm.out_kind != OUT_SPANS) return;
+    if (prm.out_kind != OUT_SPANS || pass == 1) return;
 
-    if (pass == 0) {
-      int total;
-      const int rank = block_exclusive_scan(cnt, sh.scan_ws, &total);
-      if (tid < 32) {
-        const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
-        if (tid == 0) {
-          sh.base = b;
-          if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+    // ---- tile epilogue: warp counts -> block scan -> look-back -> coalesced flush
+    int total;
+    const int rank = block_exclusive_scan(lane == 0 ? list_n : 0, sh.scan_ws, &total);
+    if (tid < 32) {
+      const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
+      if (tid == 0) {
+        sh.base = b;
+        if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+      }
+    }
+    __syncthreads();
+    out_idx = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0);
+    if (!sh.overflow) {
+      for (int i = lane; i < list_n; i += 32) {
+        const unsigned long long o = out_idx + i;
+        if (o < (unsigned long long)prm.cap) {
+          const uint32_t kb = sh.list_kb[warp][i];
+          const int64_t key = tile_start + (kb & 0xffffu);
+          const int64_t s = key - (kb >> 16);
+          st_span(prm.spans + 2 * o, s + prm.rebase, s + sh.list_len[warp][i] + prm.rebase);
+          if (prm.keys) prm.keys[o] = key + prm.rebase;
         }
       }
-      __syncthreads();
-      out_idx = sh.base + (unsigned long long)rank;
-      if (!sh.overflow) {
-        for (int i = 0; i < cnt; ++i) {
-          const unsigned long long o = out_idx + i;
-          if (o < (unsigned long long)prm.cap) {
-            const int64_t s = (int64_t)sh.slot_s[tid * kSlots + i] + (tile_start - kBackSlack);
-            const int64_t e = s + sh.slot_l[tid * kSlots + i];
-            st_span(prm.spans + 2 * o, s + prm.rebase, e + prm.rebase);
-            if (prm.keys) prm.keys[o] = s + sh.slot_k[tid * kSlots + i] + prm.rebase;
-          }
-        }
-        return;
-      }
+      return;
     }
   }
 }

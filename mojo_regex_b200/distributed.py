@@ -1,0 +1,237 @@
+"""Multi-GPU layer: one process per GPU, contiguous shards, counts gathered over NCCL.
+
+The matching path shards naturally: documents are independent (C3) and a
+single huge buffer splits into byte ranges that only need a small halo (C1/C2) or a cut at a
+byte no match can straddle (C4/C5).  No text crosses the links; the only exchange is one
+all-gather of a small per-rank record {n_units, out_bytes, first_span, last_span} from which
+every rank derives the global offset of its slice of the result ("global compaction") and,
+for class-run patterns, stitches a run that touches a shard boundary.
+
+`torch.distributed` (NCCL on GPUs, gloo in the CPU tests) is the plumbing; the math on the
+gathered records is plain Python so that the world_size-2 gloo tests exercise it.
+"""
+
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+from typing import List, Optional, Tuple
+
+import torch
+
+HALO = 1 << 16
+
+
+@dataclass
+class Shard:
+    config: str
+    buffer: torch.Tensor        # uint8 [left halo | core | right halo]
+    core_begin: int             # in buffer coordinates
+    core_end: int
+    global_offset: int          # position of buffer[0] in the whole corpus
+    rank: int
+    world: int
+    n_docs: int = 0
+    text: object = None         # mr.Text over `buffer` with the window set (GPU only)
+
+    @property
+    def core_bytes(self) -> int:
+        return self.core_end - self.core_begin
+
+
+def shard_bounds(total: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous, near-equal byte ranges."""
+    return [((total * r) // world, (total * (r + 1)) // world) for r in range(world)]
+
+
+def _core(config: str, size: int, rank: int, device):
+    from . import corpora
+
+    base = {"c1": 0xC1, "c2": 0xC2, "c3": 0xC3, "c4": 0xC4, "c5": 0xC5}[config]
+    return corpora.make(config, size, seed=base + 1000003 * rank, device=device)
+
+
+def make_shard(config: str, size: int, rank: int, world: int, device, with_text: bool = True) -> Shard:
+    """Weak-scaling shard: every rank owns `size` units (bytes; lines for c3) of a world*size corpus."""
+    core = _core(config, size, rank, device)
+    if config == "c3":
+        buf, cb, ce, goff, n_docs = core, 0, core.numel(), rank * core.numel(), size
+    elif config in ("c4", "c5") or world == 1:
+        # sub/split assemble per shard: end every shard on a byte no match can straddle
+        if world > 1:
+            core[-1] = 32 if config == "c4" else 10
+        buf, cb, ce, goff, n_docs = core, 0, core.numel(), rank * core.numel(), 0
+    else:
+        n = core.numel()
+        h = min(HALO, n)
+        left = _core(config, size, rank - 1, device)[n - h:] if rank > 0 else core[:0]
+        right = _core(config, size, rank + 1, device)[:h] if rank + 1 < world else core[:0]
+        buf = torch.cat([left, core, right])
+        cb, ce, goff, n_docs = left.numel(), left.numel() + n, rank * n - left.numel(), 0
+    sh = Shard(config, buf.contiguous(), cb, ce, goff, rank, world, n_docs)
+    if with_text and buf.is_cuda:
+        import mojo_regex_b200 as mr
+
+        sh.text = mr.Text.from_tensor(sh.buffer)
+        sh.text.set_window(cb, ce, goff)
+    return sh
+
+
+# ---- the exchanged record --------------------------------------------------------------------
+def gather_records(rec: List[int], device) -> List[List[int]]:
+    """All-gather one small int64 record per rank (the only collective on the path)."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [list(rec)]
+    t = torch.tensor(rec, dtype=torch.int64, device=device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+def global_offsets(counts: List[int]) -> List[int]:
+    """Exclusive prefix sum: where each rank's slice of the global result starts."""
+    out, acc = [], 0
+    for c in counts:
+        out.append(acc)
+        acc += c
+    return out
+
+
+def stitch_class_runs(records: List[List[int]]) -> Tuple[List[int], List[Optional[Tuple[int, int]]], List[bool]]:
+    """CLASS_RUNS shards report runs clipped to their core.  Record = [n, first_s, first_e, last_s,
+    last_e, core_begin_global, core_end_global].  A run that ends exactly on a shard's end and a run
+    that starts exactly on the next shard's begin are one run of the reference.
+
+    Returns (counts after stitching, replacement for each rank's last span or None, drop_first flags).
+    """
+    world = len(records)
+    counts = [r[0] for r in records]
+    new_last: List[Optional[Tuple[int, int]]] = [None] * world
+    drop_first = [False] * world
+    r = 0
+    while r < world:
+        n, fs, fe, ls, le, cb, ce = records[r]
+        if n == 0 or le != ce:
+            r += 1
+            continue
+        # run open at the end of rank r: extend through following ranks
+        end, k = le, r + 1
+        while k < world:
+            nk, fsk, fek, lsk, lek, cbk, cek = records[k]
+            if nk == 0 or fsk != cbk or fsk != end:
+                break
+            drop_first[k] = True
+            counts[k] -= 1
+            end = fek
+            if not (nk == 1 and fek == cek):
+                break
+            k += 1
+        if end != le:
+            new_last[r] = (ls, end)
+        # a rank whose single run was swallowed and continues is skipped by the loop above
+        r = max(k, r + 1) if end != le else r + 1
+    return counts, new_last, drop_first
+
+
+# ---- bench helpers (GPU) ---------------------------------------------------------------------------
+class OpResult:
+    def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, global_base: int = 0):
+        self.units = units
+        self.algorithmic_bytes = algorithmic_bytes
+        self.kernel = kernel
+        self.holder = holder
+        self.global_base = global_base
+
+    def close(self):
+        if self.holder is not None and hasattr(self.holder, "close"):
+            self.holder.close()
+        self.holder = None
+
+
+def run_op_device(rx, cfg, shard: Shard) -> OpResult:
+    """One step with the shard resident in HBM and the result left in HBM."""
+    n = shard.core_bytes
+    dev = shard.buffer.device
+    if cfg["op"] == "findall":
+        ds = rx.match_all_device(shard.text)
+        recs = gather_records([ds.n], dev) if shard.world > 1 else [[ds.n]]
+        base = global_offsets([r[0] for r in recs])[shard.rank]
+        mode = rx.info().findall_mode
+        return OpResult(ds.n, n + 16 * ds.n, "k_runs" if mode in (4, 8) else "k_scan", ds, base)
+    if cfg["op"] == "search_batch":
+        out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
+        rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128)
+        if shard.world > 1:
+            gather_records([shard.n_docs], dev)
+        return OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_scan", None)
+    if cfg["op"] == "sub":
+        ob = rx.sub_device(cfg["repl"], shard.text)
+        recs = gather_records([ob.n], dev) if shard.world > 1 else [[ob.n]]
+        base = global_offsets([r[0] for r in recs])[shard.rank]
+        return OpResult(n, n + ob.n, "k_runs", ob, base)
+    if cfg["op"] == "split":
+        pc = rx.split_device(shard.text)
+        total = int(pc.offsets_tensor()[-1].item())
+        recs = gather_records([pc.n, total], dev) if shard.world > 1 else [[pc.n, total]]
+        base = global_offsets([r[0] for r in recs])[shard.rank]
+        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan", pc, base)
+    raise ValueError(cfg["op"])
+
+
+def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
+    """One step through the public API from a pinned host buffer; returns bytes copied back."""
+    import mojo_regex_b200 as mr
+
+    t = mr.Text.from_pinned(host_pinned.data_ptr(), host_pinned.numel())
+    t.set_window(shard.core_begin, shard.core_end, shard.global_offset)
+    try:
+        if cfg["op"] == "findall":
+            ml = rx.match_all(t)
+            return int(ml.spans.nbytes)
+        if cfg["op"] == "search_batch":
+            out = rx.search_batch(t, doc_stride=128, n_docs=shard.n_docs)
+            return int(out.nbytes)
+        if cfg["op"] == "sub":
+            return len(rx.sub(cfg["repl"], t))
+        if cfg["op"] == "split":
+            data, offs = rx.split_raw(t)
+            return len(data) + int(offs.nbytes)
+    finally:
+        t.close()
+    raise ValueError(cfg["op"])
+
+
+def cpu_baseline(config: str, cfg, shard: Shard, seconds: float = 10.0) -> dict:
+    """The oracle (restated reference) on one host thread over a bounded sample of the shard."""
+    import oracle
+
+    rx = oracle.compile(cfg["pattern"])
+    core = shard.buffer[shard.core_begin:shard.core_end]
+
+    def run(sample):
+        t0 = time.perf_counter()
+        if cfg["op"] == "findall":
+            rx.findall(sample)
+        elif cfg["op"] == "sub":
+            rx.sub(cfg["repl"].encode(), sample)
+        elif cfg["op"] == "split":
+            rx.split_raw(sample)
+        else:
+            for j in range(0, sample.size, 128):
+                rx.search(sample[j:j + 128])
+        return time.perf_counter() - t0
+
+    probe_n = min(core.numel(), 8 << 20 if cfg["op"] != "search_batch" else 128 * 20000)
+    probe = core[:probe_n].cpu().numpy()
+    dt = max(run(probe), 1e-6)
+    rate = probe_n / dt
+    n = int(min(core.numel(), max(probe_n, rate * seconds / 3), 1 << 30))
+    if cfg["op"] == "search_batch":
+        n -= n % 128
+    sample = core[:n].cpu().numpy()
+    times = sorted(run(sample) for _ in range(3))
+    return {"value": n / times[1] / 1e9, "unit": "GB/s", "cores": 1, "kind": "port",
+            "sample": "%d MiB prefix of this rank's %s corpus, median of 3 passes, 1 thread; restated reference "
+                      "(oracle/), not Mojo" % (n >> 20, config)}

@@ -202,7 +202,7 @@ class OracleRegex:
             raise Unsupported("general capture-group sub uses the NFA engine (matcher.mojo:1783-1821)")
         if t.size == 0:
             return b""
-        res = ctypes.string_at(out_v.value, out_n.value)
+        res = np.ctypeslib.as_array(ctypes.cast(out_v, ctypes.POINTER(ctypes.c_uint8)), shape=(out_n.value,)).tobytes()
         self._lib.orx_free(out_v)
         return res
 
@@ -217,7 +217,8 @@ class OracleRegex:
             raise Unsupported("overlapping separator spans: text[prev_end:start] with prev_end > start "
                               "is undefined in the reference (SURVEY appendix B-3)")
         offs = np.ctypeslib.as_array(ctypes.cast(oo, ctypes.POINTER(ctypes.c_int64)), shape=(n + 1,)).copy()
-        data = ctypes.string_at(ob.value, int(offs[-1])) if offs[-1] > 0 else b""
+        data = (np.ctypeslib.as_array(ctypes.cast(ob, ctypes.POINTER(ctypes.c_uint8)), shape=(int(offs[-1]),)).tobytes()
+                if offs[-1] > 0 else b"")
         if ob.value:
             self._lib.orx_free(ob)
         self._lib.orx_free(oo)
