@@ -86,6 +86,7 @@ typedef struct {
   int32_t findall_direct;    /* 1 = potential matches are provably non-overlapping (no selection) */
   int32_t search_direct;
   int32_t fixed_sub_total_width, fixed_sub_num_groups, fixed_sub_concat;
+  int32_t findall_dense, search_dense; /* 1 = served by the dense literal-set automaton (k_dense)       */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */

@@ -67,7 +67,7 @@ class Info(ctypes.Structure):
         "n_states", "n_classes", "start_state", "has_start_anchor", "has_end_anchor", "is_pure_literal",
         "has_matcher", "scan_eligible", "required_byte", "is_wildcard_any", "is_exact_literal",
         "has_prefilter", "findall_mode", "search_mode", "findall_direct", "search_direct",
-        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat")]
+        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat", "findall_dense", "search_dense")]
 
 
 class DfaDesc(ctypes.Structure):

@@ -111,6 +111,7 @@ struct DevTmp {
 struct mrx_regex {
   Program prog;
   DevProg *d_findall = nullptr, *d_search = nullptr;
+  uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
   bool search_dominated = false;
 };
 
@@ -185,8 +186,26 @@ int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
   return MRX_OK;
 }
 
+int upload_dense(const DenseTable &dt, uint8_t **out) {
+  std::vector<uint8_t> raw(sizeof(DenseHdr) + dt.next.size() * 2, 0);
+  DenseHdr *h = reinterpret_cast<DenseHdr *>(raw.data());
+  h->n_states = dt.n_states; h->acc_base = dt.acc_base; h->max_len = dt.max_len;
+  h->table_bytes = (int32_t)(dt.next.size() * 2);
+  if (dt.out_len.size() > sizeof(h->out_len)) return fail(MRX_E_UNSUPPORTED, "too many literals for the dense table");
+  std::memcpy(h->out_len, dt.out_len.data(), dt.out_len.size());
+  std::memcpy(raw.data() + sizeof(DenseHdr), dt.next.data(), dt.next.size() * 2);
+  void *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, raw.size()));
+  CUDA_TRY(cudaMemcpyAsync(d, raw.data(), raw.size(), cudaMemcpyHostToDevice, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  *out = static_cast<uint8_t *>(d);
+  return MRX_OK;
+}
+
 int ensure_uploaded(mrx_regex *re) {
   if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
+  if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
+  if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
   if (!re->d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->d_findall); if (rc) return rc; }
   if (!re->d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->d_search); if (rc) return rc; }
   return MRX_OK;
@@ -236,6 +255,7 @@ struct ListJob {
   const DevProg *dprog;
   int64_t key_lo, key_hi;  // buffer coordinates
   int64_t rebase;
+  const uint8_t *dense = nullptr;  // DenseHdr + table when the plan has a dense automaton
 };
 
 int64_t n_tiles_for(int64_t origin, int64_t hi_inclusive) {
@@ -272,7 +292,16 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
     if (g.profiling) cudaEventRecord(g.ev0, g.stream);
-    launch_scan(p, (int)tiles, g.stream);
+    if (job.dense && !want_keys) {
+      DenseParams dp{};
+      dp.text = job.t->d; dp.n = n; dp.tile_origin = origin; dp.key_lo = job.key_lo; dp.key_hi = job.key_hi;
+      dp.dense = job.dense; dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
+      dp.n_tiles = (int)tiles; dp.spans = (int64_t *)spans; dp.cap = cap; dp.rebase = job.rebase;
+      dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = g.scalars;
+      launch_dense(dp, (int)tiles, g.stream);
+    } else {
+      launch_scan(p, (int)tiles, g.stream);
+    }
     if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
@@ -381,6 +410,7 @@ int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const Dev
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
   const int64_t n = (int64_t)t->n;
   ListJob job{re, t, &pl, dprog, (int64_t)t->core_begin, (int64_t)t->core_end, t->global_offset};
+  if (pl.dense.valid) job.dense = (&pl == &re->prog.findall) ? re->d_dense_findall : re->d_dense_search;
   switch (pl.mode) {
     case MRX_MODE_WILDCARD_ANY: {  // matcher.mojo:809-813
       void *p = nullptr;
@@ -433,6 +463,35 @@ int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t o
     return 0;
   }
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  if (pl.dense.valid && re->d_dense_search) {
+    if (pl.mode == MRX_MODE_EXACT_LITERAL && start >= n) return 0;  // matcher.mojo:773-774
+    if (start >= n) return 0;
+    const int64_t origin = start & ~15ll;
+    const int64_t tiles = n_tiles_for(origin, n - 1);
+    DenseParams dp{};
+    dp.text = t->d; dp.n = n; dp.key_lo = start; dp.key_hi = n; dp.dense = re->d_dense_search;
+    dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_FIRST; dp.best = g.scalars + 1;
+    launch_fill_u64(g.scalars + 1, 1, ~0ull, g.stream);
+    ++g.launches;
+    int64_t done = 0, win = 64;
+    while (done < tiles) {
+      const int64_t cnt = std::min(win, tiles - done);
+      dp.tile_origin = origin + done * kTile;
+      dp.n_tiles = (int)cnt;
+      launch_dense(dp, (int)cnt, g.stream);
+      ++g.launches;
+      CUDA_TRY(cudaGetLastError());
+      int rc = read_scalars(1, 1);
+      if (rc) return rc;
+      if (g.h_scalars[1] != ~0ull) break;
+      done += cnt;
+      win *= 4;
+    }
+    if (g.h_scalars[1] == ~0ull) return 0;
+    out[0] = (int64_t)(g.h_scalars[1] >> 8);
+    out[1] = out[0] + (int64_t)(g.h_scalars[1] & 0xff);
+    return 1;
+  }
   ScanParams p{};
   p.text = t->d; p.n = n; p.prog = re->d_search; p.filt = make_filter(pl); p.mode = pl.mode;
   p.search_start = start; p.rebase = 0;
@@ -674,6 +733,7 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
   o->findall_direct = p.findall.direct; o->search_direct = p.search.direct;
   o->fixed_sub_total_width = p.fixed_total_width; o->fixed_sub_num_groups = p.fixed_num_groups;
   o->fixed_sub_concat = p.fixed_concat;
+  o->findall_dense = p.findall.dense.valid; o->search_dense = p.search.dense.valid;
   return MRX_OK;
 }
 
@@ -681,6 +741,8 @@ void mrx_regex_free(mrx_regex *re) {
   if (!re) return;
   if (re->d_findall) cudaFree(re->d_findall);
   if (re->d_search) cudaFree(re->d_search);
+  if (re->d_dense_findall) cudaFree(re->d_dense_findall);
+  if (re->d_dense_search) cudaFree(re->d_dense_search);
   delete re;
 }
 

@@ -345,6 +345,195 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// dense literal-set scan: one table lookup per text byte (Aho-Corasick completion of the reference's
+// trie, see program.cpp:build_dense).  Thread t owns the 144 contiguous bytes [144 t, 144 t + 144) of
+// the tile (9 x LDS.128, conflict free), warms its state up on the max_len - 1 bytes before them and
+// then walks them; "a literal ends here" states are the highest-numbered ones, so the per-byte test is
+// one compare.  Matches are parked in a per-warp pool tagged (lane, sequence) and written to their
+// final, position-ordered slot once lane prefixes and the tile's global rank are known.
+constexpr int kPoolCap = 192;
+
+struct DenseShared {
+  alignas(16) uint8_t text[kTile + kHalo];
+  alignas(8) uint64_t bar;
+  int scan_ws[kThreads / 32 + 2];
+  int tile;
+  int overflow;
+  unsigned long long base;
+  uint32_t pool_a[kThreads / 32][kPoolCap];  // (end - tile_start) | len << 16
+  uint16_t pool_b[kThreads / 32][kPoolCap];  // lane | seq << 5
+  DenseHdr hdr;
+  alignas(16) uint16_t table[8];             // n_states * 256 entries follow
+};
+
+__global__ void __launch_bounds__(kThreads, 3) k_dense(const DenseParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    sh.tile = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
+    sh.overflow = 0;
+    sh.base = (prm.out_kind == OUT_FIRST) ? ld_volatile_u64(prm.best) : ~0ull;
+  }
+  {  // header + table -> shared memory (16-byte vectors)
+    const int total = (int)sizeof(DenseHdr) + prm.table_bytes;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.dense);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&sh.hdr);
+    for (int i = tid; i < total / 16; i += kThreads) d4[i] = s4[i];
+  }
+  __syncthreads();
+  const int tile = sh.tile;
+  const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
+  if (prm.out_kind == OUT_FIRST && (sh.base >> 8) < (unsigned long long)tile_start && sh.base != ~0ull) return;
+  int stage_bytes = kTile + kHalo;
+  if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
+  stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
+  TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
+
+  const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
+  const uint32_t acc_off = (uint32_t)sh.hdr.acc_base * 512u;
+  const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
+  // warm-up: the state after the max_len - 1 bytes preceding the chunk is exact
+  uint32_t s0 = 0;
+  {
+    int64_t q = chunk0 - (sh.hdr.max_len - 1);
+    if (q < 0) q = 0;
+    const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
+    for (; q < stop; ++q) s0 = *reinterpret_cast<const uint16_t *>(tbl + s0 + 2u * tv.at(q));
+  }
+
+  int mycnt = 0, pool_n = 0;
+  int lane_prefix = 0;
+  unsigned long long out_base = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    uint32_t s = s0;
+    mycnt = 0;
+    for (int v = 0; v < kVecs; ++v) {
+      const int64_t pos0 = chunk0 + 16 * v;
+      uint32_t m01 = 0, m23 = 0;  // up to four (byte index + 1, length) records, 16 bits each
+      int kk = 0;
+      const uint32_t s_in = s;
+      if (pos0 < prm.n) {
+        const uint4 w4 = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
+        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        const int lim = (pos0 + 16 <= prm.n) ? 16 : (int)(prm.n - pos0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if (i < lim) {
+            const uint32_t b = (ws[i >> 2] >> (8 * (i & 3))) & 0xffu;
+            s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * b);
+            if (s >= acc_off) {
+              const uint32_t len = sh.hdr.out_len[(s >> 9) - sh.hdr.acc_base];
+              const int64_t start = pos0 + i + 1 - (int64_t)len;
+              if (start >= prm.key_lo && start < prm.key_hi) {
+                const uint32_t rec = (uint32_t)(i + 1) | (len << 8);
+                if (kk == 0) m01 = rec;
+                else if (kk == 1) m01 |= rec << 16;
+                else if (kk == 2) m23 = rec;
+                else if (kk == 3) m23 |= rec << 16;
+                ++kk;
+              }
+            }
+          }
+        }
+      }
+      if (prm.out_kind == OUT_FIRST) {
+        if (kk > 0) {
+          const uint32_t len = (m01 >> 8) & 0xff;
+          const int64_t start = pos0 + (m01 & 0xff) - (int64_t)len;
+          atomicMin(prm.best, ((unsigned long long)start << 8) | len);
+        }
+        continue;
+      }
+      if (pass == 0) {
+        const unsigned b1 = __ballot_sync(0xffffffffu, kk >= 1);
+        if (b1) {
+          const unsigned b2 = __ballot_sync(0xffffffffu, kk >= 2), b3 = __ballot_sync(0xffffffffu, kk >= 3),
+                         b4 = __ballot_sync(0xffffffffu, kk >= 4);
+          const unsigned lt = (1u << lane) - 1u;
+          const int slot = pool_n + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt) + __popc(b4 & lt);
+          if (kk > 4) sh.overflow = 1;
+          const int nrec = kk < 4 ? kk : 4;
+          for (int r = 0; r < nrec; ++r) {
+            const uint32_t rec = ((r < 2 ? m01 : m23) >> (16 * (r & 1))) & 0xffffu;
+            if (slot + r < kPoolCap) {
+              sh.pool_a[warp][slot + r] = (uint32_t)(pos0 - tile_start + (rec & 0xff)) | ((rec >> 8) << 16);
+              sh.pool_b[warp][slot + r] = (uint16_t)(lane | ((mycnt + r) << 5));
+            } else {
+              sh.overflow = 1;
+            }
+          }
+          pool_n += __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4);
+        }
+        mycnt += kk;
+      } else if (kk > 0) {
+        // recompute path (only after a pool overflow): re-walk these 16 bytes and emit directly
+        uint32_t s2 = s_in;
+        const int lim = (pos0 + 16 <= prm.n) ? 16 : (int)(prm.n - pos0);
+        for (int i = 0; i < lim; ++i) {
+          s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[tid * kChunk + 16 * v + i]);
+          if (s2 >= acc_off) {
+            const uint32_t len = sh.hdr.out_len[(s2 >> 9) - sh.hdr.acc_base];
+            const int64_t start = pos0 + i + 1 - (int64_t)len;
+            if (start >= prm.key_lo && start < prm.key_hi) {
+              const unsigned long long o = out_base + lane_prefix + mycnt;
+              if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
+              ++mycnt;
+            }
+          }
+        }
+      }
+    }
+    if (prm.out_kind != OUT_SPANS || pass == 1) return;
+
+    // lane prefixes inside the warp, warp totals across the block, tile rank across the grid
+    int inc = mycnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    lane_prefix = inc - mycnt;
+    const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+    int total;
+    const int rank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
+    if (tid < 32) {
+      const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
+      if (tid == 0) {
+        sh.base = b;
+        if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+      }
+    }
+    __syncthreads();
+    out_base = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0);
+    if (!sh.overflow) {
+      const int rounds = (pool_n + 31) / 32;
+      for (int r = 0; r < rounds; ++r) {
+        const int i = r * 32 + lane;
+        uint32_t a = 0;
+        int owner = 0, seq = 0;
+        if (i < pool_n) {
+          a = sh.pool_a[warp][i];
+          const uint16_t bb = sh.pool_b[warp][i];
+          owner = bb & 31;
+          seq = bb >> 5;
+        }
+        const int pre = __shfl_sync(0xffffffffu, lane_prefix, owner);
+        if (i < pool_n) {
+          const unsigned long long o = out_base + pre + seq;
+          if (o < (unsigned long long)prm.cap) {
+            const int64_t end = tile_start + (a & 0xffffu);
+            const int64_t len = a >> 16;
+            st_span(prm.spans + 2 * o, end - len + prm.rebase, end + prm.rebase);
+          }
+        }
+      }
+      return;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // class runs
 struct RunsShared {
   DevProg prog;
@@ -916,6 +1105,15 @@ void launch_runs(const RunsParams &p, int grid, cudaStream_t st) {
     case FILT_ALL: launch_runs_t<FILT_ALL>(p, grid, st); break;
     default: launch_runs_t<FILT_LUT>(p, grid, st); break;
   }
+}
+void launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
+  const int smem = (int)sizeof(DenseShared) + p.table_bytes;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(k_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_smem = smem;
+  }
+  k_dense<<<grid, kThreads, smem, st>>>(p);
 }
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st) {

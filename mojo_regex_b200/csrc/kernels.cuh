@@ -64,6 +64,30 @@ struct RunsParams {
   unsigned long long *total;
 };
 
+// Dense literal-set automaton in HBM: header, then uint16 table[n_states * 256] (entry = next * 512).
+struct DenseHdr {
+  int32_t n_states, acc_base, max_len, table_bytes;
+  uint8_t out_len[64];
+};
+
+struct DenseParams {
+  const uint8_t *text;
+  int64_t n;
+  int64_t tile_origin;
+  int64_t key_lo, key_hi;  // match starts reported: [key_lo, key_hi)
+  const uint8_t *dense;    // DenseHdr + table
+  int32_t table_bytes;
+  int32_t out_kind;        // OUT_SPANS or OUT_FIRST
+  int32_t n_tiles;
+  int64_t *spans;
+  int64_t cap;
+  int64_t rebase;
+  unsigned long long *desc;
+  unsigned int *ticket;
+  unsigned long long *total;
+  unsigned long long *best;  // OUT_FIRST: min over (start << 8 | len)
+};
+
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };
 
 constexpr int kMaxTplSegs = 32;
@@ -77,6 +101,7 @@ struct SubTemplate {
 
 void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
+void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st);
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st);

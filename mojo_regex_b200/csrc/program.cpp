@@ -255,6 +255,126 @@ bool detect_uniform_run(const Program &p, const Plan &pl, int &mn, int &mx) {
   return true;
 }
 
+// Enumerate the (finite) language of the automaton from the start state.  Fails on cycles, on more than
+// `max_strings` strings, on strings longer than 255 bytes, and when an accepting state can still reach
+// another accept (then "longest accept" matters and the language is not prefix-free).
+bool enumerate_language(const Program &p, std::vector<std::string> &out, size_t max_strings) {
+  const int nc = p.n_classes;
+  std::vector<std::vector<int>> class_bytes(nc);
+  for (int b = 0; b < 256; ++b) class_bytes[p.byte_class[b]].push_back(b);
+  std::vector<uint8_t> on_path(p.n_states, 0);
+  std::string cur;
+  bool ok = true;
+  std::vector<uint8_t> reach = can_reach_accept(p);
+  // iterative DFS with explicit recursion via lambda
+  struct Rec {
+    const Program &p; std::vector<std::vector<int>> &cb; std::vector<uint8_t> &on; std::string &cur;
+    std::vector<std::string> &out; size_t maxs; bool &ok; std::vector<uint8_t> &reach;
+    void go(int s) {
+      if (!ok) return;
+      if (on[s]) { ok = false; return; }
+      if (p.accepting[s]) {
+        for (int c = 0; c < p.n_classes; ++c) {
+          int t = p.trans[(size_t)s * p.n_classes + c];
+          if (t != kDead && reach[t]) { ok = false; return; }
+        }
+        if (cur.empty() || cur.size() > 255 || out.size() >= maxs) { ok = false; return; }
+        out.push_back(cur);
+        return;
+      }
+      on[s] = 1;
+      for (int c = 0; c < p.n_classes && ok; ++c) {
+        int t = p.trans[(size_t)s * p.n_classes + c];
+        if (t == kDead || !reach[t]) continue;
+        for (int b : cb[c]) {
+          if (cur.size() >= 255) { ok = false; break; }
+          cur.push_back((char)b);
+          go(t);
+          cur.pop_back();
+          if (!ok) break;
+        }
+      }
+      on[s] = 0;
+    }
+  } rec{p, class_bytes, on_path, cur, out, max_strings, ok, reach};
+  rec.go(p.start_state);
+  return ok && !out.empty();
+}
+
+// Aho-Corasick completion.  Fails (returns false) when a literal occurs inside / as a suffix of a
+// proper prefix of another one (two occurrences could then overlap or nest) unless `allow_suffix` --
+// for a single literal nesting is impossible.
+bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
+  struct Node { int next[256]; int fail = 0; int out = 0; };
+  std::vector<Node> nodes(1);
+  std::fill(std::begin(nodes[0].next), std::end(nodes[0].next), -1);
+  size_t maxlen = 0;
+  for (const std::string &w : lits) {
+    int cur = 0;
+    for (unsigned char ch : w) {
+      if (nodes[cur].next[ch] < 0) {
+        nodes[cur].next[ch] = (int)nodes.size();
+        nodes.emplace_back();
+        std::fill(std::begin(nodes.back().next), std::end(nodes.back().next), -1);
+      }
+      cur = nodes[cur].next[ch];
+      if (nodes[cur].out) return false;  // another literal is a proper prefix of this one
+    }
+    if (nodes[cur].out) continue;  // duplicate
+    for (int b = 0; b < 256; ++b) if (nodes[cur].next[b] >= 0) return false;  // this literal is a prefix of another
+    nodes[cur].out = (int)w.size();
+    maxlen = std::max(maxlen, w.size());
+  }
+  if (nodes.size() > 120) return false;
+  // BFS: failure links + complete transitions
+  std::queue<int> q;
+  for (int b = 0; b < 256; ++b) {
+    int t = nodes[0].next[b];
+    if (t < 0) nodes[0].next[b] = 0; else { nodes[t].fail = 0; q.push(t); }
+  }
+  while (!q.empty()) {
+    int u = q.front(); q.pop();
+    if (nodes[nodes[u].fail].out) return false;  // a literal ends inside another: occurrences nest
+    for (int b = 0; b < 256; ++b) {
+      int t = nodes[u].next[b];
+      if (t < 0) nodes[u].next[b] = nodes[nodes[u].fail].next[b];
+      else { nodes[t].fail = nodes[nodes[u].fail].next[b]; q.push(t); }
+    }
+  }
+  // renumber: non-output states first
+  std::vector<int> id(nodes.size(), -1);
+  int k = 0;
+  for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) id[i] = k++;
+  dt.acc_base = k;
+  for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) id[i] = k++;
+  dt.n_states = (int)nodes.size();
+  dt.max_len = (int)maxlen;
+  dt.next.assign((size_t)dt.n_states * 256, 0);
+  dt.out_len.assign(dt.n_states - dt.acc_base, 0);
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    for (int b = 0; b < 256; ++b) dt.next[(size_t)id[i] * 256 + b] = (uint16_t)(id[nodes[i].next[b]] * 512);
+    if (nodes[i].out) dt.out_len[id[i] - dt.acc_base] = (uint8_t)nodes[i].out;
+  }
+  dt.valid = true;
+  return true;
+}
+
+void try_dense(const Program &p, Plan &pl) {
+  pl.dense = DenseTable();
+  if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) return;
+  std::vector<std::string> lits;
+  if (pl.mode == MRX_MODE_LITERAL || pl.mode == MRX_MODE_EXACT_LITERAL) {
+    if (pl.literal.empty() || pl.literal.size() > 255) return;
+    lits.push_back(pl.literal);
+  } else if (pl.mode == MRX_MODE_EVERY_POS && pl.direct && !pl.shortcut && !p.start_accepting()) {
+    if (!enumerate_language(p, lits, 64)) return;
+  } else {
+    return;
+  }
+  DenseTable dt;
+  if (build_dense(lits, dt) && dt.n_states <= 48) pl.dense = dt;
+}
+
 void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
   pl.shortcut = p.flag(BF_HAS_MATCHER) && p.n_states > 0 && (p.flag(BF_SCAN_ELIGIBLE) || p.start_accepting());
   if (first_class) {
@@ -368,6 +488,8 @@ void make_plans(Program &p) {
   } else {
     plan_attempt_mode(p, se, false);
   }
+  try_dense(p, fa);
+  try_dense(p, se);
 }
 
 }  // namespace

@@ -47,8 +47,20 @@ enum FilterKind : int32_t {
   FILT_ALL = 3,      // every position
 };
 
+// Dense search automaton for finite, prefix-free literal sets whose occurrences never overlap
+// (or a single literal): the Aho-Corasick completion of the reference's trie.  One table lookup per
+// text byte, no restarts, no divergence.  Entry [s][b] holds next_state * 512 (= byte offset of the
+// next row), states >= acc_base are "a literal ends here" states, out_len[s - acc_base] its length.
+struct DenseTable {
+  bool valid = false;
+  int32_t n_states = 0, acc_base = 0, max_len = 0;
+  std::vector<uint16_t> next;    // n_states * 256
+  std::vector<uint8_t> out_len;  // n_states - acc_base
+};
+
 struct Plan {
   int32_t mode = -1;  // MRX_MODE_*
+  DenseTable dense;
   bool direct = false;        // potential matches provably never overlap: emit them as final
   bool unsupported = false;   // plan cannot be executed faithfully
   std::string why;

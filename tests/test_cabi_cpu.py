@@ -111,6 +111,7 @@ def test_plans_for_the_five_configs():
     assert names[i.findall_mode] == "CLASS_RUNS" and i.findall_direct
     i = mr.CompiledRegex(r"(hello|world|foo)").info()
     assert names[i.findall_mode] == "EVERY_POS" and i.findall_direct and (i.n_states, i.n_classes) == (12, 9)
+    assert i.findall_dense and i.search_dense  # literal set -> dense Aho-Corasick table
     i = mr.CompiledRegex(r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}").info()
     assert names[i.search_mode] == "FIRST_CLASS" and names[i.findall_mode] == "REQUIRED_BYTE" and i.findall_direct
     i = mr.CompiledRegex(r"(\d{3})(\d{3})(\d{4})").info()
@@ -118,7 +119,9 @@ def test_plans_for_the_five_configs():
     i = mr.CompiledRegex(r"\s*,\s*").info()
     assert names[i.findall_mode] == "REQUIRED_BYTE" and i.findall_direct and i.required_byte == ord(",")
     # overlapping candidates -> selection pass needed
-    assert not mr.CompiledRegex("aa").info().findall_direct
+    assert not mr.CompiledRegex("aa").info().findall_direct and mr.CompiledRegex("aa").info().findall_dense
+    assert not mr.CompiledRegex("a|ab|abc").info().findall_dense  # not prefix-free: longest-accept matters
+    assert not mr.CompiledRegex(r"[a-z]+[0-9]+").info().findall_dense
     assert mr.CompiledRegex("ab").info().findall_direct
     assert not mr.CompiledRegex(r"[a-z]+[0-9]+").info().findall_direct
 
