@@ -366,7 +366,7 @@ struct DenseShared {
   alignas(16) uint16_t table[8];             // n_states * 256 entries follow
 };
 
-__global__ void __launch_bounds__(kThreads, 3) k_dense(const DenseParams prm) {
+__global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_dense(const DenseParams prm) {
   TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
 
   const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
-  const uint32_t acc_off = (uint32_t)sh.hdr.acc_base * 512u;
+  const int acc_base = sh.hdr.acc_base;
   const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
   // warm-up: the state after the max_len - 1 bytes preceding the chunk is exact
   uint32_t s0 = 0;
@@ -410,31 +410,51 @@ __global__ void __launch_bounds__(kThreads, 3) k_dense(const DenseParams prm) {
     mycnt = 0;
     for (int v = 0; v < kVecs; ++v) {
       const int64_t pos0 = chunk0 + 16 * v;
-      uint32_t m01 = 0, m23 = 0;  // up to four (byte index + 1, length) records, 16 bits each
-      int kk = 0;
-      const uint32_t s_in = s;
-      if (pos0 < prm.n) {
+      uint32_t pk[4] = {0, 0, 0, 0};
+      uint32_t hits = 0;
+      if (pos0 < prm.n) {  // (lanes past the end of the text still take part in the ballots below)
         const uint4 w4 = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
         const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-        const int lim = (pos0 + 16 <= prm.n) ? 16 : (int)(prm.n - pos0);
+        // ---- hot loop: 4 instructions per byte (extract, address, LDS, pack byte 1 of the new row offset)
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if (i < lim) {
-            const uint32_t b = (ws[i >> 2] >> (8 * (i & 3))) & 0xffu;
-            s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * b);
-            if (s >= acc_off) {
-              const uint32_t len = sh.hdr.out_len[(s >> 9) - sh.hdr.acc_base];
-              const int64_t start = pos0 + i + 1 - (int64_t)len;
-              if (start >= prm.key_lo && start < prm.key_hi) {
-                const uint32_t rec = (uint32_t)(i + 1) | (len << 8);
-                if (kk == 0) m01 = rec;
-                else if (kk == 1) m01 |= rec << 16;
-                else if (kk == 2) m23 = rec;
-                else if (kk == 3) m23 |= rec << 16;
-                ++kk;
-              }
-            }
+        for (int wi = 0; wi < 4; ++wi) {
+          uint32_t acc = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + k);
+            s = *reinterpret_cast<const uint16_t *>(tbl + (s + 2u * b));
+            acc = __byte_perm(acc, s, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
           }
+          pk[wi] = acc;
+        }
+        // bit 0 of every packed byte = "a literal ends after this byte"
+        const uint32_t any = (pk[0] | pk[1] | pk[2] | pk[3]) & kL;
+        if (any) {
+          hits = flags_to_nibble((pk[0] & kL) << 7) | flags_to_nibble((pk[1] & kL) << 7) << 4 |
+                 flags_to_nibble((pk[2] & kL) << 7) << 8 | flags_to_nibble((pk[3] & kL) << 7) << 12;
+          if (pos0 + 16 > prm.n) hits &= (1u << (int)(prm.n - pos0)) - 1u;
+        }
+      }
+      // ---- decode the (rare) hits of this lane
+      uint32_t m01 = 0, m23 = 0;  // up to four (byte index + 1, length) records, 16 bits each
+      int kk = 0;
+      while (hits) {
+        const int i = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const uint32_t row_hi = (pk[i >> 2] >> (8 * (i & 3))) & 0xffu;  // byte 1 of the row offset = 2 * row + 1
+        const uint32_t len = sh.hdr.out_len[(int)(row_hi >> 1) - acc_base];
+        const int64_t start = pos0 + i + 1 - (int64_t)len;
+        if (start >= prm.key_lo && start < prm.key_hi) {
+          const uint32_t rec = (uint32_t)(i + 1) | (len << 8);
+          if (kk == 0) m01 = rec;
+          else if (kk == 1) m01 |= rec << 16;
+          else if (kk == 2) m23 = rec;
+          else if (kk == 3) m23 |= rec << 16;
+          if (pass == 1 && prm.out_kind == OUT_SPANS) {  // recompute path: emit directly
+            const unsigned long long o = out_base + lane_prefix + mycnt + kk;
+            if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
+          }
+          ++kk;
         }
       }
       if (prm.out_kind == OUT_FIRST) {
@@ -465,24 +485,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_dense(const DenseParams prm) {
           }
           pool_n += __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4);
         }
-        mycnt += kk;
-      } else if (kk > 0) {
-        // recompute path (only after a pool overflow): re-walk these 16 bytes and emit directly
-        uint32_t s2 = s_in;
-        const int lim = (pos0 + 16 <= prm.n) ? 16 : (int)(prm.n - pos0);
-        for (int i = 0; i < lim; ++i) {
-          s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[tid * kChunk + 16 * v + i]);
-          if (s2 >= acc_off) {
-            const uint32_t len = sh.hdr.out_len[(s2 >> 9) - sh.hdr.acc_base];
-            const int64_t start = pos0 + i + 1 - (int64_t)len;
-            if (start >= prm.key_lo && start < prm.key_hi) {
-              const unsigned long long o = out_base + lane_prefix + mycnt;
-              if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
-              ++mycnt;
-            }
-          }
-        }
       }
+      mycnt += kk;
     }
     if (prm.out_kind != OUT_SPANS || pass == 1) return;
 

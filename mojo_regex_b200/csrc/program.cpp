@@ -341,19 +341,23 @@ bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
       else { nodes[t].fail = nodes[nodes[u].fail].next[b]; q.push(t); }
     }
   }
-  // renumber: non-output states first
-  std::vector<int> id(nodes.size(), -1);
-  int k = 0;
-  for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) id[i] = k++;
-  dt.acc_base = k;
-  for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) id[i] = k++;
+  // Row placement: row r of a non-output state sits at byte offset 512 r; output ("a literal ends
+  // here") states follow at 512 n_plain + 256 + 512 j, so bit 8 of a row offset is the accept flag and
+  // `row + 2 * byte` still addresses the right entry (entries are uint16, rows 512 bytes).
+  std::vector<int> off(nodes.size(), -1);
+  int n_plain = 0, n_out = 0;
+  for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) off[i] = 512 * n_plain++;
+  for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) off[i] = 512 * n_plain + 256 + 512 * n_out++;
+  const int table_bytes = 512 * n_plain + 256 + 512 * n_out + 256;  // multiple of 512
+  if (table_bytes > 65536 || n_out > 64) return false;
+  dt.acc_base = n_plain;
   dt.n_states = (int)nodes.size();
   dt.max_len = (int)maxlen;
-  dt.next.assign((size_t)dt.n_states * 256, 0);
-  dt.out_len.assign(dt.n_states - dt.acc_base, 0);
+  dt.next.assign((size_t)table_bytes / 2, 0);
+  dt.out_len.assign(n_out, 0);
   for (size_t i = 0; i < nodes.size(); ++i) {
-    for (int b = 0; b < 256; ++b) dt.next[(size_t)id[i] * 256 + b] = (uint16_t)(id[nodes[i].next[b]] * 512);
-    if (nodes[i].out) dt.out_len[id[i] - dt.acc_base] = (uint8_t)nodes[i].out;
+    for (int b = 0; b < 256; ++b) dt.next[(size_t)off[i] / 2 + b] = (uint16_t)off[nodes[i].next[b]];
+    if (nodes[i].out) dt.out_len[(off[i] - 512 * n_plain - 256) / 512] = (uint8_t)nodes[i].out;
   }
   dt.valid = true;
   return true;
@@ -372,7 +376,7 @@ void try_dense(const Program &p, Plan &pl) {
     return;
   }
   DenseTable dt;
-  if (build_dense(lits, dt) && dt.n_states <= 48) pl.dense = dt;
+  if (build_dense(lits, dt) && dt.next.size() * 2 <= 24576) pl.dense = dt;
 }
 
 void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {

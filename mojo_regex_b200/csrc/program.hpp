@@ -49,12 +49,14 @@ enum FilterKind : int32_t {
 
 // Dense search automaton for finite, prefix-free literal sets whose occurrences never overlap
 // (or a single literal): the Aho-Corasick completion of the reference's trie.  One table lookup per
-// text byte, no restarts, no divergence.  Entry [s][b] holds next_state * 512 (= byte offset of the
-// next row), states >= acc_base are "a literal ends here" states, out_len[s - acc_base] its length.
+// text byte, no restarts, no divergence.  The uint16 entry for (row, byte) sits at byte offset
+// row + 2 * byte and holds the byte offset of the next row.  Plain rows start at multiples of 512;
+// "a literal ends here" rows start at 512 * acc_base + 256 + 512 j, so bit 8 of a row offset is the
+// accept flag and out_len[j] the length of the literal that ends there.
 struct DenseTable {
   bool valid = false;
   int32_t n_states = 0, acc_base = 0, max_len = 0;
-  std::vector<uint16_t> next;    // n_states * 256
+  std::vector<uint16_t> next;    // whole table, table_bytes / 2 entries
   std::vector<uint8_t> out_len;  // n_states - acc_base
 };
 
