@@ -2,6 +2,7 @@
 // every byte of text is touched by the kernels in kernels.cu, never by host code.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -191,6 +192,12 @@ int upload_dense(const DenseTable &dt, uint8_t **out) {
   DenseHdr *h = reinterpret_cast<DenseHdr *>(raw.data());
   h->n_states = dt.n_states; h->acc_base = dt.acc_base; h->max_len = dt.max_len;
   h->table_bytes = (int32_t)(dt.next.size() * 2);
+  h->uniform_len = 0;
+  if (!dt.out_len.empty()) {
+    bool same = true;
+    for (uint8_t l : dt.out_len) same = same && l == dt.out_len[0];
+    if (same) h->uniform_len = dt.out_len[0];
+  }
   if (dt.out_len.size() > sizeof(h->out_len)) return fail(MRX_E_UNSUPPORTED, "too many literals for the dense table");
   std::memcpy(h->out_len, dt.out_len.data(), dt.out_len.size());
   std::memcpy(raw.data() + sizeof(DenseHdr), dt.next.data(), dt.next.size() * 2);
@@ -298,6 +305,7 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
       dp.dense = job.dense; dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
       dp.n_tiles = (int)tiles; dp.spans = (int64_t *)spans; dp.cap = cap; dp.rebase = job.rebase;
       dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = g.scalars;
+      dp.debug_no_lookback = getenv("MRX_DEBUG_NOLOOKBACK") != nullptr;
       launch_dense(dp, (int)tiles, g.stream);
     } else {
       launch_scan(p, (int)tiles, g.stream);

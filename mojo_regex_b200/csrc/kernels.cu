@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
 // then walks them; "a literal ends here" states are the highest-numbered ones, so the per-byte test is
 // one compare.  Matches are parked in a per-warp pool tagged (lane, sequence) and written to their
 // final, position-ordered slot once lane prefixes and the tile's global rank are known.
-constexpr int kPoolCap = 192;
+constexpr int kPriv = 14;  // private match records per thread and tile
 
 struct DenseShared {
   alignas(16) uint8_t text[kTile + kHalo];
@@ -360,16 +360,27 @@ struct DenseShared {
   int tile;
   int overflow;
   unsigned long long base;
-  uint32_t pool_a[kThreads / 32][kPoolCap];  // (end - tile_start) | len << 16
-  uint16_t pool_b[kThreads / 32][kPoolCap];  // lane | seq << 5
+  uint16_t priv[kThreads * kPriv];  // end - tile_start of every match of a thread, in position order
   DenseHdr hdr;
-  alignas(16) uint16_t table[8];             // n_states * 256 entries follow
+  alignas(16) uint16_t table[8];    // the whole table follows
 };
+
+// Length of the literal that ends at `end`: replay the automaton over the max_len bytes before it
+// (the state after max_len - 1 bytes of history is exact).  Only needed for literal sets of mixed
+// lengths; uniform sets carry the length in the header.
+__device__ __forceinline__ uint32_t dense_len_at(const DenseShared &sh, const uint8_t *tbl, const TextView &tv, int64_t end) {
+  if (sh.hdr.uniform_len) return (uint32_t)sh.hdr.uniform_len;
+  int64_t q = end - sh.hdr.max_len;
+  if (q < 0) q = 0;
+  uint32_t s = 0;
+  for (; q < end; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
+  return sh.hdr.out_len[(int)(s >> 9) - sh.hdr.acc_base];
+}
 
 __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) {
     sh.tile = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
     sh.overflow = 0;
@@ -384,155 +395,148 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   __syncthreads();
   const int tile = sh.tile;
   const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
-  if (prm.out_kind == OUT_FIRST && (sh.base >> 8) < (unsigned long long)tile_start && sh.base != ~0ull) return;
+  if (prm.out_kind == OUT_FIRST && sh.base != ~0ull && (sh.base >> 8) < (unsigned long long)tile_start) return;
   int stage_bytes = kTile + kHalo;
   if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
   stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
   TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
 
   const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
-  const int acc_base = sh.hdr.acc_base;
-  const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
+  const int chunk_rel = tid * kChunk;
+  // start positions are filtered against the key window only in tiles that touch its edges
+  const bool edge_tile = tile_start - 256 < prm.key_lo || tile_start + kTile > prm.key_hi;
+  const int valid = (int)min((int64_t)kTile, prm.n - tile_start);  // text bytes in this tile
   // warm-up: the state after the max_len - 1 bytes preceding the chunk is exact
-  uint32_t s0 = 0;
+  uint32_t s = 0;
   {
+    const int w = sh.hdr.max_len - 1;
+    if (tid > 0 && w <= kChunk) {
+      if (chunk_rel <= valid)
+        for (int r = chunk_rel - w; r < chunk_rel; ++r) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * sh.text[r]);
+    } else {
+      const int64_t chunk0 = tile_start + chunk_rel;
+      int64_t q = chunk0 - w;
+      if (q < 0) q = 0;
+      const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
+      for (; q < stop; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
+    }
+  }
+
+  uint16_t *mine = sh.priv + tid * kPriv;
+  int cnt = 0;
+#pragma unroll 1
+  for (int v3 = 0; v3 < kVecs / 3; ++v3) {
+    const int rel0 = chunk_rel + 48 * v3;
+    if (rel0 >= valid) break;
+    // ---- hot loop over 48 bytes: per byte PRMT (extract), IMAD (address), LDS.U16 (next row),
+    //      PRMT (pack byte 1 of the row offset; its bit 0 is the "a literal ends here" flag)
+    uint32_t pk[12];
+#pragma unroll
+    for (int vv = 0; vv < 3; ++vv) {
+      const uint4 w4 = *reinterpret_cast<const uint4 *>(sh.text + rel0 + 16 * vv);
+      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + k);
+          uint32_t addr;
+          asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(s));
+          s = *reinterpret_cast<const uint16_t *>(tbl + addr);
+          acc = __byte_perm(acc, s, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
+        }
+        pk[4 * vv + wi] = acc;
+      }
+    }
+    // ---- 48-bit hit mask (bit i = a literal ends after byte i of these 48)
+    uint32_t any = 0;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) any |= pk[j];
+    if ((any & kL) == 0) continue;
+    uint32_t mlo = 0, mhi = 0;  // bytes 0..31, 32..47
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mlo |= (((pk[j] & kL) * 0x10204080u) >> 28) << (4 * j);
+#pragma unroll
+    for (int j = 8; j < 12; ++j) mhi |= (((pk[j] & kL) * 0x10204080u) >> 28) << (4 * (j - 8));
+    if (rel0 + 48 > valid) {  // drop flags produced by bytes past the end of the text
+      const int live = valid - rel0;  // 1..47
+      if (live < 32) { mlo &= (1u << live) - 1u; mhi = 0; } else mhi &= (1u << (live - 32)) - 1u;
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint32_t f = half ? mhi : mlo;
+      while (f) {
+        const int i = __ffs(f) - 1;
+        f &= f - 1;
+        const int end_rel = rel0 + 32 * half + i + 1;
+        if (edge_tile || prm.out_kind == OUT_FIRST) {
+          const int64_t end = tile_start + end_rel;
+          const uint32_t len = dense_len_at(sh, tbl, tv, end);
+          const int64_t start = end - (int64_t)len;
+          if (start < prm.key_lo || start >= prm.key_hi) continue;
+          if (prm.out_kind == OUT_FIRST) {
+            atomicMin(prm.best, ((unsigned long long)start << 8) | len);
+            continue;
+          }
+        }
+        if (cnt < kPriv) mine[cnt] = (uint16_t)end_rel;
+        ++cnt;
+      }
+    }
+  }
+  if (prm.out_kind != OUT_SPANS) return;
+  if (cnt > kPriv) sh.overflow = 1;
+
+  // lane prefixes inside the warp, warp totals across the block, tile rank across the grid
+  int inc = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  const int lane_prefix = inc - cnt;
+  const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+  int total;
+  const int rank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
+  if (tid < 32) {
+    const unsigned long long b = prm.debug_no_lookback ? (unsigned long long)tile * 700ull
+                                                       : lookback_exclusive(prm.desc, tile, (unsigned long long)total);
+    if (tid == 0) {
+      sh.base = b;
+      if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+    }
+  }
+  __syncthreads();
+  unsigned long long o = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0) + lane_prefix;
+  if (!sh.overflow) {
+    for (int i = 0; i < cnt; ++i, ++o) {
+      if (o < (unsigned long long)prm.cap) {
+        const int64_t end = tile_start + mine[i];
+        const int64_t len = dense_len_at(sh, tbl, tv, end);
+        st_span(prm.spans + 2 * o, end - len + prm.rebase, end + prm.rebase);
+      }
+    }
+    return;
+  }
+  // recompute path (a thread found more than kPriv matches in its 144 bytes): walk again, emit directly
+  {
+    const int64_t chunk0 = tile_start + chunk_rel;
+    uint32_t s2 = 0;
     int64_t q = chunk0 - (sh.hdr.max_len - 1);
     if (q < 0) q = 0;
     const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
-    for (; q < stop; ++q) s0 = *reinterpret_cast<const uint16_t *>(tbl + s0 + 2u * tv.at(q));
-  }
-
-  int mycnt = 0, pool_n = 0;
-  int lane_prefix = 0;
-  unsigned long long out_base = 0;
-  for (int pass = 0; pass < 2; ++pass) {
-    uint32_t s = s0;
-    mycnt = 0;
-    for (int v = 0; v < kVecs; ++v) {
-      const int64_t pos0 = chunk0 + 16 * v;
-      uint32_t pk[4] = {0, 0, 0, 0};
-      uint32_t hits = 0;
-      if (pos0 < prm.n) {  // (lanes past the end of the text still take part in the ballots below)
-        const uint4 w4 = *reinterpret_cast<const uint4 *>(sh.text + tid * kChunk + 16 * v);
-        const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-        // ---- hot loop: 4 instructions per byte (extract, address, LDS, pack byte 1 of the new row offset)
-#pragma unroll
-        for (int wi = 0; wi < 4; ++wi) {
-          uint32_t acc = 0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + k);
-            s = *reinterpret_cast<const uint16_t *>(tbl + (s + 2u * b));
-            acc = __byte_perm(acc, s, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
-          }
-          pk[wi] = acc;
-        }
-        // bit 0 of every packed byte = "a literal ends after this byte"
-        const uint32_t any = (pk[0] | pk[1] | pk[2] | pk[3]) & kL;
-        if (any) {
-          hits = flags_to_nibble((pk[0] & kL) << 7) | flags_to_nibble((pk[1] & kL) << 7) << 4 |
-                 flags_to_nibble((pk[2] & kL) << 7) << 8 | flags_to_nibble((pk[3] & kL) << 7) << 12;
-          if (pos0 + 16 > prm.n) hits &= (1u << (int)(prm.n - pos0)) - 1u;
-        }
-      }
-      // ---- decode the (rare) hits of this lane
-      uint32_t m01 = 0, m23 = 0;  // up to four (byte index + 1, length) records, 16 bits each
-      int kk = 0;
-      while (hits) {
-        const int i = __ffs(hits) - 1;
-        hits &= hits - 1;
-        const uint32_t row_hi = (pk[i >> 2] >> (8 * (i & 3))) & 0xffu;  // byte 1 of the row offset = 2 * row + 1
-        const uint32_t len = sh.hdr.out_len[(int)(row_hi >> 1) - acc_base];
-        const int64_t start = pos0 + i + 1 - (int64_t)len;
+    for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * tv.at(q));
+    for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {
+      s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[chunk_rel + i]);
+      if (s2 & 0x100u) {
+        const uint32_t len = sh.hdr.out_len[(int)(s2 >> 9) - sh.hdr.acc_base];
+        const int64_t start = chunk0 + i + 1 - (int64_t)len;
         if (start >= prm.key_lo && start < prm.key_hi) {
-          const uint32_t rec = (uint32_t)(i + 1) | (len << 8);
-          if (kk == 0) m01 = rec;
-          else if (kk == 1) m01 |= rec << 16;
-          else if (kk == 2) m23 = rec;
-          else if (kk == 3) m23 |= rec << 16;
-          if (pass == 1 && prm.out_kind == OUT_SPANS) {  // recompute path: emit directly
-            const unsigned long long o = out_base + lane_prefix + mycnt + kk;
-            if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
-          }
-          ++kk;
+          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
+          ++o;
         }
       }
-      if (prm.out_kind == OUT_FIRST) {
-        if (kk > 0) {
-          const uint32_t len = (m01 >> 8) & 0xff;
-          const int64_t start = pos0 + (m01 & 0xff) - (int64_t)len;
-          atomicMin(prm.best, ((unsigned long long)start << 8) | len);
-        }
-        continue;
-      }
-      if (pass == 0) {
-        const unsigned b1 = __ballot_sync(0xffffffffu, kk >= 1);
-        if (b1) {
-          const unsigned b2 = __ballot_sync(0xffffffffu, kk >= 2), b3 = __ballot_sync(0xffffffffu, kk >= 3),
-                         b4 = __ballot_sync(0xffffffffu, kk >= 4);
-          const unsigned lt = (1u << lane) - 1u;
-          const int slot = pool_n + __popc(b1 & lt) + __popc(b2 & lt) + __popc(b3 & lt) + __popc(b4 & lt);
-          if (kk > 4) sh.overflow = 1;
-          const int nrec = kk < 4 ? kk : 4;
-          for (int r = 0; r < nrec; ++r) {
-            const uint32_t rec = ((r < 2 ? m01 : m23) >> (16 * (r & 1))) & 0xffffu;
-            if (slot + r < kPoolCap) {
-              sh.pool_a[warp][slot + r] = (uint32_t)(pos0 - tile_start + (rec & 0xff)) | ((rec >> 8) << 16);
-              sh.pool_b[warp][slot + r] = (uint16_t)(lane | ((mycnt + r) << 5));
-            } else {
-              sh.overflow = 1;
-            }
-          }
-          pool_n += __popc(b1) + __popc(b2) + __popc(b3) + __popc(b4);
-        }
-      }
-      mycnt += kk;
-    }
-    if (prm.out_kind != OUT_SPANS || pass == 1) return;
-
-    // lane prefixes inside the warp, warp totals across the block, tile rank across the grid
-    int inc = mycnt;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, inc, o);
-      if (lane >= o) inc += t;
-    }
-    lane_prefix = inc - mycnt;
-    const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
-    int total;
-    const int rank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
-    if (tid < 32) {
-      const unsigned long long b = lookback_exclusive(prm.desc, tile, (unsigned long long)total);
-      if (tid == 0) {
-        sh.base = b;
-        if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
-      }
-    }
-    __syncthreads();
-    out_base = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0);
-    if (!sh.overflow) {
-      const int rounds = (pool_n + 31) / 32;
-      for (int r = 0; r < rounds; ++r) {
-        const int i = r * 32 + lane;
-        uint32_t a = 0;
-        int owner = 0, seq = 0;
-        if (i < pool_n) {
-          a = sh.pool_a[warp][i];
-          const uint16_t bb = sh.pool_b[warp][i];
-          owner = bb & 31;
-          seq = bb >> 5;
-        }
-        const int pre = __shfl_sync(0xffffffffu, lane_prefix, owner);
-        if (i < pool_n) {
-          const unsigned long long o = out_base + pre + seq;
-          if (o < (unsigned long long)prm.cap) {
-            const int64_t end = tile_start + (a & 0xffffu);
-            const int64_t len = a >> 16;
-            st_span(prm.spans + 2 * o, end - len + prm.rebase, end + prm.rebase);
-          }
-        }
-      }
-      return;
     }
   }
 }

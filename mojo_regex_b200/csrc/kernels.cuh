@@ -67,6 +67,7 @@ struct RunsParams {
 // Dense literal-set automaton in HBM: header, then uint16 table[n_states * 256] (entry = next * 512).
 struct DenseHdr {
   int32_t n_states, acc_base, max_len, table_bytes;
+  int32_t uniform_len, pad0, pad1, pad2;  // > 0 when every literal has this length
   uint8_t out_len[64];
 };
 
@@ -86,6 +87,7 @@ struct DenseParams {
   unsigned int *ticket;
   unsigned long long *total;
   unsigned long long *best;  // OUT_FIRST: min over (start << 8 | len)
+  int32_t debug_no_lookback;  // measurement only (MRX_DEBUG_NOLOOKBACK=1): results are NOT ordered
 };
 
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };
