@@ -370,10 +370,16 @@ struct DenseShared {
 // lengths; uniform sets carry the length in the header.
 __device__ __forceinline__ uint32_t dense_len_at(const DenseShared &sh, const uint8_t *tbl, const TextView &tv, int64_t end) {
   if (sh.hdr.uniform_len) return (uint32_t)sh.hdr.uniform_len;
-  int64_t q = end - sh.hdr.max_len;
-  if (q < 0) q = 0;
+  const int ml = sh.hdr.max_len;
+  const int end_rel = (int)(end - tv.s_begin);
   uint32_t s = 0;
-  for (; q < end; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
+  if (end_rel >= ml) {  // the whole history window is in the staged tile
+    for (int r = end_rel - ml; r < end_rel; ++r) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.s[r]);
+  } else {
+    int64_t q = end - ml;
+    if (q < 0) q = 0;
+    for (; q < end; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
+  }
   return sh.hdr.out_len[(int)(s >> 9) - sh.hdr.acc_base];
 }
 
@@ -510,12 +516,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   __syncthreads();
   unsigned long long o = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0) + lane_prefix;
   if (!sh.overflow) {
-    for (int i = 0; i < cnt; ++i, ++o) {
-      if (o < (unsigned long long)prm.cap) {
-        const int64_t end = tile_start + mine[i];
-        const int64_t len = dense_len_at(sh, tbl, tv, end);
-        st_span(prm.spans + 2 * o, end - len + prm.rebase, end + prm.rebase);
-      }
+    const int64_t tbase = tile_start + prm.rebase;
+    int64_t *dst = prm.spans + 2 * o;
+    const int room = o < (unsigned long long)prm.cap ? (int)min((unsigned long long)cnt, (unsigned long long)prm.cap - o) : 0;
+    for (int i = 0; i < room; ++i, dst += 2) {
+      const int end_rel = mine[i];
+      const int64_t end = tbase + end_rel;
+      st_span(dst, end - (int64_t)dense_len_at(sh, tbl, tv, tile_start + end_rel), end);
     }
     return;
   }
