@@ -135,6 +135,38 @@ def stitch_class_runs(records: List[List[int]]) -> Tuple[List[int], List[Optiona
     return counts, new_last, drop_first
 
 
+def findall_record(spans, shard: Shard) -> List[int]:
+    """The per-rank record exchanged for findall: [n, first_s, first_e, last_s, last_e, core_begin_g, core_end_g]
+    (global coordinates; spans is an (n, 2) array-like of this rank's matches)."""
+    n = int(len(spans))
+    cb, ce = shard.global_offset + shard.core_begin, shard.global_offset + shard.core_end
+    if n == 0:
+        return [0, -1, -1, -1, -1, cb, ce]
+    return [n, int(spans[0][0]), int(spans[0][1]), int(spans[-1][0]), int(spans[-1][1]), cb, ce]
+
+
+def finish_findall(spans, records: List[List[int]], rank: int, class_runs: bool):
+    """Turn a rank's local span list into its slice of the global result.
+
+    Returns (spans_for_this_rank, global_index_of_first_span, total_matches).  For class-run patterns
+    runs were clipped at the shard edges and are stitched here; for every other mode shards already
+    report exactly the matches whose key lies in their core, so only offsets are needed."""
+    import numpy as np
+
+    spans = np.asarray(spans, dtype=np.int64).reshape(-1, 2)
+    if class_runs:
+        counts, new_last, drop_first = stitch_class_runs(records)
+        if drop_first[rank] and len(spans):
+            spans = spans[1:]
+        if new_last[rank] is not None and len(spans):
+            spans = spans.copy()
+            spans[-1] = new_last[rank]
+    else:
+        counts = [r[0] for r in records]
+    offs = global_offsets(counts)
+    return spans, offs[rank], sum(counts)
+
+
 # ---- bench helpers (GPU) ---------------------------------------------------------------------------
 class OpResult:
     def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, global_base: int = 0):
@@ -158,8 +190,9 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         ds = rx.match_all_device(shard.text)
         recs = gather_records([ds.n], dev) if shard.world > 1 else [[ds.n]]
         base = global_offsets([r[0] for r in recs])[shard.rank]
-        mode = rx.info().findall_mode
-        return OpResult(ds.n, n + 16 * ds.n, "k_runs" if mode in (4, 8) else "k_scan", ds, base)
+        info = rx.info()
+        kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
+        return OpResult(ds.n, n + 16 * ds.n, kernel, ds, base)
     if cfg["op"] == "search_batch":
         out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128)

@@ -253,3 +253,22 @@ def test_windowed_text_reports_only_core_keys():
     got = rx.match_all(t).spans
     sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)] + 1000
     assert np.array_equal(got, sel)
+
+
+@pytest.mark.parametrize("config,size", [("c2", 400_000), ("c1", 250_000)])
+def test_sharded_findall_emulated_ranks(config, size):
+    """The multi-GPU path with the ranks run one after another on this GPU: every rank scans its
+    windowed shard through the C ABI, records are merged exactly as the NCCL all-gather would."""
+    from mojo_regex_b200 import distributed as mrd
+
+    world = 3
+    pat = corpora.CONFIGS[config]["pattern"]
+    rx = mr.compile_regex(pat)
+    class_runs = config == "c1"
+    shards = [mrd.make_shard(config, size, r, world, "cuda") for r in range(world)]
+    locals_ = [rx.match_all(sh.text).spans for sh in shards]
+    records = [mrd.findall_record(locals_[r], shards[r]) for r in range(world)]
+    got = np.concatenate([mrd.finish_findall(locals_[r], records, r, class_runs)[0] for r in range(world)])
+    whole = torch.cat([mrd._core(config, size, r, "cuda") for r in range(world)]).cpu().numpy()
+    want = oracle.compile(pat).findall(whole)
+    assert np.array_equal(got, want)
