@@ -380,31 +380,44 @@ __device__ __forceinline__ uint32_t dense_len_at(const DenseShared &sh, const ui
     if (q < 0) q = 0;
     for (; q < end; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
   }
-  return sh.hdr.out_len[(int)(s >> 9) - sh.hdr.acc_base];
+  return sh.hdr.out_len[(int)((s - 4u) / 520u) - sh.hdr.acc_base];
 }
 
 __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31;
+  // One thread takes the ticket and issues both TMA bulk copies (automaton + text tile) on one mbarrier.
+  const bool text_aligned = (reinterpret_cast<uintptr_t>(prm.text + prm.tile_origin) & 15) == 0;
   if (tid == 0) {
-    sh.tile = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
+    const int t = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
+    sh.tile = t;
     sh.overflow = 0;
     sh.base = (prm.out_kind == OUT_FIRST) ? ld_volatile_u64(prm.best) : ~0ull;
-  }
-  {  // header + table -> shared memory (16-byte vectors)
-    const int total = (int)sizeof(DenseHdr) + prm.table_bytes;
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.dense);
-    uint4 *d4 = reinterpret_cast<uint4 *>(&sh.hdr);
-    for (int i = tid; i < total / 16; i += kThreads) d4[i] = s4[i];
+    mbar_init(&sh.bar, 1);
+    fence_proxy_async();
+    const int64_t ts = prm.tile_origin + (int64_t)t * kTile;
+    int64_t sb = prm.n - ts;
+    if (sb > kTile + kHalo) sb = kTile + kHalo;
+    if (sb < 0) sb = 0;
+    const uint32_t tab = (uint32_t)sizeof(DenseHdr) + (uint32_t)prm.table_bytes;
+    const uint32_t bulk = text_aligned ? ((uint32_t)sb & ~15u) : 0u;
+    mbar_expect_tx(&sh.bar, tab + bulk);
+    tma_bulk_g2s(&sh.hdr, prm.dense, tab, &sh.bar);
+    if (bulk) tma_bulk_g2s(sh.text, prm.text + ts, bulk, &sh.bar);
   }
   __syncthreads();
   const int tile = sh.tile;
   const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
-  if (prm.out_kind == OUT_FIRST && sh.base != ~0ull && (sh.base >> 8) < (unsigned long long)tile_start) return;
   int stage_bytes = kTile + kHalo;
   if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
-  stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
+  {
+    const int bulk = text_aligned ? (stage_bytes & ~15) : 0;
+    for (int i = bulk + tid; i < stage_bytes; i += kThreads) sh.text[i] = prm.text[tile_start + i];
+    mbar_wait(&sh.bar, 0);
+    if (bulk != stage_bytes) __syncthreads();
+  }
+  if (prm.out_kind == OUT_FIRST && sh.base != ~0ull && (sh.base >> 8) < (unsigned long long)tile_start) return;
   TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
 
   const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     const int rel0 = chunk_rel + 48 * v3;
     if (rel0 >= valid) break;
     // ---- hot loop over 48 bytes: per byte PRMT (extract), IMAD (address), LDS.U16 (next row),
-    //      PRMT (pack byte 1 of the row offset; its bit 0 is the "a literal ends here" flag)
+    //      PRMT (pack byte 0 of the row offset; its bit 2 is the "a literal ends here" flag)
     uint32_t pk[12];
 #pragma unroll
     for (int vv = 0; vv < 3; ++vv) {
@@ -450,7 +463,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
           uint32_t addr;
           asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(s));
           s = *reinterpret_cast<const uint16_t *>(tbl + addr);
-          acc = __byte_perm(acc, s, k == 0 ? 0x3215 : k == 1 ? 0x3250 : k == 2 ? 0x3510 : 0x5210);
+          acc = __byte_perm(acc, s, k == 0 ? 0x3214 : k == 1 ? 0x3240 : k == 2 ? 0x3410 : 0x4210);
         }
         pk[4 * vv + wi] = acc;
       }
@@ -459,12 +472,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     uint32_t any = 0;
 #pragma unroll
     for (int j = 0; j < 12; ++j) any |= pk[j];
-    if ((any & kL) == 0) continue;
+    constexpr uint32_t kF = 0x04040404u;  // bit 2 of every packed byte = accept flag
+    if ((any & kF) == 0) continue;
     uint32_t mlo = 0, mhi = 0;  // bytes 0..31, 32..47
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mlo |= (((pk[j] & kL) * 0x10204080u) >> 28) << (4 * j);
+    for (int j = 0; j < 8; ++j) mlo |= (((pk[j] & kF) * 0x04081020u) >> 28) << (4 * j);
 #pragma unroll
-    for (int j = 8; j < 12; ++j) mhi |= (((pk[j] & kL) * 0x10204080u) >> 28) << (4 * (j - 8));
+    for (int j = 8; j < 12; ++j) mhi |= (((pk[j] & kF) * 0x04081020u) >> 28) << (4 * (j - 8));
     if (rel0 + 48 > valid) {  // drop flags produced by bytes past the end of the text
       const int live = valid - rel0;  // 1..47
       if (live < 32) { mlo &= (1u << live) - 1u; mhi = 0; } else mhi &= (1u << (live - 32)) - 1u;
@@ -536,8 +550,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * tv.at(q));
     for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {
       s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[chunk_rel + i]);
-      if (s2 & 0x100u) {
-        const uint32_t len = sh.hdr.out_len[(int)(s2 >> 9) - sh.hdr.acc_base];
+      if (s2 & 4u) {
+        const uint32_t len = sh.hdr.out_len[(int)((s2 - 4u) / 520u) - sh.hdr.acc_base];
         const int64_t start = chunk0 + i + 1 - (int64_t)len;
         if (start >= prm.key_lo && start < prm.key_hi) {
           if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);

@@ -341,14 +341,16 @@ bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
       else { nodes[t].fail = nodes[nodes[u].fail].next[b]; q.push(t); }
     }
   }
-  // Row placement: row r of a non-output state sits at byte offset 512 r; output ("a literal ends
-  // here") states follow at 512 n_plain + 256 + 512 j, so bit 8 of a row offset is the accept flag and
-  // `row + 2 * byte` still addresses the right entry (entries are uint16, rows 512 bytes).
+  // Row placement.  Rows are 512 bytes of uint16 entries; the entry for (row, byte) sits at byte offset
+  // row + 2 * byte and holds the byte offset of the next row.  Rows are spaced 520 bytes apart so that
+  // different rows map the same text byte to different shared-memory banks (a 512-byte spacing makes
+  // every lane that is not in the root state collide with the root-state lanes).  Plain rows start at
+  // multiples of 8; "a literal ends here" rows start at 8k + 4, so bit 2 of a row offset is the accept flag.
   std::vector<int> off(nodes.size(), -1);
   int n_plain = 0, n_out = 0;
-  for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) off[i] = 512 * n_plain++;
-  for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) off[i] = 512 * n_plain + 256 + 512 * n_out++;
-  const int table_bytes = 512 * n_plain + 256 + 512 * n_out + 256;  // multiple of 512
+  for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) off[i] = 520 * n_plain++;
+  for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) off[i] = 520 * (n_plain + n_out++) + 4;
+  const int table_bytes = ((520 * (n_plain + n_out) + 8) + 15) & ~15;
   if (table_bytes > 65536 || n_out > 64) return false;
   dt.acc_base = n_plain;
   dt.n_states = (int)nodes.size();
@@ -357,7 +359,7 @@ bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
   dt.out_len.assign(n_out, 0);
   for (size_t i = 0; i < nodes.size(); ++i) {
     for (int b = 0; b < 256; ++b) dt.next[(size_t)off[i] / 2 + b] = (uint16_t)off[nodes[i].next[b]];
-    if (nodes[i].out) dt.out_len[(off[i] - 512 * n_plain - 256) / 512] = (uint8_t)nodes[i].out;
+    if (nodes[i].out) dt.out_len[(off[i] - 4) / 520 - n_plain] = (uint8_t)nodes[i].out;
   }
   dt.valid = true;
   return true;

@@ -50,9 +50,9 @@ enum FilterKind : int32_t {
 // Dense search automaton for finite, prefix-free literal sets whose occurrences never overlap
 // (or a single literal): the Aho-Corasick completion of the reference's trie.  One table lookup per
 // text byte, no restarts, no divergence.  The uint16 entry for (row, byte) sits at byte offset
-// row + 2 * byte and holds the byte offset of the next row.  Plain rows start at multiples of 512;
-// "a literal ends here" rows start at 512 * acc_base + 256 + 512 j, so bit 8 of a row offset is the
-// accept flag and out_len[j] the length of the literal that ends there.
+// row + 2 * byte and holds the byte offset of the next row.  Rows are spaced 520 bytes apart (bank
+// skew); plain rows start at multiples of 8, "a literal ends here" rows at 8k + 4, so bit 2 of a row
+// offset is the accept flag; out_len[j] is the length of the literal ending in accept row j.
 struct DenseTable {
   bool valid = false;
   int32_t n_states = 0, acc_base = 0, max_len = 0;

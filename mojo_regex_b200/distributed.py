@@ -90,6 +90,39 @@ def gather_records(rec: List[int], device) -> List[List[int]]:
     return [o.tolist() for o in out]
 
 
+class DeviceGather:
+    """All-gather of a small int64 record that never leaves the device: the record and the gathered
+    table live in preallocated HBM tensors and the exclusive scan is a device op, so a step pays one
+    NCCL launch and no host synchronisation."""
+
+    def __init__(self, width: int, device):
+        import torch.distributed as dist
+
+        self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.rec = torch.zeros(width, dtype=torch.int64, device=device)
+        self.table = torch.zeros((self.world, width), dtype=torch.int64, device=device)
+        self.host = torch.zeros(width, dtype=torch.int64).pin_memory() if torch.device(device).type == "cuda" else torch.zeros(width, dtype=torch.int64)
+
+    def gather(self, values: List[int]) -> torch.Tensor:
+        """-> (world, width) device tensor; row r is rank r's record."""
+        import torch.distributed as dist
+
+        for i, v in enumerate(values):
+            self.host[i] = int(v)
+        self.rec.copy_(self.host, non_blocking=True)
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.table, self.rec)
+        else:
+            self.table[0].copy_(self.rec)
+        return self.table
+
+    def base_offset(self, column: int = 0) -> torch.Tensor:
+        """Exclusive prefix of `column` at this rank (0-d device tensor)."""
+        col = self.table[:, column]
+        return torch.cumsum(col, 0)[self.rank] - col[self.rank]
+
+
 def global_offsets(counts: List[int]) -> List[int]:
     """Exclusive prefix sum: where each rank's slice of the global result starts."""
     out, acc = [], 0
@@ -168,8 +201,18 @@ def finish_findall(spans, records: List[List[int]], rank: int, class_runs: bool)
 
 
 # ---- bench helpers (GPU) ---------------------------------------------------------------------------
+_GATHERS = {}
+
+
+def _gather_for(width: int, device) -> DeviceGather:
+    key = (width, str(device))
+    if key not in _GATHERS:
+        _GATHERS[key] = DeviceGather(width, device)
+    return _GATHERS[key]
+
+
 class OpResult:
-    def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, global_base: int = 0):
+    def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, global_base=0):
         self.units = units
         self.algorithmic_bytes = algorithmic_bytes
         self.kernel = kernel
@@ -188,8 +231,11 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
     dev = shard.buffer.device
     if cfg["op"] == "findall":
         ds = rx.match_all_device(shard.text)
-        recs = gather_records([ds.n], dev) if shard.world > 1 else [[ds.n]]
-        base = global_offsets([r[0] for r in recs])[shard.rank]
+        base = 0
+        if shard.world > 1:
+            g = _gather_for(1, dev)
+            g.gather([ds.n])
+            base = g.base_offset()
         info = rx.info()
         kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
         return OpResult(ds.n, n + 16 * ds.n, kernel, ds, base)
@@ -197,18 +243,24 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128)
         if shard.world > 1:
-            gather_records([shard.n_docs], dev)
+            _gather_for(1, dev).gather([shard.n_docs])
         return OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_scan", None)
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
-        recs = gather_records([ob.n], dev) if shard.world > 1 else [[ob.n]]
-        base = global_offsets([r[0] for r in recs])[shard.rank]
+        base = 0
+        if shard.world > 1:
+            g = _gather_for(1, dev)
+            g.gather([ob.n])
+            base = g.base_offset()
         return OpResult(n, n + ob.n, "k_runs", ob, base)
     if cfg["op"] == "split":
         pc = rx.split_device(shard.text)
         total = int(pc.offsets_tensor()[-1].item())
-        recs = gather_records([pc.n, total], dev) if shard.world > 1 else [[pc.n, total]]
-        base = global_offsets([r[0] for r in recs])[shard.rank]
+        base = 0
+        if shard.world > 1:
+            g = _gather_for(2, dev)
+            g.gather([pc.n, total])
+            base = g.base_offset()
         return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan", pc, base)
     raise ValueError(cfg["op"])
 
