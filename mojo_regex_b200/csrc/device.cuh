@@ -143,6 +143,74 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
   return excl;
 }
 
+// The same look-back split in two, for kernels that publish a tile's aggregate as soon as it is known
+// and resolve its prefix later (one tile behind), so that nobody waits on a predecessor.
+__device__ __forceinline__ void lookback_publish(unsigned long long *desc, int tile, unsigned long long aggregate) {
+  st_volatile_u64(desc + tile, (tile == 0 ? kFlagPre : kFlagAgg) | aggregate);
+}
+// all 32 lanes of one warp; aggregate(tile) must already be published
+__device__ __forceinline__ unsigned long long lookback_resolve(unsigned long long *desc, int tile,
+                                                               unsigned long long aggregate) {
+  const int lane = threadIdx.x & 31;
+  if (tile == 0) return 0;
+  unsigned long long excl = 0;
+  int idx = tile - 1;
+  while (true) {
+    const int my = idx - lane;
+    unsigned long long d = kFlagPre;
+    if (my >= 0) {
+      do { d = ld_volatile_u64(desc + my); } while ((d >> 62) == 0);
+    }
+    const unsigned pre_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+    const int first_pre = pre_mask ? (__ffs(pre_mask) - 1) : 32;
+    unsigned long long v = (lane <= first_pre) ? (d & kValMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if (pre_mask) break;
+    idx -= 32;
+  }
+  if (lane == 0) st_volatile_u64(desc + tile, kFlagPre | (excl + aggregate));
+  return excl;
+}
+
+// Block-wide resolve (all kThreads threads): looks at 256 predecessors per round, so a whole wave of
+// concurrently running tiles is crossed in two or three rounds.  Needs every predecessor's AGGREGATE to
+// be published (true one tile behind); never waits for a predecessor's prefix.  `ws`: 2 * kThreads/32 + 2
+// unsigned long long of shared memory.  Returns the exclusive prefix to every thread.
+__device__ __forceinline__ unsigned long long lookback_resolve_block(unsigned long long *desc, int tile,
+                                                                     unsigned long long aggregate,
+                                                                     unsigned long long *ws) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int W = kThreads / 32;
+  unsigned long long excl = 0;
+  int idx = tile - 1;
+  while (idx >= 0) {
+    const int my = idx - tid;
+    unsigned long long d = kFlagPre;  // positions before tile 0 act as a zero prefix
+    if (my >= 0) {
+      do { d = ld_volatile_u64(desc + my); } while ((d >> 62) == 0);
+    }
+    const unsigned pre_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+    const int first_pre = pre_mask ? (__ffs(pre_mask) - 1) : 32;
+    unsigned long long v = (lane <= first_pre) ? (d & kValMask) : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) { ws[warp] = v; ws[W + warp] = pre_mask ? 1ull : 0ull; }
+    __syncthreads();
+    bool found = false;
+    for (int w = 0; w < W; ++w) {  // warps are ordered nearest-first
+      excl += ws[w];
+      if (ws[W + w]) { found = true; break; }
+    }
+    __syncthreads();
+    if (found) break;
+    idx -= kThreads;
+  }
+  if (tid == 0 && tile > 0) st_volatile_u64(desc + tile, kFlagPre | (excl + aggregate));
+  return excl;
+}
+
 // Block-wide exclusive scan of one int per thread (kThreads threads). Returns exclusive value;
 // *total gets the block sum.  `ws` needs kThreads/32 + 1 ints of shared memory.
 __device__ __forceinline__ int block_exclusive_scan(int v, int *ws, int *total) {

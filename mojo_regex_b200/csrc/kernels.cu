@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
 // then walks them; "a literal ends here" states are the highest-numbered ones, so the per-byte test is
 // one compare.  Matches are parked in a per-warp pool tagged (lane, sequence) and written to their
 // final, position-ordered slot once lane prefixes and the tile's global rank are known.
-constexpr int kPriv = 14;  // private match records per thread and tile
+constexpr int kPriv = 12;  // private match records per thread and tile
 
 struct DenseShared {
   alignas(16) uint8_t text[kTile + kHalo];
@@ -360,7 +360,10 @@ struct DenseShared {
   int tile;
   int overflow;
   unsigned long long base;
-  uint16_t priv[kThreads * kPriv];  // end - tile_start of every match of a thread, in position order
+  unsigned long long lb_ws[2 * (kThreads / 32) + 2];
+  // (end - chunk start) | len << 8 for every match of a thread, in position order; two generations so
+  // that a tile's matches can be flushed while the next tile is already being loaded
+  uint16_t priv[2][kThreads * kPriv];
   DenseHdr hdr;
   alignas(16) uint16_t table[8];    // the whole table follows
 };
@@ -383,43 +386,12 @@ __device__ __forceinline__ uint32_t dense_len_at(const DenseShared &sh, const ui
   return sh.hdr.out_len[(int)((s - 4u) / 520u) - sh.hdr.acc_base];
 }
 
-__global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
-  // One thread takes the ticket and issues both TMA bulk copies (automaton + text tile) on one mbarrier.
-  const bool text_aligned = (reinterpret_cast<uintptr_t>(prm.text + prm.tile_origin) & 15) == 0;
-  if (tid == 0) {
-    const int t = (prm.out_kind == OUT_SPANS) ? (int)atomicAdd(prm.ticket, 1u) : (int)blockIdx.x;
-    sh.tile = t;
-    sh.overflow = 0;
-    sh.base = (prm.out_kind == OUT_FIRST) ? ld_volatile_u64(prm.best) : ~0ull;
-    mbar_init(&sh.bar, 1);
-    fence_proxy_async();
-    const int64_t ts = prm.tile_origin + (int64_t)t * kTile;
-    int64_t sb = prm.n - ts;
-    if (sb > kTile + kHalo) sb = kTile + kHalo;
-    if (sb < 0) sb = 0;
-    const uint32_t tab = (uint32_t)sizeof(DenseHdr) + (uint32_t)prm.table_bytes;
-    const uint32_t bulk = text_aligned ? ((uint32_t)sb & ~15u) : 0u;
-    mbar_expect_tx(&sh.bar, tab + bulk);
-    tma_bulk_g2s(&sh.hdr, prm.dense, tab, &sh.bar);
-    if (bulk) tma_bulk_g2s(sh.text, prm.text + ts, bulk, &sh.bar);
-  }
-  __syncthreads();
-  const int tile = sh.tile;
-  const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
-  int stage_bytes = kTile + kHalo;
-  if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
-  {
-    const int bulk = text_aligned ? (stage_bytes & ~15) : 0;
-    for (int i = bulk + tid; i < stage_bytes; i += kThreads) sh.text[i] = prm.text[tile_start + i];
-    mbar_wait(&sh.bar, 0);
-    if (bulk != stage_bytes) __syncthreads();
-  }
-  if (prm.out_kind == OUT_FIRST && sh.base != ~0ull && (sh.base >> 8) < (unsigned long long)tile_start) return;
-  TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
-
+// Walk this thread's 144 bytes of the staged tile.  SPANS: tokens go to `mine`, returns the number of
+// matches (which may exceed kPriv: the caller then takes the recompute path).  FIRST: atomicMin on best.
+template <bool FIRST>
+__device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseShared &sh, const TextView &tv,
+                                                int64_t tile_start, uint16_t *mine) {
+  const int tid = threadIdx.x;
   const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
   const int chunk_rel = tid * kChunk;
   // start positions are filtered against the key window only in tiles that touch its edges
@@ -440,8 +412,6 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
       for (; q < stop; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
     }
   }
-
-  uint16_t *mine = sh.priv + tid * kPriv;
   int cnt = 0;
 #pragma unroll 1
   for (int v3 = 0; v3 < kVecs / 3; ++v3) {
@@ -489,77 +459,181 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
       while (f) {
         const int i = __ffs(f) - 1;
         f &= f - 1;
-        const int end_rel = rel0 + 32 * half + i + 1;
-        if (edge_tile || prm.out_kind == OUT_FIRST) {
-          const int64_t end = tile_start + end_rel;
+        const int end_loc = 48 * v3 + 32 * half + i + 1;  // 1..144, relative to the chunk start
+        if (edge_tile || FIRST) {
+          const int64_t end = tile_start + chunk_rel + end_loc;
           const uint32_t len = dense_len_at(sh, tbl, tv, end);
           const int64_t start = end - (int64_t)len;
           if (start < prm.key_lo || start >= prm.key_hi) continue;
-          if (prm.out_kind == OUT_FIRST) {
+          if (FIRST) {
             atomicMin(prm.best, ((unsigned long long)start << 8) | len);
             continue;
           }
         }
-        if (cnt < kPriv) mine[cnt] = (uint16_t)end_rel;
+        if (cnt < kPriv) mine[cnt] = (uint16_t)end_loc;
         ++cnt;
       }
     }
   }
-  if (prm.out_kind != OUT_SPANS) return;
-  if (cnt > kPriv) sh.overflow = 1;
-
-  // lane prefixes inside the warp, warp totals across the block, tile rank across the grid
-  int inc = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  const int lane_prefix = inc - cnt;
-  const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
-  int total;
-  const int rank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
-  if (tid < 32) {
-    const unsigned long long b = prm.debug_no_lookback ? (unsigned long long)tile * 700ull
-                                                       : lookback_exclusive(prm.desc, tile, (unsigned long long)total);
-    if (tid == 0) {
-      sh.base = b;
-      if (tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+  if (!FIRST) {  // resolve lengths while the text is still staged
+    const int m = cnt < kPriv ? cnt : kPriv;
+    for (int i = 0; i < m; ++i) {
+      const int end_loc = mine[i];
+      mine[i] = (uint16_t)(end_loc | (dense_len_at(sh, tbl, tv, tile_start + chunk_rel + end_loc) << 8));
     }
+  }
+  return cnt;
+}
+
+// search variant: one CTA per tile, no output list
+__global__ void __launch_bounds__(kThreads, 4) k_dense_first(const DenseParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x;
+  const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
+  if (tid == 0) sh.base = ld_volatile_u64(prm.best);
+  {
+    const int total = (int)sizeof(DenseHdr) + prm.table_bytes;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.dense);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&sh.hdr);
+    for (int i = tid; i < total / 16; i += kThreads) d4[i] = s4[i];
   }
   __syncthreads();
-  unsigned long long o = sh.base + (unsigned long long)__shfl_sync(0xffffffffu, rank, 0) + lane_prefix;
-  if (!sh.overflow) {
-    const int64_t tbase = tile_start + prm.rebase;
-    int64_t *dst = prm.spans + 2 * o;
-    const int room = o < (unsigned long long)prm.cap ? (int)min((unsigned long long)cnt, (unsigned long long)prm.cap - o) : 0;
-    for (int i = 0; i < room; ++i, dst += 2) {
-      const int end_rel = mine[i];
-      const int64_t end = tbase + end_rel;
-      st_span(dst, end - (int64_t)dense_len_at(sh, tbl, tv, tile_start + end_rel), end);
-    }
-    return;
+  if (sh.base != ~0ull && (sh.base >> 8) < (unsigned long long)tile_start) return;
+  int stage_bytes = kTile + kHalo;
+  if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
+  stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
+  TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
+  dense_scan_chunk<true>(prm, sh, tv, tile_start, nullptr);
+}
+
+// findall variant: persistent CTAs.  Per iteration: take a ticket, start the TMA of that tile, and while
+// it is in flight resolve the look-back of the PREVIOUS tile and flush its matches; then scan the new
+// tile and publish its aggregate.  Nobody ever waits for a predecessor that is still scanning.
+__global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  DenseShared &sh = *reinterpret_cast<DenseShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool text_aligned = (reinterpret_cast<uintptr_t>(prm.text + prm.tile_origin) & 15) == 0;
+  const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
+  if (tid == 0) {
+    mbar_init(&sh.bar, 1);
+    fence_proxy_async();
   }
-  // recompute path (a thread found more than kPriv matches in its 144 bytes): walk again, emit directly
-  {
-    const int64_t chunk0 = tile_start + chunk_rel;
-    uint32_t s2 = 0;
-    int64_t q = chunk0 - (sh.hdr.max_len - 1);
-    if (q < 0) q = 0;
-    const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
-    for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * tv.at(q));
-    for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {
-      s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[chunk_rel + i]);
-      if (s2 & 4u) {
-        const uint32_t len = sh.hdr.out_len[(int)((s2 - 4u) / 520u) - sh.hdr.acc_base];
-        const int64_t start = chunk0 + i + 1 - (int64_t)len;
-        if (start >= prm.key_lo && start < prm.key_hi) {
-          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
-          ++o;
+  {  // automaton -> shared memory, once per CTA
+    const int total = (int)sizeof(DenseHdr) + prm.table_bytes;
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.dense);
+    uint4 *d4 = reinterpret_cast<uint4 *>(&sh.hdr);
+    for (int i = tid; i < total / 16; i += kThreads) d4[i] = s4[i];
+  }
+  __syncthreads();
+
+  // state of the tile whose flush is pending
+  bool pending = false;
+  int p_tile = 0, p_cnt = 0, p_rank = 0, p_total = 0, p_gen = 0;
+  int64_t p_start = 0;
+
+  auto take_ticket_and_load = [&]() {  // thread 0 only
+    const int t = (int)atomicAdd(prm.ticket, 1u);
+    sh.tile = t;
+    if (t < prm.n_tiles) {
+      const int64_t ts = prm.tile_origin + (int64_t)t * kTile;
+      int64_t sb = prm.n - ts;
+      if (sb > kTile + kHalo) sb = kTile + kHalo;
+      if (sb < 0) sb = 0;
+      const uint32_t bulk = text_aligned ? ((uint32_t)sb & ~15u) : 0u;
+      mbar_expect_tx(&sh.bar, bulk);
+      if (bulk) tma_bulk_g2s(sh.text, prm.text + ts, bulk, &sh.bar);
+    }
+  };
+  auto flush_pending = [&]() {  // all threads; may wait for predecessors' aggregates (one scan behind)
+    const unsigned long long p_base = lookback_resolve_block(prm.desc, p_tile, (unsigned long long)p_total, sh.lb_ws);
+    if (tid == 0 && p_tile == prm.n_tiles - 1) *prm.total = p_base + (unsigned long long)p_total;
+    const unsigned long long o = p_base + (unsigned long long)p_rank;
+    const uint16_t *rec = sh.priv[p_gen] + tid * kPriv;
+    const int64_t cbase = p_start + (int64_t)tid * kChunk + prm.rebase;
+    const int room = o < (unsigned long long)prm.cap ? (int)min((unsigned long long)p_cnt, (unsigned long long)prm.cap - o) : 0;
+    int64_t *dst = prm.spans + 2 * o;
+    for (int i = 0; i < room; ++i, dst += 2) {
+      const uint32_t r = rec[i];
+      const int64_t end = cbase + (r & 0xffu);
+      st_span(dst, end - (int64_t)(r >> 8), end);
+    }
+    pending = false;
+  };
+
+  if (tid == 0) take_ticket_and_load();
+  __syncthreads();
+  int tile = sh.tile;
+  for (int it = 0; tile < prm.n_tiles; ++it) {
+    const int64_t tile_start = prm.tile_origin + (int64_t)tile * kTile;
+    int stage_bytes = kTile + kHalo;
+    if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
+    {
+      const int bulk = text_aligned ? (stage_bytes & ~15) : 0;
+      for (int i = bulk + tid; i < stage_bytes; i += kThreads) sh.text[i] = prm.text[tile_start + i];
+      mbar_wait(&sh.bar, (uint32_t)(it & 1));
+      if (bulk != stage_bytes) __syncthreads();
+    }
+    TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
+    const int gen = it & 1;
+    uint16_t *mine = sh.priv[gen] + tid * kPriv;
+    // ---- scan (never waits on other CTAs), ranks inside the tile, publish the aggregate
+    const int cnt = dense_scan_chunk<false>(prm, sh, tv, tile_start, mine);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int lane_prefix = inc - cnt;
+    const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+    const int overflow = __syncthreads_or(cnt > kPriv);
+    int total;
+    const int wrank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
+    const int rank = __shfl_sync(0xffffffffu, wrank, 0) + lane_prefix;
+    if (tid == 0) lookback_publish(prm.desc, tile, (unsigned long long)total);
+    if (overflow) {
+      // recompute path (some thread found more than kPriv matches in its 144 bytes): flush what is
+      // pending, resolve this tile now, walk the chunk again and emit directly while the text is staged
+      if (pending) flush_pending();
+      const unsigned long long b = lookback_resolve_block(prm.desc, tile, (unsigned long long)total, sh.lb_ws);
+      if (tid == 0 && tile == prm.n_tiles - 1) *prm.total = b + (unsigned long long)total;
+      unsigned long long o = b + (unsigned long long)rank;
+      const int chunk_rel = tid * kChunk;
+      const int valid = (int)min((int64_t)kTile, prm.n - tile_start);
+      const int64_t chunk0 = tile_start + chunk_rel;
+      uint32_t s2 = 0;
+      int64_t q = chunk0 - (sh.hdr.max_len - 1);
+      if (q < 0) q = 0;
+      const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
+      for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * tv.at(q));
+      for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {
+        s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[chunk_rel + i]);
+        if (s2 & 4u) {
+          const uint32_t len = sh.hdr.out_len[(int)((s2 - 4u) / 520u) - sh.hdr.acc_base];
+          const int64_t start = chunk0 + i + 1 - (int64_t)len;
+          if (start >= prm.key_lo && start < prm.key_hi) {
+            if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
+            ++o;
+          }
         }
       }
+      __syncthreads();
     }
+    // ---- the text buffer is free (block scan ended with a barrier): prefetch the next tile, and while it
+    //      is in flight flush the tile scanned one iteration ago
+    if (tid == 0) take_ticket_and_load();
+    if (pending) flush_pending();
+    if (!overflow) {
+      pending = true;
+      p_tile = tile; p_cnt = cnt; p_rank = rank; p_total = total; p_gen = gen; p_start = tile_start;
+    }
+    __syncthreads();
+    tile = sh.tile;
   }
+  if (pending) flush_pending();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1137,12 +1211,23 @@ void launch_runs(const RunsParams &p, int grid, cudaStream_t st) {
 }
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
   const int smem = (int)sizeof(DenseShared) + p.table_bytes;
-  static int attr_smem = 0;
+  static int attr_smem = 0, resident = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    cudaFuncSetAttribute(k_dense_first, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
+    int per_sm = 0, dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_dense, kThreads, smem);
+    resident = sms * (per_sm > 0 ? per_sm : 1);
   }
-  k_dense<<<grid, kThreads, smem, st>>>(p);
+  if (p.out_kind == OUT_FIRST) {
+    k_dense_first<<<grid, kThreads, smem, st>>>(p);
+  } else {
+    // persistent: every CTA must be resident (tiles are handed out by ticket, flushes are deferred)
+    k_dense<<<grid < resident ? grid : resident, kThreads, smem, st>>>(p);
+  }
 }
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st) {
