@@ -477,9 +477,22 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
   }
   if (!FIRST) {  // resolve lengths while the text is still staged
     const int m = cnt < kPriv ? cnt : kPriv;
+    const int ul = sh.hdr.uniform_len, ml = sh.hdr.max_len, ab = sh.hdr.acc_base;
     for (int i = 0; i < m; ++i) {
       const int end_loc = mine[i];
-      mine[i] = (uint16_t)(end_loc | (dense_len_at(sh, tbl, tv, tile_start + chunk_rel + end_loc) << 8));
+      uint32_t len = (uint32_t)ul;
+      if (ul == 0) {
+        const int end_rel = chunk_rel + end_loc;
+        if (end_rel >= ml) {  // replay the max_len bytes before the end from the staged tile
+          const uint8_t *p = sh.text + end_rel - ml;
+          uint32_t st = 0;
+          for (int k = 0; k < ml; ++k) st = *reinterpret_cast<const uint16_t *>(tbl + st + 2u * p[k]);
+          len = sh.hdr.out_len[(int)((st - 4u) / 520u) - ab];
+        } else {
+          len = dense_len_at(sh, tbl, tv, tile_start + end_rel);
+        }
+      }
+      mine[i] = (uint16_t)(end_loc | (len << 8));
     }
   }
   return cnt;
