@@ -245,6 +245,21 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
         if (pos0 + 16 > key_hi) m &= (1u << (int)(key_hi - pos0)) - 1u;
         if (pos0 < key_lo) m &= ~((1u << (int)(key_lo - pos0)) - 1u);
       }
+      // dominated candidates (search / batch search, exact filters only): a candidate whose predecessor
+      // byte is a candidate too can never be the leftmost match start -- drop it here, before the queue.
+      // Document starts and the search start itself are kept.
+      if (FILT != FILT_NEEDLES && prm.dominated && m && (prm.out_kind != OUT_BATCH || prm.doc_offsets == nullptr)) {
+        const uint32_t prev = (pos0 > 0 && cand[at.tv.at(pos0 - 1)]) ? 1u : 0u;
+        uint32_t keep = 0;
+        if (prm.out_kind == OUT_BATCH) {
+          const int64_t r = pos0 % prm.doc_stride;
+          const int64_t first = r == 0 ? 0 : prm.doc_stride - r;
+          for (int64_t b = first; b < 16; b += prm.doc_stride) keep |= 1u << (int)b;
+        } else if (prm.search_start >= pos0 && prm.search_start < pos0 + 16) {
+          keep = 1u << (int)(prm.search_start - pos0);
+        }
+        m &= ~((m << 1) | prev) | keep;
+      }
       if (prm.key_hi_inclusive_n && prm.n >= pos0 && prm.n < pos0 + 16) m |= 1u << (int)(prm.n - pos0);
       // ---- 2. compaction: exclusive scan of popcounts, lanes append their positions in order
       const int c = __popc(m);
