@@ -105,7 +105,23 @@ struct Attempt {
     int64_t last = (p->flags & DF_START_ACCEPTING) ? start : -1;
     int64_t q = start;
     const int nc = p->n_classes;
-    while (q < n) {
+    // fast path: walk inside the staged tile with 32-bit indices
+    if (start >= tv.s_begin && start < tv.s_end) {
+      const int lim = (int)((n < tv.s_end ? n : tv.s_end) - tv.s_begin);
+      int r = (int)(start - tv.s_begin), last_r = -1;
+      bool dead = false;
+      while (r < lim) {
+        const int nx = p->trans[state * nc + p->byte_class[tv.s[r]]];
+        if (nx == 0xFF) { dead = true; break; }
+        state = nx;
+        ++r;
+        if (p->accepting[state]) last_r = r;
+      }
+      if (last_r >= 0) last = tv.s_begin + last_r;
+      q = tv.s_begin + r;
+      if (dead) q = n;  // skip the slow continuation
+    }
+    while (q < n) {  // continuation past the staged window (rare) or start outside it
       const int nx = p->trans[state * nc + p->byte_class[tv.at(q)]];
       if (nx == 0xFF) break;
       state = nx;
