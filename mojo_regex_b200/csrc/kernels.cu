@@ -717,7 +717,19 @@ __device__ __forceinline__ uint32_t class_bits16(const uint4 &w, const Filter &f
 // 144 membership bits of one thread's chunk
 struct ChunkBits {
   uint32_t w[5];  // bit i of w[i/32] = byte i of the chunk (bits 144..159 of w[4] are zero)
-  __device__ __forceinline__ bool get(int i) const { return (w[i >> 5] >> (i & 31)) & 1u; }
+  // first position >= i whose bit equals `set` (kChunk if none); fully unrolled so w[] stays in registers
+  __device__ __forceinline__ int find(int i, bool set) const {
+    int res = kChunk;
+#pragma unroll
+    for (int k = 4; k >= 0; --k) {
+      uint32_t x = set ? w[k] : ~w[k];
+      if (k == 4) x &= 0xffffu;
+      if (32 * k + 31 < i) x = 0;
+      else if (32 * k < i) x &= ~0u << (i - 32 * k);
+      if (x) res = 32 * k + __ffs(x) - 1;
+    }
+    return res;
+  }
 };
 
 template <int FILT>
@@ -871,11 +883,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
     int i = 0;
     while (i < kChunk) {
       // find next run segment [i0, i1) inside the chunk
-      int i0 = i;
-      while (i0 < kChunk && !cb.get(i0)) ++i0;
+      const int i0 = cb.find(i, true);
       if (i0 >= kChunk) break;
-      int i1 = i0;
-      while (i1 < kChunk && cb.get(i1)) ++i1;
+      const int i1 = cb.find(i0, false);
       const long long d0 = (i0 == 0) ? carry : 0;  // distance of byte i0 from its run start
       int ext = 0;                                 // in-class bytes following the chunk, capped at K
       if (i1 == kChunk) {
