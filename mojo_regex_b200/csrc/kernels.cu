@@ -399,26 +399,12 @@ struct DenseShared {
   alignas(16) uint16_t table[8];    // the whole table follows
 };
 
-// Length of the literal that ends at `end`: replay the automaton over the max_len bytes before it
-// (the state after max_len - 1 bytes of history is exact).  Only needed for literal sets of mixed
-// lengths; uniform sets carry the length in the header.
-__device__ __forceinline__ uint32_t dense_len_at(const DenseShared &sh, const uint8_t *tbl, const TextView &tv, int64_t end) {
-  if (sh.hdr.uniform_len) return (uint32_t)sh.hdr.uniform_len;
-  const int ml = sh.hdr.max_len;
-  const int end_rel = (int)(end - tv.s_begin);
-  uint32_t s = 0;
-  if (end_rel >= ml) {  // the whole history window is in the staged tile
-    for (int r = end_rel - ml; r < end_rel; ++r) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.s[r]);
-  } else {
-    int64_t q = end - ml;
-    if (q < 0) q = 0;
-    for (; q < end; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
-  }
-  return sh.hdr.out_len[(int)((s - 4u) / 520u) - sh.hdr.acc_base];
-}
-
-// Walk this thread's 144 bytes of the staged tile.  SPANS: tokens go to `mine`, returns the number of
-// matches (which may exceed kPriv: the caller then takes the recompute path).  FIRST: atomicMin on best.
+// Walk this thread's 144 bytes of the staged tile.  SPANS: tokens (end - chunk start) | len << 8 go to
+// `mine`, returns the number of matches (which may exceed kPriv: the caller then takes the recompute
+// path).  FIRST: atomicMin on best.  The packed state bytes (low byte of the row offset = row mod 32 and
+// the accept flag) are written back over the consumed text, so the literal that ended at a hit is one
+// byte load + one LUT load away instead of a replay of max_len dependent lookups.  All threads of the
+// block must call this (it contains a barrier).
 template <bool FIRST>
 __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseShared &sh, const TextView &tv,
                                                 int64_t tile_start, uint16_t *mine) {
@@ -443,6 +429,7 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
       for (; q < stop; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
     }
   }
+  __syncthreads();  // every warm-up has read its predecessor's tail: the text may now be overwritten
   int cnt = 0;
 #pragma unroll 1
   for (int v3 = 0; v3 < kVecs / 3; ++v3) {
@@ -453,7 +440,8 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
     uint32_t pk[12];
 #pragma unroll
     for (int vv = 0; vv < 3; ++vv) {
-      const uint4 w4 = *reinterpret_cast<const uint4 *>(sh.text + rel0 + 16 * vv);
+      uint4 *slot = reinterpret_cast<uint4 *>(sh.text + rel0 + 16 * vv);
+      const uint4 w4 = *slot;
       const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
       for (int wi = 0; wi < 4; ++wi) {
@@ -468,6 +456,7 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
         }
         pk[4 * vv + wi] = acc;
       }
+      *slot = make_uint4(pk[4 * vv], pk[4 * vv + 1], pk[4 * vv + 2], pk[4 * vv + 3]);
     }
     // ---- 48-bit hit mask (bit i = a literal ends after byte i of these 48)
     uint32_t any = 0;
@@ -490,40 +479,19 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
       while (f) {
         const int i = __ffs(f) - 1;
         f &= f - 1;
-        const int end_loc = 48 * v3 + 32 * half + i + 1;  // 1..144, relative to the chunk start
+        const int off = 48 * v3 + 32 * half + i;   // byte of the chunk the literal ends on
+        const uint32_t len = sh.hdr.len_lut[sh.text[chunk_rel + off] >> 3];
         if (edge_tile || FIRST) {
-          const int64_t end = tile_start + chunk_rel + end_loc;
-          const uint32_t len = dense_len_at(sh, tbl, tv, end);
-          const int64_t start = end - (int64_t)len;
+          const int64_t start = tile_start + chunk_rel + off + 1 - (int64_t)len;
           if (start < prm.key_lo || start >= prm.key_hi) continue;
           if (FIRST) {
             atomicMin(prm.best, ((unsigned long long)start << 8) | len);
             continue;
           }
         }
-        if (cnt < kPriv) mine[cnt] = (uint16_t)end_loc;
+        if (cnt < kPriv) mine[cnt] = (uint16_t)((off + 1) | (len << 8));
         ++cnt;
       }
-    }
-  }
-  if (!FIRST) {  // resolve lengths while the text is still staged
-    const int m = cnt < kPriv ? cnt : kPriv;
-    const int ul = sh.hdr.uniform_len, ml = sh.hdr.max_len, ab = sh.hdr.acc_base;
-    for (int i = 0; i < m; ++i) {
-      const int end_loc = mine[i];
-      uint32_t len = (uint32_t)ul;
-      if (ul == 0) {
-        const int end_rel = chunk_rel + end_loc;
-        if (end_rel >= ml) {  // replay the max_len bytes before the end from the staged tile
-          const uint8_t *p = sh.text + end_rel - ml;
-          uint32_t st = 0;
-          for (int k = 0; k < ml; ++k) st = *reinterpret_cast<const uint16_t *>(tbl + st + 2u * p[k]);
-          len = sh.hdr.out_len[(int)((st - 4u) / 520u) - ab];
-        } else {
-          len = dense_len_at(sh, tbl, tv, tile_start + end_rel);
-        }
-      }
-      mine[i] = (uint16_t)(end_loc | (len << 8));
     }
   }
   return cnt;
@@ -652,9 +620,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
       int64_t q = chunk0 - (sh.hdr.max_len - 1);
       if (q < 0) q = 0;
       const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
-      for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * tv.at(q));
-      for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {
-        s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * sh.text[chunk_rel + i]);
+      for (; q < stop; ++q) s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * prm.text[q]);
+      for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {  // (the staged copy now holds state bytes)
+        s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * prm.text[chunk0 + i]);
         if (s2 & 4u) {
           const uint32_t len = sh.hdr.out_len[(int)((s2 - 4u) / 520u) - sh.hdr.acc_base];
           const int64_t start = chunk0 + i + 1 - (int64_t)len;

@@ -351,7 +351,7 @@ bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
   for (size_t i = 0; i < nodes.size(); ++i) if (!nodes[i].out) off[i] = 520 * n_plain++;
   for (size_t i = 0; i < nodes.size(); ++i) if (nodes[i].out) off[i] = 520 * (n_plain + n_out++) + 4;
   const int table_bytes = ((520 * (n_plain + n_out) + 8) + 15) & ~15;
-  if (table_bytes > 65536 || n_out > 64) return false;
+  if (table_bytes > 65536 || n_out > 32) return false;  // 32: DenseHdr::len_lut is indexed by row mod 32
   dt.acc_base = n_plain;
   dt.n_states = (int)nodes.size();
   dt.max_len = (int)maxlen;
