@@ -114,6 +114,9 @@ struct mrx_regex {
   DevProg *d_findall = nullptr, *d_search = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
   bool search_dominated = false;
+  // matches per key byte seen by the last list job of each plan (findall, search): sizes the span
+  // buffer of the next call so that the scan does not have to be repeated with a larger one
+  double density[2] = {0.0, 0.0};
 };
 
 struct mrx_text {
@@ -267,6 +270,24 @@ struct ListJob {
   const uint8_t *dense = nullptr;  // DenseHdr + table when the plan has a dense automaton
 };
 
+// Span-buffer capacity for a list job: a guess of one match per 8 bytes (at most 2^26 spans) the first
+// time, then 1/8 above the density the same plan saw last time.  A scan that overflows its buffer still
+// reports the exact count, and is repeated once with that.
+double &density_slot(const ListJob &job) {
+  mrx_regex *re = const_cast<mrx_regex *>(job.re);
+  return re->density[job.pl == &job.re->prog.findall ? 0 : 1];
+}
+int64_t initial_cap(const ListJob &job) {
+  const int64_t keys = job.key_hi - job.key_lo;
+  const double d = density_slot(job);
+  if (d > 0.0) return (int64_t)(d * 1.125 * (double)keys) + 4096;
+  return std::min<int64_t>(keys / 8 + 1024, 1ll << 26);
+}
+void note_density(const ListJob &job, int64_t total) {
+  const int64_t keys = job.key_hi - job.key_lo;
+  if (keys > 0) density_slot(job) = (double)total / (double)keys;
+}
+
 int64_t n_tiles_for(int64_t origin, int64_t hi_inclusive) {
   if (hi_inclusive < origin) return 0;
   return (hi_inclusive - origin) / kTile + 1;
@@ -282,7 +303,7 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
   out.n = 0;
   if (tiles <= 0) return MRX_OK;
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
-  int64_t cap = std::min<int64_t>((job.key_hi - job.key_lo) / 8 + 1024, 1ll << 26);
+  int64_t cap = initial_cap(job);
   DevTmp desc;
   int rc = desc.get(sizeof(unsigned long long) * tiles);
   if (rc) return rc;
@@ -318,6 +339,7 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     rc = read_scalars(0, 1);
     if (rc) { dev_release(spans); dev_release(keys); return rc; }
     const int64_t total = (int64_t)g.h_scalars[0];
+    note_density(job, total);
     if (total <= cap) {
       out.spans = (int64_t *)spans;
       out.n = total;
@@ -354,7 +376,7 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     g.launches += 2;
     d_carry = carry.as<long long>();
   }
-  int64_t cap = std::min<int64_t>((job.key_hi - job.key_lo) / 8 + 1024, 1ll << 26);
+  int64_t cap = initial_cap(job);
   for (int attempt = 0; attempt < 3; ++attempt) {
     void *spans = nullptr;
     if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &spans))) return rc;
@@ -373,6 +395,7 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     CUDA_TRY(cudaGetLastError());
     if ((rc = read_scalars(0, 1))) { dev_release(spans); return rc; }
     const int64_t total = (int64_t)g.h_scalars[0];
+    note_density(job, total);
     if (total <= cap) { out.spans = (int64_t *)spans; out.n = total; return MRX_OK; }
     dev_release(spans);
     cap = total;
@@ -993,20 +1016,27 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   if ((rc = match_list(re, t, p.search, re->d_search, ms))) return bail(rc);
   int64_t M = ms.n;
   if (count > 0 && M > count) M = count;
-  DevTmp d_repl, d_offs, d_desc, d_bad;
+  DevTmp d_tpl, d_offs, d_desc, d_bad, d_tseg;
   struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
-  if ((rc = d_repl.get(repl_n + 16))) return bail(rc);
-  if (repl_n) CUDA_TRY(cudaMemcpyAsync(d_repl.p, repl, repl_n, cudaMemcpyHostToDevice, g.stream));
-  tpl.literal = d_repl.as<uint8_t>();
+  // flattened replacement: one int32 per output byte of the template (see k_assemble)
+  std::vector<int32_t> flat;
+  flat.reserve((size_t)repl_len);
+  for (int k = 0; k < tpl.n_segs; ++k)
+    for (int i = 0; i < tpl.len[k]; ++i)
+      flat.push_back(tpl.group_off[k] >= 0 ? tpl.group_off[k] + i : -1 - (int32_t)repl[tpl.lit_off[k] + i]);
+  if ((rc = d_tpl.get(sizeof(int32_t) * (flat.size() + 4)))) return bail(rc);
+  if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(d_tpl.p, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, g.stream));
   const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
+  const int64_t out_bound = n + M * (repl_len + 1) + 1;
   if ((rc = d_offs.get(sizeof(int64_t) * (M + 2)))) return bail(rc);
   if ((rc = d_desc.get(sizeof(unsigned long long) * seg_tiles))) return bail(rc);
   if ((rc = d_bad.get(16))) return bail(rc);
+  if ((rc = d_tseg.get(sizeof(int64_t) * (out_bound / kAsmTile + 2)))) return bail(rc);
   CUDA_TRY(cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long) * seg_tiles, g.stream));
   CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
   CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 16, g.stream));
   launch_seg_lengths(ms.spans, M, n, SEG_SUB, repl_len, d_desc.as<unsigned long long>(), g.ticket, d_offs.as<int64_t>(),
-                     d_bad.as<int>(), g.stream);
+                     d_bad.as<int>(), d_tseg.as<int64_t>(), g.stream);
   ++g.launches;
   CUDA_TRY(cudaGetLastError());
   int64_t total = 0;
@@ -1016,9 +1046,14 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   void *d_out = nullptr;
   if ((rc = dev_alloc((size_t)total + 16, &d_out))) return bail(rc);
   own->dev[0] = d_out;
-  launch_seg_repl(t->d, n, ms.spans, M, d_offs.as<int64_t>(), tpl, (uint8_t *)d_out, g.stream);
-  launch_seg_gaps(t->d, n, ms.spans, M, d_offs.as<int64_t>(), SEG_SUB, (uint8_t *)d_out, g.stream);
-  g.launches += (M > 0 ? 1 : 0) + 1;
+  {
+    AsmParams ap{};
+    ap.text = t->d; ap.n = n; ap.spans = ms.spans; ap.M = M; ap.offs = d_offs.as<int64_t>();
+    ap.tile_seg = d_tseg.as<int64_t>(); ap.n_tiles = (total + kAsmTile - 1) / kAsmTile; ap.mode = SEG_SUB;
+    ap.repl_len = repl_len; ap.tpl_src = d_tpl.as<int32_t>(); ap.total = total; ap.out = (uint8_t *)d_out;
+    launch_assemble(ap, g.stream);
+    g.launches += total > 0 ? 1 : 0;
+  }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)total;
   if (location == MRX_OUT_DEVICE) {
@@ -1056,18 +1091,19 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   OwnedOut *own = new OwnedOut();
   out->_owner = own;
   auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
-  DevTmp d_desc, d_bad;
+  DevTmp d_desc, d_bad, d_tseg;
   const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
   void *d_offs = nullptr;
   if ((rc = dev_alloc(sizeof(int64_t) * (M + 2), &d_offs))) return bail(rc);
   own->dev[1] = d_offs;
   if ((rc = d_desc.get(sizeof(unsigned long long) * seg_tiles))) return bail(rc);
   if ((rc = d_bad.get(16))) return bail(rc);
+  if ((rc = d_tseg.get(sizeof(int64_t) * (n / kAsmTile + 2)))) return bail(rc);
   CUDA_TRY(cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long) * seg_tiles, g.stream));
   CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
   CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 16, g.stream));
   launch_seg_lengths(ms.spans, M, n, SEG_SPLIT, 0, d_desc.as<unsigned long long>(), g.ticket, (int64_t *)d_offs,
-                     d_bad.as<int>(), g.stream);
+                     d_bad.as<int>(), d_tseg.as<int64_t>(), g.stream);
   ++g.launches;
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 8, (int64_t *)d_offs + (M + 1), 8, cudaMemcpyDeviceToHost, g.stream));
@@ -1080,8 +1116,14 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   void *d_bytes = nullptr;
   if ((rc = dev_alloc((size_t)total + 16, &d_bytes))) return bail(rc);
   own->dev[0] = d_bytes;
-  launch_seg_gaps(t->d, n, ms.spans, M, (int64_t *)d_offs, SEG_SPLIT, (uint8_t *)d_bytes, g.stream);
-  ++g.launches;
+  {
+    AsmParams ap{};
+    ap.text = t->d; ap.n = n; ap.spans = ms.spans; ap.M = M; ap.offs = (int64_t *)d_offs;
+    ap.tile_seg = d_tseg.as<int64_t>(); ap.n_tiles = (total + kAsmTile - 1) / kAsmTile; ap.mode = SEG_SPLIT;
+    ap.repl_len = 0; ap.tpl_src = nullptr; ap.total = total; ap.out = (uint8_t *)d_bytes;
+    launch_assemble(ap, g.stream);
+    g.launches += total > 0 ? 1 : 0;
+  }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)(M + 1);
   if (location == MRX_OUT_DEVICE) {

@@ -921,10 +921,41 @@ __global__ void k_tile_trailing(const uint8_t *text, int64_t n, int64_t tile_ori
 
 // carry[tile] = in-class bytes immediately before the tile start (sequential over tiles; n_tiles is
 // text/36 KB, so this is microseconds)
-__global__ void k_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  long long c = 0;
-  for (int t = 0; t < n_tiles; ++t) {
+// carry[t] = length of the class run that ends exactly at the start of tile t.  Segmented scan over
+// (all, trail) pairs with  (a1,l1) o (a2,l2) = (a1 & a2, a2 ? l1 + l2 : l2):  one block of 1024 threads,
+// every thread owns a contiguous slice of tiles (serial), slices are combined by a block scan.
+__global__ void __launch_bounds__(1024) k_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry) {
+  __shared__ long long s_len[1024];
+  __shared__ int s_all[1024];
+  const int tid = threadIdx.x;
+  const int per = (n_tiles + 1023) / 1024;
+  const int t0 = min(tid * per, n_tiles), t1 = min(t0 + per, n_tiles);
+  long long len = 0;
+  int a = 1;
+  for (int t = t0; t < t1; ++t) {
+    const int at = all[t];
+    len = at ? len + trail[t] : trail[t];
+    a &= at;
+  }
+  s_len[tid] = len;
+  s_all[tid] = a;
+  __syncthreads();
+  for (int o = 1; o < 1024; o <<= 1) {  // inclusive Hillis-Steele scan of the slice summaries
+    long long l2 = s_len[tid];
+    int a2 = s_all[tid];
+    if (tid >= o) {
+      const long long l1 = s_len[tid - o];
+      const int a1 = s_all[tid - o];
+      if (a2) l2 += l1;
+      a2 &= a1;
+    }
+    __syncthreads();
+    s_len[tid] = l2;
+    s_all[tid] = a2;
+    __syncthreads();
+  }
+  long long c = tid > 0 ? s_len[tid - 1] : 0;  // run length entering this thread's slice
+  for (int t = t0; t < t1; ++t) {
     carry[t] = c;
     c = all[t] ? c + trail[t] : trail[t];
   }
@@ -1105,7 +1136,7 @@ __device__ __forceinline__ int64_t seg_pos(const int64_t *spans, int64_t j, int 
 
 __global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
                               unsigned long long *desc, unsigned int *ticket, int64_t *offs /* M+2 */,
-                              int *bad, int n_tiles) {
+                              int *bad, int n_tiles, int64_t *tile_seg) {
   __shared__ int s_tile;
   __shared__ long long s_warp[kThreads / 32];
   __shared__ unsigned long long s_base;
@@ -1145,53 +1176,147 @@ __global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mo
     }
   }
   __syncthreads();
-  if (j <= M) offs[j] = (int64_t)(s_base + before + inc - len);
+  if (j <= M) {
+    const int64_t O = (int64_t)(s_base + before + inc - len);
+    offs[j] = O;
+    // segment that owns the first byte of every output tile it covers (k_assemble's search window)
+    if (tile_seg && len > 0)
+      for (int64_t t = (O + kAsmTile - 1) / kAsmTile; t * kAsmTile < O + len; ++t) tile_seg[t] = j;
+  }
 }
 
-// one thread per match: replacement bytes (and the zero-width extra byte)
-__global__ void k_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
-                           const SubTemplate tpl, uint8_t *out) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= M) return;
-  const int64_t s = spans[2 * j], e = spans[2 * j + 1];
-  const int64_t pos = seg_pos(spans, j, SEG_SUB);
-  int64_t o = offs[j] + (s - pos);
-  for (int k = 0; k < tpl.n_segs; ++k) {
-    if (tpl.group_off[k] >= 0) {
-      const uint8_t *src = text + s + tpl.group_off[k];
-      for (int i = 0; i < tpl.len[k]; ++i) out[o++] = src[i];
+// Output-stationary assembly: thread = 16 consecutive output bytes, one aligned STG.128 each (a warp
+// writes 512 contiguous bytes).  The segment holding the chunk's first byte is found by a binary search
+// over `offs`, restricted by `tile_seg` to the handful of segments that touch this CTA's output tile
+// (they stay in L1); the chunk is then filled byte by byte, walking segments: gap bytes come from the
+// text, replacement bytes from the flattened template (tpl_src[r] >= 0: text[match_start + tpl_src[r]],
+// < 0: the literal byte -1 - tpl_src[r]), then the extra byte of a zero-width match.  Text bytes are
+// read through a one-word cache (consecutive bytes of a gap share an aligned 32-bit load).
+struct SegCursor {
+  int64_t j, O, O_next, pos, s, gap;
+};
+// Segment records of one output tile, staged in shared memory by coalesced loads: output offset, search
+// position and match start of segment lo_seg + k, relative to the first segment's (32 bits each).
+struct AsmShared {
+  uint32_t O[kAsmSegCap + 1];
+  uint32_t pos[kAsmSegCap];
+  uint32_t s[kAsmSegCap];
+};
+__device__ __forceinline__ int64_t seg_pos_ldg(const AsmParams &p, int64_t j) {
+  if (j == 0) return 0;
+  const int64_t ps = __ldg(p.spans + 2 * (j - 1)), pe = __ldg(p.spans + 2 * (j - 1) + 1);
+  return (p.mode == SEG_SPLIT) ? pe : (pe == ps ? pe + 1 : pe);
+}
+template <bool FAST>
+__device__ __forceinline__ void seg_load(const AsmParams &p, const AsmShared &sh, int64_t lo_seg, int64_t O_base,
+                                         int64_t x_base, int64_t j, SegCursor &c) {
+  c.j = j;
+  if (FAST) {
+    const int k = (int)(j - lo_seg);
+    c.O = O_base + sh.O[k];
+    c.O_next = O_base + sh.O[k + 1];
+    c.pos = x_base + sh.pos[k];
+    c.s = x_base + sh.s[k];
+  } else {
+    c.O = __ldg(p.offs + j);
+    c.O_next = __ldg(p.offs + j + 1);
+    c.pos = seg_pos_ldg(p, j);
+    c.s = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
+  }
+  c.gap = c.s > c.pos ? c.s - c.pos : 0;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void assemble_tile(const AsmParams &p, const AsmShared &sh, int64_t tile, int64_t lo_seg,
+                                              int64_t hi_seg, int64_t O_base, int64_t x_base) {
+  uint32_t cw = 0;         // cached aligned text word (aligned in the address space: the text itself
+  uintptr_t cw_addr = 1;   // may start at any byte of a wrapped tensor); a word that holds a valid byte
+                           // never leaves that byte's 32-byte sector, so the over-read is harmless
+  auto rd = [&](int64_t x) -> uint32_t {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p.text + x);
+    const uintptr_t wa = a & ~(uintptr_t)3;
+    if (wa != cw_addr) {
+      cw = __ldg(reinterpret_cast<const uint32_t *>(wa));
+      cw_addr = wa;
+    }
+    return (cw >> (8 * (int)(a & 3))) & 0xffu;
+  };
+#pragma unroll 1
+  for (int r = 0; r < kAsmRounds; ++r) {
+    const int64_t o0 = tile * kAsmTile + ((int64_t)r * kThreads + threadIdx.x) * 16;
+    if (o0 >= p.total) return;
+    // largest j in [lo_seg, hi_seg] with offs[j] <= o0
+    int64_t j0;
+    if (FAST) {
+      const uint32_t key = (uint32_t)(o0 - O_base);
+      int lo = 0, hi = (int)(hi_seg - lo_seg);
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (sh.O[mid] <= key) lo = mid; else hi = mid - 1;
+      }
+      j0 = lo_seg + lo;
     } else {
-      const uint8_t *src = tpl.literal + tpl.lit_off[k];
-      for (int i = 0; i < tpl.len[k]; ++i) out[o++] = src[i];
+      int64_t lo = lo_seg, hi = hi_seg;
+      while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(p.offs + mid) <= o0) lo = mid; else hi = mid - 1;
+      }
+      j0 = lo;
     }
+    SegCursor c;
+    seg_load<FAST>(p, sh, lo_seg, O_base, x_base, j0, c);
+    uint32_t w[4] = {0, 0, 0, 0};
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int64_t o = o0 + k;
+      uint32_t b = 0;
+      if (o < p.total) {
+        while (o >= c.O_next) seg_load<FAST>(p, sh, lo_seg, O_base, x_base, c.j + 1, c);
+        const int64_t d = o - c.O;
+        if (d < c.gap) {
+          b = rd(c.pos + d);
+        } else {
+          const int64_t q = d - c.gap;
+          if (q < p.repl_len) {
+            const int32_t src = __ldg(p.tpl_src + q);
+            b = src >= 0 ? rd(c.s + src) : (uint32_t)(-1 - src);
+          } else {
+            b = rd(c.pos);  // zero-width match: the byte at the search position (matcher.mojo:1771-1778)
+          }
+        }
+      }
+      w[k >> 2] |= b << (8 * (k & 3));
+    }
+    *reinterpret_cast<uint4 *>(p.out + o0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
-  if (e == s && pos < n) out[o] = text[pos];
 }
 
-// gap copy: grid over input tiles; every thread copies the gap bytes among its 16 input bytes
-__global__ void __launch_bounds__(kThreads) k_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans,
-                                                       int64_t M, const int64_t *offs, int mode, uint8_t *out) {
-  const int64_t x0 = ((int64_t)blockIdx.x * kThreads + threadIdx.x) * 16;
-  if (x0 >= n) return;
-  // j = number of matches with start <= x0  (segment index whose gap could contain x0 is j, if x0 >= pos_j)
-  int64_t lo = 0, hi = M;  // first index with spans[2*idx] > x0
-  while (lo < hi) {
-    const int64_t mid = (lo + hi) >> 1;
-    if (spans[2 * mid] > x0) hi = mid; else lo = mid + 1;
-  }
-  int64_t j = lo;  // gap j = [pos_j, s_j) with s_j > x0 (or tail when j == M)
-  int64_t pos = seg_pos(spans, j, mode);
-  int64_t gend = (j < M) ? spans[2 * j] : n;
-  int64_t o = offs[j];
-  const int64_t x1 = min(x0 + 16, n);
-  for (int64_t x = x0; x < x1; ++x) {
-    while (x >= gend && j < M) {
-      ++j;
-      pos = seg_pos(spans, j, mode);
-      gend = (j < M) ? spans[2 * j] : n;
-      o = offs[j];
+__global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  AsmShared &sh = *reinterpret_cast<AsmShared *>(smem_raw);
+  const int64_t tile = blockIdx.x;
+  const int64_t lo_seg = __ldg(p.tile_seg + tile);
+  const int64_t hi_seg = (tile + 1 < p.n_tiles) ? __ldg(p.tile_seg + tile + 1) : p.M;
+  const int64_t cnt = hi_seg - lo_seg + 1;
+  const int64_t O_base = __ldg(p.offs + lo_seg), O_end = __ldg(p.offs + hi_seg + 1);
+  const int64_t x_base = seg_pos_ldg(p, lo_seg);
+  const int64_t x_last = hi_seg < p.M ? __ldg(p.spans + 2 * hi_seg + 1) + 1 : p.n + 1;  // bounds every pos / s of the window
+  const bool fast = cnt <= kAsmSegCap && O_end - O_base < 0xfffffff0ll && x_last - x_base < 0xfffffff0ll;
+  if (fast) {
+    for (int k = threadIdx.x; k < (int)cnt; k += kThreads) {
+      const int64_t j = lo_seg + k;
+      const int64_t pj = seg_pos_ldg(p, j);
+      int64_t sj = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
+      if (sj < pj) sj = pj;  // tail segment after a zero-width match at n: empty gap
+      sh.O[k] = (uint32_t)(__ldg(p.offs + j) - O_base);
+      sh.pos[k] = (uint32_t)(pj - x_base);
+      sh.s[k] = (uint32_t)(sj - x_base);
     }
-    if (x >= pos && x < gend) out[o + (x - pos)] = text[x];
+    if (threadIdx.x == 0) sh.O[cnt] = (uint32_t)(O_end - O_base);
+    __syncthreads();
+    assemble_tile<true>(p, sh, tile, lo_seg, hi_seg, O_base, x_base);
+  } else {
+    assemble_tile<false>(p, sh, tile, lo_seg, hi_seg, O_base, x_base);
   }
 }
 
@@ -1258,7 +1383,7 @@ void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_
       text, n, origin, n_tiles, prog, trail, all);
 }
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st) {
-  k_carry_scan<<<1, 32, 0, st>>>(n_tiles, trail, all, carry);
+  k_carry_scan<<<1, 1024, 0, st>>>(n_tiles, trail, all, carry);
 }
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st) {
   k_attempt_one<<<1, 32, 0, st>>>(p, pos, out);
@@ -1288,20 +1413,19 @@ void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, 
   k_select_compact<<<tiles, kThreads, 0, st>>>(spans, sel, m, desc, ticket, out, total, tiles);
 }
 void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
-                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, cudaStream_t st) {
+                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, int64_t *tile_seg,
+                        cudaStream_t st) {
   const int tiles = (int)((M + 1 + kThreads - 1) / kThreads);
-  k_seg_lengths<<<tiles, kThreads, 0, st>>>(spans, M, n, mode, repl_len, desc, ticket, offs, bad, tiles);
+  k_seg_lengths<<<tiles, kThreads, 0, st>>>(spans, M, n, mode, repl_len, desc, ticket, offs, bad, tiles, tile_seg);
 }
-void launch_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
-                     const SubTemplate &tpl, uint8_t *out, cudaStream_t st) {
-  if (M <= 0) return;
-  k_seg_repl<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(text, n, spans, M, offs, tpl, out);
-}
-void launch_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs, int mode,
-                     uint8_t *out, cudaStream_t st) {
-  if (n <= 0) return;
-  const int64_t threads = (n + 15) / 16;
-  k_seg_gaps<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, st>>>(text, n, spans, M, offs, mode, out);
+void launch_assemble(const AsmParams &p, cudaStream_t st) {
+  if (p.total <= 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmShared));
+    attr_set = true;
+  }
+  k_assemble<<<(unsigned)p.n_tiles, kThreads, sizeof(AsmShared), st>>>(p);
 }
 
 }  // namespace mrx

@@ -103,6 +103,25 @@ struct SubTemplate {
   const uint8_t *literal;  // replacement string in device memory
 };
 
+// sub / split output assembly (k_assemble): one CTA per kAsmTile output bytes
+constexpr int kAsmRounds = 4;
+constexpr int kAsmTile = kThreads * 16 * kAsmRounds;  // 16 KiB
+constexpr int kAsmSegCap = 4096;                       // segment records staged per tile (48 KiB)
+struct AsmParams {
+  const uint8_t *text;
+  int64_t n;
+  const int64_t *spans;
+  int64_t M;
+  const int64_t *offs;      // M + 2 output offsets of the segments (k_seg_lengths)
+  const int64_t *tile_seg;  // segment owning the first byte of every output tile
+  int64_t n_tiles;
+  int32_t mode;             // SegMode
+  int64_t repl_len;
+  const int32_t *tpl_src;   // flattened replacement, repl_len entries
+  int64_t total;            // output bytes
+  uint8_t *out;             // 16-byte aligned, at least total + 16 bytes
+};
+
 void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
@@ -121,10 +140,8 @@ void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t
 void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
                            unsigned int *ticket, int64_t *out, unsigned long long *total, cudaStream_t st);
 void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
-                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, cudaStream_t st);
-void launch_seg_repl(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs,
-                     const SubTemplate &tpl, uint8_t *out, cudaStream_t st);
-void launch_seg_gaps(const uint8_t *text, int64_t n, const int64_t *spans, int64_t M, const int64_t *offs, int mode,
-                     uint8_t *out, cudaStream_t st);
+                        unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, int64_t *tile_seg,
+                        cudaStream_t st);
+void launch_assemble(const AsmParams &p, cudaStream_t st);
 
 }  // namespace mrx
