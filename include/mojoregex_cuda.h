@@ -160,6 +160,16 @@ void mrx_text_free(mrx_text *t);
 /* ---- matching (all of these launch CUDA kernels) ----------------------------------------- */
 /* CompiledRegex.match_all / findall (matcher.mojo:1078-1089, 1341-1354). */
 int mrx_findall(const mrx_regex *re, const mrx_text *t, int location, mrx_spans *out);
+/* findall(pattern, text) with the text in HOST memory (matcher.mojo:1341-1354: the reference's callers
+ * hold the text on the host and get a host MatchList back).  Equivalent to mrx_text_upload +
+ * mrx_findall(MRX_OUT_HOST) + mrx_text_free, but for large texts the upload, the scan and the download
+ * of the spans are pipelined chunk by chunk over three CUDA streams.  `host` should be page-locked
+ * (cudaHostAlloc / cudaHostRegister) for the copies to overlap; pageable memory works, serially. */
+int mrx_findall_host(const mrx_regex *re, const uint8_t *host, size_t n, mrx_spans *out);
+/* The same for one shard of a multi-GPU corpus: the host buffer is [left halo | core | right halo] with
+ * the window semantics of mrx_text_set_window. */
+int mrx_findall_host_shard(const mrx_regex *re, const uint8_t *host, size_t n, size_t core_begin,
+                           size_t core_end, int64_t global_offset, mrx_spans *out);
 /* CompiledRegex.match_next(text, start) / search (matcher.mojo:1064-1076, 1325-1338).
  * Returns 1 and fills out[0..1] on a match, 0 on no match, <0 on error. */
 int mrx_search(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]);

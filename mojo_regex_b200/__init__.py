@@ -82,7 +82,7 @@ EXPORTS = [
     "mrx_abi_version", "mrx_init", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
     "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
-    "mrx_text_free", "mrx_findall", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
+    "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
     "mrx_split", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
 ]
 
@@ -117,6 +117,8 @@ def _load() -> ctypes.CDLL:
     lib.mrx_text_free.argtypes = [vp]
     lib.mrx_text_free.restype = None
     lib.mrx_findall.argtypes = [vp, vp, c.c_int, P(_Spans)]
+    lib.mrx_findall_host.argtypes = [vp, vp, sz, P(_Spans)]
+    lib.mrx_findall_host_shard.argtypes = [vp, vp, sz, sz, sz, i64, P(_Spans)]
     lib.mrx_search.argtypes = [vp, vp, i64, P(i64)]
     lib.mrx_match_first.argtypes = [vp, vp, i64, P(i64)]
     lib.mrx_search_batch.argtypes = [vp, vp, vp, sz, i64, c.c_int, vp]
@@ -350,6 +352,11 @@ class CompiledRegex:
         return Match(out[0], out[1], raw) if rc == 1 else None
 
     def match_all(self, text) -> MatchList:
+        if isinstance(text, np.ndarray) and text.dtype == np.uint8 and text.flags["C_CONTIGUOUS"]:
+            _ensure_init()
+            ml = self.match_all_host(text.ctypes.data, text.size)
+            ml._keep = text
+            return ml
         t, raw = _text_of(text)
         sp = _Spans()
         _check(lib.mrx_findall(self._h, t._h, OUT_HOST, ctypes.byref(sp)))
@@ -361,6 +368,21 @@ class CompiledRegex:
         finally:
             lib.mrx_spans_free(ctypes.byref(sp))
         return MatchList(arr, raw)
+
+    def match_all_host(self, ptr: int, nbytes: int, core_begin: int = 0, core_end: Optional[int] = None,
+                       global_offset: int = 0) -> "MatchList":
+        """findall over `nbytes` at host address `ptr` (page-locked for full speed): upload, scan and span
+        download are pipelined inside the library.  The returned MatchList views the library's pinned
+        result buffer (no copy); it is released when the MatchList is garbage collected."""
+        sp = _Spans()
+        _check(lib.mrx_findall_host_shard(self._h, ptr, nbytes, core_begin, nbytes if core_end is None else core_end,
+                                          global_offset, ctypes.byref(sp)))
+        owner = _HostSpans(sp)
+        if sp.n:
+            arr = np.ctypeslib.as_array(sp.start_end, shape=(sp.n * 2,)).reshape(-1, 2)
+        else:
+            arr = np.zeros((0, 2), dtype=np.int64)
+        return MatchList(arr, None, owner)
 
     def match_all_device(self, text: Text):
         """findall with the span array left in HBM: returns (torch int64 tensor view (n,2), keepalive)."""
@@ -431,6 +453,24 @@ class CompiledRegex:
         if self._h:
             lib.mrx_regex_free(self._h)
             self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _HostSpans:
+    """Keeps a pinned host span array of the library alive for the numpy view built on it."""
+
+    def __init__(self, sp: _Spans):
+        self._sp = sp
+
+    def close(self):
+        if self._sp is not None:
+            lib.mrx_spans_free(ctypes.byref(self._sp))
+            self._sp = None
 
     def __del__(self):
         try:

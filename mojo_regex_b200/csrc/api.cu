@@ -27,6 +27,8 @@ struct Lib {
   bool inited = false;
   int device = -1;
   cudaStream_t stream = nullptr;
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the host-buffer pipelines (H2D / D2H)
+  std::vector<cudaEvent_t> ev_pool;              // untimed events for those pipelines
   uint64_t launches = 0;
   // caching allocators: device blocks and pinned host blocks, bucketed by power-of-two size
   std::multimap<size_t, void *> dev_free, host_free;
@@ -602,6 +604,127 @@ int finish_spans(DevSpans &ds, int location, mrx_spans *out) {
   return MRX_OK;
 }
 
+// ---- findall over a host buffer, pipelined ---------------------------------------------------------
+// The text is uploaded in chunks on the H2D stream; as soon as a chunk has landed, the tiles it completes
+// are scanned on the compute stream (one logical job: the ticket, the look-back descriptors and the span
+// array continue across launches), and the spans found so far travel back on the D2H stream while the next
+// chunk is still arriving.  PCIe is full duplex, so the call costs about one upload of the text.
+// Plans served this way read at most kLookAhead bytes past the tile they scan (dense literal sets: none,
+// class runs: one byte); every other plan uploads first and scans after.
+constexpr int64_t kPipeChunk = 32ll << 20;
+constexpr int64_t kLookAhead = 16;
+
+cudaEvent_t pipe_event(size_t i) {
+  while (g.ev_pool.size() <= i) {
+    cudaEvent_t e = nullptr;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    g.ev_pool.push_back(e);
+  }
+  return g.ev_pool[i];
+}
+
+bool plan_pipelines(const Plan &pl) {
+  if (pl.unsupported) return false;
+  return pl.dense.valid || pl.mode == MRX_MODE_CLASS_RUNS;
+}
+
+int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_t core_begin, int64_t core_end,
+                           int64_t global_offset, mrx_spans *out) {
+  const Plan &pl = re->prog.findall;
+  int rc;
+  DevTmp d_text, desc;
+  if ((rc = d_text.get((size_t)n + 512))) return rc;
+  uint8_t *dt = d_text.as<uint8_t>();
+  mrx_text tview;
+  tview.d = dt; tview.n = (size_t)n; tview.owned = false; tview.core_begin = (size_t)core_begin; tview.core_end = (size_t)core_end;
+  tview.global_offset = global_offset;
+  const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
+  CUDA_TRY(cudaMemsetAsync(dt + n, 0, 512, g.s_in));
+  for (int64_t c = 0; c < n_chunks; ++c) {
+    const int64_t b = c * kPipeChunk, len = std::min(kPipeChunk, n - b);
+    CUDA_TRY(cudaMemcpyAsync(dt + b, host + b, (size_t)len, cudaMemcpyHostToDevice, g.s_in));
+    CUDA_TRY(cudaEventRecord(pipe_event((size_t)c), g.s_in));
+  }
+  ListJob job{re, &tview, &pl, re->d_findall, core_begin, core_end, global_offset};
+  if (pl.dense.valid) job.dense = re->d_dense_findall;
+  const int64_t origin = core_begin & ~15ll;
+  const int64_t tiles = n_tiles_for(origin, core_end - 1);
+  if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
+  if (tiles <= 0) {
+    CUDA_TRY(cudaStreamSynchronize(g.s_in));
+    out->n = 0; out->location = MRX_OUT_HOST;
+    return MRX_OK;
+  }
+  const int64_t cap = initial_cap(job);
+  void *d_spans = nullptr, *h_spans = nullptr;
+  if ((rc = desc.get(sizeof(unsigned long long) * tiles))) return rc;
+  if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &d_spans))) return rc;
+  if ((rc = host_alloc(sizeof(int64_t) * 2 * std::max<int64_t>(cap, 1), &h_spans))) { dev_release(d_spans); return rc; }
+  auto cleanup = [&]() { dev_release(d_spans); host_release(h_spans); };
+  CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+  const bool runs = !pl.dense.valid;  // CLASS_RUNS: the last run may still be open, its end is written later
+  int64_t t0 = 0, copied = 0, total = 0;
+  bool overflow = false;
+  for (int64_t c = 0; c < n_chunks && !overflow; ++c) {
+    const int64_t vis = std::min(n, (c + 1) * kPipeChunk);
+    const int64_t t1 = (c == n_chunks - 1) ? tiles
+                                           : std::min(tiles, std::max<int64_t>(t0, (vis - kLookAhead - origin) / kTile));
+    if (t1 <= t0) continue;
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event((size_t)c), 0));
+    CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+    if (g.profiling && c == 0) cudaEventRecord(g.ev0, g.stream);
+    if (pl.dense.valid) {
+      DenseParams dp{};
+      dp.text = dt; dp.n = n; dp.tile_origin = origin; dp.key_lo = core_begin; dp.key_hi = core_end; dp.dense = job.dense;
+      dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
+      dp.n_tiles = (int)t1; dp.tile_base = (int)t0; dp.spans = (int64_t *)d_spans; dp.cap = cap; dp.rebase = global_offset;
+      dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = g.scalars;
+      launch_dense(dp, (int)(t1 - t0), g.stream);
+    } else {
+      RunsParams p{};
+      p.text = dt; p.n = n; p.tile_origin = origin; p.key_lo = core_begin; p.key_hi = core_end; p.prog = re->d_findall; p.filt = make_filter(pl);
+      p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max; p.n_tiles = (int)t1; p.tile_base = (int)t0;
+      p.tile_carry = nullptr; p.spans = (int64_t *)d_spans; p.cap = cap; p.rebase = global_offset;
+      p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
+      launch_runs(p, (int)(t1 - t0), g.stream);
+    }
+    if (g.profiling && c == 0) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = read_scalars(0, 1))) { cleanup(); return rc; }  // waits for this launch only; uploads keep going
+    total = (int64_t)g.h_scalars[0];
+    if (total > cap) { overflow = true; break; }
+    const int64_t ready = (t1 == tiles) ? total : (runs ? std::max<int64_t>(total - 1, copied) : total);
+    if (ready > copied) {
+      CUDA_TRY(cudaMemcpyAsync((int64_t *)h_spans + 2 * copied, (int64_t *)d_spans + 2 * copied,
+                               sizeof(int64_t) * 2 * (ready - copied), cudaMemcpyDeviceToHost, g.s_out));
+      copied = ready;
+    }
+    t0 = t1;
+  }
+  if (overflow) {
+    // the capacity guess was too small: finish the upload, then run the plain (resizing) list job
+    cleanup();
+    CUDA_TRY(cudaStreamSynchronize(g.s_out));
+    CUDA_TRY(cudaStreamSynchronize(g.s_in));
+    DevSpans ds;
+    if ((rc = match_list(re, &tview, pl, re->d_findall, ds))) return rc;
+    return finish_spans(ds, MRX_OUT_HOST, out);
+  }
+  note_density(job, total);
+  CUDA_TRY(cudaStreamSynchronize(g.s_out));
+  CUDA_TRY(cudaStreamSynchronize(g.s_in));
+  dev_release(d_spans);
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = h_spans;
+  out->_owner = own;
+  out->start_end = (int64_t *)h_spans;
+  out->n = (size_t)total;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
 }  // namespace
 
 // =================================================================================================
@@ -619,6 +742,8 @@ int mrx_init(int device) {
   if (device < 0 || device >= count) return fail(MRX_E_INVALID, "device index out of range");
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&g.s_out, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&g.ticket, 64));
   CUDA_TRY(cudaMalloc(&g.scalars, 64 * sizeof(unsigned long long)));
   CUDA_TRY(cudaHostAlloc(&g.h_scalars, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
@@ -642,6 +767,9 @@ int mrx_shutdown(void) {
   cudaFreeHost(g.h_scalars);
   cudaEventDestroy(g.ev0);
   cudaEventDestroy(g.ev1);
+  for (cudaEvent_t e : g.ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(g.s_in);
+  cudaStreamDestroy(g.s_out);
   cudaStreamDestroy(g.stream);
   g = Lib();
   return MRX_OK;
@@ -840,6 +968,28 @@ int mrx_findall(const mrx_regex *re_c, const mrx_text *t, int location, mrx_span
   DevSpans ds;
   if ((rc = match_list(re, t, re->prog.findall, re->d_findall, ds))) return rc;
   return finish_spans(ds, location, out);
+}
+
+int mrx_findall_host_shard(const mrx_regex *re_c, const uint8_t *host, size_t n, size_t core_begin, size_t core_end,
+                           int64_t global_offset, mrx_spans *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !out || (!host && n) || core_begin > core_end || core_end > n) return fail(MRX_E_INVALID, "bad argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  if ((rc = ensure_uploaded(re))) return rc;
+  if (plan_pipelines(re->prog.findall) && (int64_t)n >= 2 * kPipeChunk)
+    return findall_host_pipelined(re, host, (int64_t)n, (int64_t)core_begin, (int64_t)core_end, global_offset, out);
+  mrx_text *t = nullptr;
+  if ((rc = mrx_text_upload(host, n, &t))) return rc;
+  if ((rc = mrx_text_set_window(t, core_begin, core_end, global_offset)) == MRX_OK)
+    rc = mrx_findall(re_c, t, MRX_OUT_HOST, out);
+  mrx_text_free(t);
+  return rc;
+}
+
+int mrx_findall_host(const mrx_regex *re_c, const uint8_t *host, size_t n, mrx_spans *out) {
+  return mrx_findall_host_shard(re_c, host, n, 0, n, 0, out);
 }
 
 int mrx_search(const mrx_regex *re_c, const mrx_text *t, int64_t start, int64_t out[2]) {

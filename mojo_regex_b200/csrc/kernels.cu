@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
   int64_t p_start = 0;
 
   auto take_ticket_and_load = [&]() {  // thread 0 only
-    const int t = (int)atomicAdd(prm.ticket, 1u);
+    const int t = prm.tile_base + (int)atomicAdd(prm.ticket, 1u);
     sh.tile = t;
     if (t < prm.n_tiles) {
       const int64_t ts = prm.tile_origin + (int64_t)t * kTile;
@@ -705,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   RunsShared &sh = *reinterpret_cast<RunsShared *>(smem_raw);
   const int tid = threadIdx.x;
-  if (tid == 0) sh.tile = (int)atomicAdd(prm.ticket, 1u);
+  if (tid == 0) sh.tile = prm.tile_base + (int)atomicAdd(prm.ticket, 1u);
   load_prog(&sh.prog, prm.prog);
   __syncthreads();
   const int tile = sh.tile;

@@ -55,6 +55,7 @@ struct RunsParams {
   int32_t mode;  // MRX_MODE_CLASS_RUNS or MRX_MODE_UNIFORM_RUN
   int32_t run_min, run_max;
   int32_t n_tiles;
+  int32_t tile_base;    // tiles [tile_base, n_tiles) are handed out by this launch (ticket starts at 0)
   const long long *tile_carry;
   int64_t *spans;
   int64_t cap;
@@ -82,6 +83,7 @@ struct DenseParams {
   int32_t table_bytes;
   int32_t out_kind;        // OUT_SPANS or OUT_FIRST
   int32_t n_tiles;
+  int32_t tile_base;       // tiles [tile_base, n_tiles) are handed out by this launch (ticket starts at 0)
   int64_t *spans;
   int64_t cap;
   int64_t rebase;

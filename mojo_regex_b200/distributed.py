@@ -269,6 +269,11 @@ def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
     """One step through the public API from a pinned host buffer; returns bytes copied back."""
     import mojo_regex_b200 as mr
 
+    if cfg["op"] == "findall":
+        # one C-ABI call on the host buffer: upload, scan and span download are pipelined inside
+        ml = rx.match_all_host(host_pinned.data_ptr(), host_pinned.numel(), shard.core_begin, shard.core_end,
+                               shard.global_offset)
+        return int(ml.spans.nbytes)
     t = mr.Text.from_pinned(host_pinned.data_ptr(), host_pinned.numel())
     t.set_window(shard.core_begin, shard.core_end, shard.global_offset)
     try:

@@ -272,3 +272,57 @@ def test_sharded_findall_emulated_ranks(config, size):
     whole = torch.cat([mrd._core(config, size, r, "cuda") for r in range(world)]).cpu().numpy()
     want = oracle.compile(pat).findall(whole)
     assert np.array_equal(got, want)
+
+
+# ---- host-buffer entry point (mrx_findall_host): chunked upload / scan / download pipeline --------------
+PIPE_CHUNK = 32 << 20
+
+
+@pytest.mark.parametrize("config", ["c2", "c1"])
+def test_findall_host_pipelined_matches_oracle(config):
+    """Texts of several pipeline chunks: the spans streamed back chunk by chunk must equal the oracle's, and
+    the device-resident path's, bit for bit (dense literal set and class runs are the pipelined plans)."""
+    pat = corpora.CONFIGS[config]["pattern"]
+    n = 3 * PIPE_CHUNK + 12345
+    text = corpora.make(config, n)
+    if config == "c1":
+        # a digit run across every chunk boundary, and one that covers a whole tile
+        for b in (PIPE_CHUNK, 2 * PIPE_CHUNK, 3 * PIPE_CHUNK):
+            text[b - 7:b + 9] = ord("7")
+        text[PIPE_CHUNK + 5 * TILE - 100:PIPE_CHUNK + 6 * TILE + 100] = ord("3")
+    else:
+        lit = torch.tensor(list(b"hello"), dtype=torch.uint8)
+        for b in (PIPE_CHUNK, 2 * PIPE_CHUNK):
+            text[b - 2:b + 3] = lit          # a literal straddling the chunk boundary
+            text[b - 40:b - 35] = lit
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    host.copy_(text)
+    rx = mr.compile_regex(pat)
+    want = oracle.compile(pat).findall(text.numpy())
+    got = rx.match_all_host(host.data_ptr(), n)
+    assert np.array_equal(got.spans, want)
+    got2 = rx.match_all_host(host.data_ptr(), n)      # second call: capacity from the remembered density
+    assert np.array_equal(got2.spans, want)
+    # pageable source memory goes through the same entry point
+    got3 = rx.match_all(text.numpy())
+    assert np.array_equal(got3.spans, want)
+    # windowed shard of the same buffer
+    lo, hi = PIPE_CHUNK - 3, 2 * PIPE_CHUNK + 11
+    got4 = rx.match_all_host(host.data_ptr(), n, lo, hi, 5000).spans
+    if config == "c1":   # class runs are clipped to the window (stitched by the caller)
+        sel = want[(want[:, 1] > lo) & (want[:, 0] < hi)].copy()
+        sel[:, 0] = np.maximum(sel[:, 0], lo)
+        sel[:, 1] = np.minimum(sel[:, 1], hi)
+    else:
+        sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)]
+    assert np.array_equal(got4, sel + 5000)
+
+
+def test_findall_host_small_and_unpipelined_plans():
+    rx = mr.compile_regex(r"[a-z]+[0-9]+")           # attempt plan: uploaded, then scanned
+    text = np.frombuffer(b"hello123 world456 test789 " * 1000, dtype=np.uint8)
+    want = oracle.compile(r"[a-z]+[0-9]+").findall(text)
+    assert np.array_equal(rx.match_all(text).spans, want)
+    empty = np.zeros(0, dtype=np.uint8)
+    assert len(rx.match_all(empty)) == 0
+    assert len(mr.compile_regex(r"(hello|world|foo)").match_all(empty)) == 0
