@@ -87,6 +87,7 @@ typedef struct {
   int32_t search_direct;
   int32_t fixed_sub_total_width, fixed_sub_num_groups, fixed_sub_concat;
   int32_t findall_dense, search_dense; /* 1 = served by the dense literal-set automaton (k_dense)       */
+  int32_t search_rev_states;           /* > 0: batch search runs the reverse-automaton kernel (k_lines)  */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */
@@ -181,8 +182,9 @@ int mrx_match_first(const mrx_regex *re, const mrx_text *t, int64_t start, int64
  * callers loop).  Document i is t[doc_offsets[i] .. doc_offsets[i+1]);
  * out_start_end[2i..2i+1] are relative to the document, (-1,-1) = None.  `doc_offsets`
  * (n_docs+1 entries) and `out_start_end` are host pointers when location == MRX_OUT_HOST,
- * device pointers when MRX_OUT_DEVICE.  doc_offsets == NULL means fixed-size documents of
- * `doc_stride` bytes. */
+ * device pointers when MRX_OUT_DEVICE (the results are then ordered on the library stream: use
+ * mrx_stream() / mrx_synchronize() before reading them from another stream or the host).
+ * doc_offsets == NULL means fixed-size documents of `doc_stride` bytes. */
 int mrx_search_batch(const mrx_regex *re, const mrx_text *t, const int64_t *doc_offsets,
                      size_t n_docs, int64_t doc_stride, int location, int64_t *out_start_end);
 /* sub(pattern, repl, text, count) (matcher.mojo:1857-1917, 1679-1854). count == 0: all. */

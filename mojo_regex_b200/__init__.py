@@ -67,7 +67,8 @@ class Info(ctypes.Structure):
         "n_states", "n_classes", "start_state", "has_start_anchor", "has_end_anchor", "is_pure_literal",
         "has_matcher", "scan_eligible", "required_byte", "is_wildcard_any", "is_exact_literal",
         "has_prefilter", "findall_mode", "search_mode", "findall_direct", "search_direct",
-        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat", "findall_dense", "search_dense")]
+        "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat", "findall_dense", "search_dense",
+        "search_rev_states")]
 
 
 class DfaDesc(ctypes.Structure):
@@ -392,8 +393,10 @@ class CompiledRegex:
         _check(lib.mrx_findall(self._h, text._h, OUT_DEVICE, ctypes.byref(sp)))
         return _DeviceSpans(sp)
 
-    def search_batch(self, text, doc_offsets=None, doc_stride: int = 0, n_docs: Optional[int] = None) -> np.ndarray:
-        """One match_next(doc, 0) per document -> (n_docs, 2) int64, (-1,-1) = no match."""
+    def search_batch(self, text, doc_offsets=None, doc_stride: int = 0, n_docs: Optional[int] = None,
+                     out: Optional[np.ndarray] = None) -> np.ndarray:
+        """One match_next(doc, 0) per document -> (n_docs, 2) int64, (-1,-1) = no match.  `out` may be a
+        caller-provided (page-locked) int64 array of 2 * n_docs elements."""
         t, _ = _text_of(text)
         if doc_offsets is not None:
             offs = np.ascontiguousarray(doc_offsets, dtype=np.int64)
@@ -404,7 +407,9 @@ class CompiledRegex:
             if n_docs is None:
                 n_docs = (len(t) + doc_stride - 1) // doc_stride
             optr = None
-        out = np.empty((n_docs, 2), dtype=np.int64)
+        if out is None:
+            out = np.empty((n_docs, 2), dtype=np.int64)
+        assert out.dtype == np.int64 and out.size >= 2 * n_docs and out.flags["C_CONTIGUOUS"]
         _check(lib.mrx_search_batch(self._h, t._h, optr, n_docs, doc_stride, OUT_HOST, out.ctypes.data))
         return out
 
@@ -434,6 +439,22 @@ class CompiledRegex:
         finally:
             lib.mrx_bytes_free(ctypes.byref(ob))
 
+    def sub_view(self, repl, text, count: int = 0) -> "HostBytes":
+        """sub() whose result stays in the library's pinned buffer: .array is a zero-copy uint8 view."""
+        t, _ = _text_of(text)
+        r = _as_bytes(repl)
+        ob = _Bytes()
+        _check(lib.mrx_sub(self._h, r, len(r), count, t._h, OUT_HOST, ctypes.byref(ob)))
+        return HostBytes(ob)
+
+    def split_view(self, text, maxsplit: int = 0) -> "HostPieces":
+        """split() whose pieces stay in the library's pinned buffers: .data (uint8) and .offsets (int64,
+        n + 1 entries) are zero-copy views; piece i is data[offsets[i]:offsets[i+1]]."""
+        t, _ = _text_of(text)
+        pc = _Pieces()
+        _check(lib.mrx_split(self._h, t._h, maxsplit, OUT_HOST, ctypes.byref(pc)))
+        return HostPieces(pc)
+
     def split_raw(self, text, maxsplit: int = 0):
         t, _ = _text_of(text)
         pc = _Pieces()
@@ -453,6 +474,56 @@ class CompiledRegex:
         if self._h:
             lib.mrx_regex_free(self._h)
             self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostBytes:
+    """sub() output in the library's pinned host memory (released on close / garbage collection)."""
+
+    def __init__(self, ob: _Bytes):
+        self._ob = ob
+        self.n = int(ob.n)
+        self.array = np.ctypeslib.as_array(ob.bytes, shape=(self.n,)) if self.n else np.zeros(0, dtype=np.uint8)
+
+    def tobytes(self) -> bytes:
+        return self.array.tobytes()
+
+    def close(self):
+        if self._ob is not None:
+            self.array = None
+            lib.mrx_bytes_free(ctypes.byref(self._ob))
+            self._ob = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class HostPieces:
+    """split() output in the library's pinned host memory."""
+
+    def __init__(self, pc: _Pieces):
+        self._pc = pc
+        self.n = int(pc.n)
+        self.offsets = np.ctypeslib.as_array(pc.offsets, shape=(self.n + 1,))
+        total = int(self.offsets[-1])
+        self.data = np.ctypeslib.as_array(pc.bytes, shape=(total,)) if total else np.zeros(0, dtype=np.uint8)
+
+    def piece(self, i: int) -> bytes:
+        return self.data[self.offsets[i]:self.offsets[i + 1]].tobytes()
+
+    def close(self):
+        if self._pc is not None:
+            self.data = self.offsets = None
+            lib.mrx_pieces_free(ctypes.byref(self._pc))
+            self._pc = None
 
     def __del__(self):
         try:

@@ -115,6 +115,7 @@ struct mrx_regex {
   Program prog;
   DevProg *d_findall = nullptr, *d_search = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
+  uint8_t *d_rev_search = nullptr;                                // RevTable::tbl of the search plan
   bool search_dominated = false;
   // matches per key byte seen by the last list job of each plan (findall, search): sizes the span
   // buffer of the next call so that the scan does not have to be repeated with a larger one
@@ -220,6 +221,14 @@ int ensure_uploaded(mrx_regex *re) {
   if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
   if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
   if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
+  if (re->prog.search.rev.valid && !re->d_rev_search) {
+    const std::vector<uint8_t> &tb = re->prog.search.rev.tbl;
+    void *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, tb.size()));
+    CUDA_TRY(cudaMemcpyAsync(d, tb.data(), tb.size(), cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    re->d_rev_search = static_cast<uint8_t *>(d);
+  }
   if (!re->d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->d_findall); if (rc) return rc; }
   if (!re->d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->d_search); if (rc) return rc; }
   return MRX_OK;
@@ -895,6 +904,7 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
   o->fixed_sub_total_width = p.fixed_total_width; o->fixed_sub_num_groups = p.fixed_num_groups;
   o->fixed_sub_concat = p.fixed_concat;
   o->findall_dense = p.findall.dense.valid; o->search_dense = p.search.dense.valid;
+  o->search_rev_states = p.search.rev.valid ? p.search.rev.n_rev : 0;
   return MRX_OK;
 }
 
@@ -904,6 +914,7 @@ void mrx_regex_free(mrx_regex *re) {
   if (re->d_search) cudaFree(re->d_search);
   if (re->d_dense_findall) cudaFree(re->d_dense_findall);
   if (re->d_dense_search) cudaFree(re->d_dense_search);
+  if (re->d_rev_search) cudaFree(re->d_rev_search);
   delete re;
 }
 
@@ -1066,6 +1077,29 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     } else {
       offs_dev = doc_offsets;
     }
+  }
+  if (re->d_rev_search && re->d_search && !getenv("MRX_NO_LINES")) {
+    // reverse-automaton kernel: one thread per document, results written in place
+    int64_t *outp = out_start_end;
+    if (location == MRX_OUT_HOST) {
+      if ((rc = d_out.get(sizeof(int64_t) * 2 * n_docs))) return rc;
+      outp = d_out.as<int64_t>();
+    }
+    LinesParams lp{};
+    lp.text = t->d; lp.n = n; lp.prog = re->d_search; lp.rev = re->d_rev_search;
+    lp.rev_bytes = (int32_t)pl.rev.tbl.size(); lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
+    lp.n_docs = (int64_t)n_docs; lp.out = outp;
+    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
+    launch_lines(lp, g.stream);
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    if (location == MRX_OUT_HOST) {
+      CUDA_TRY(cudaMemcpyAsync(out_start_end, outp, sizeof(int64_t) * 2 * n_docs, cudaMemcpyDeviceToHost, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+    }
+    // MRX_OUT_DEVICE: the results are ordered on the library stream (mrx_stream / mrx_synchronize)
+    return MRX_OK;
   }
   if ((rc = d_best.get(sizeof(unsigned long long) * n_docs))) return rc;
   launch_fill_u64(d_best.as<unsigned long long>(), (int64_t)n_docs, ~0ull, g.stream);

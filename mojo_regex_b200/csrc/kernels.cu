@@ -649,6 +649,81 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// per-document search: match_next(doc, 0) for every document of a batch (the reference's
+// callers loop over dfa.mojo:2241-2253).  One thread per document.  Pass 1 walks the document BACKWARDS
+// through the reverse automaton (program.hpp: RevTable) -- one shared-memory lookup per byte, address
+// formed by a single PRMT (set id in byte 1, text byte in byte 0) -- and remembers the last flagged
+// position it sees, which is the leftmost position whose attempt succeeds: exactly the start the
+// reference's ascending loop over candidates returns.  Pass 2 runs that one attempt forwards for the
+// longest accept.  No candidate queue, no atomics, no divergence in pass 1.
+struct LinesShared {
+  DevProg prog;
+  alignas(16) uint8_t rev[16];  // the whole table follows
+};
+
+__global__ void __launch_bounds__(kThreads) k_lines(const LinesParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
+  load_prog(&sh.prog, prm.prog);
+  {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.rev);
+    uint4 *d4 = reinterpret_cast<uint4 *>(sh.rev);
+    for (int i = threadIdx.x; i < prm.rev_bytes / 16; i += kThreads) d4[i] = s4[i];
+  }
+  __syncthreads();
+  const int64_t d = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (d >= prm.n_docs) return;
+  const int64_t lo = prm.doc_offsets ? prm.doc_offsets[d] : d * prm.doc_stride;
+  const int64_t hi = prm.doc_offsets ? prm.doc_offsets[d + 1] : min(lo + prm.doc_stride, prm.n);
+  const uint8_t *rev = sh.rev;
+  int64_t best = -1;
+  uint32_t r = 0;  // last table entry: set id (bits 0..6) | flag (bit 7); set 0 = the accepting states
+  const bool vec = prm.doc_offsets == nullptr && (prm.doc_stride & 15) == 0 && hi - lo == prm.doc_stride &&
+                   (reinterpret_cast<uintptr_t>(prm.text + lo) & 15) == 0;
+  if (vec) {
+    const uint4 *v = reinterpret_cast<const uint4 *>(prm.text + lo);
+    const int nv = (int)(prm.doc_stride >> 4);
+    uint32_t best_pk = 0;
+    int best_word = -1;  // index of the 4-byte word (from lo) that holds the leftmost flagged byte
+#pragma unroll 2
+    for (int k = nv - 1; k >= 0; --k) {
+      const uint4 w4 = __ldg(v + k);
+      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int wi = 3; wi >= 0; --wi) {
+        uint32_t pk = 0;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+          const uint32_t addr = __byte_perm(ws[wi], r, 0x5540 + j) & 0x7fffu;  // (set id << 8) | byte j
+          r = rev[addr];
+          pk = __byte_perm(pk, r, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);
+        }
+        if (pk & 0x80808080u) { best_pk = pk; best_word = 4 * k + wi; }
+      }
+    }
+    if (best_word >= 0) best = lo + 4 * best_word + ((__ffs(best_pk & 0x80808080u) - 1) >> 3);
+  } else {
+    for (int64_t q = hi - 1; q >= lo; --q) {
+      r = rev[((r & 0x7fu) << 8) | prm.text[q]];
+      if (r & 0x80u) best = q;
+    }
+  }
+  int64_t s_rel = -1, e_rel = -1;
+  if (best >= 0) {
+    Attempt at;
+    at.p = &sh.prog;
+    at.tv.g = prm.text;
+    at.tv.s = nullptr;
+    at.tv.s_begin = at.tv.s_end = 0;
+    at.lo = lo;
+    at.n = hi;
+    const int64_t e = at.dfa(best);
+    if (e >= 0) { s_rel = best - lo; e_rel = e - lo; }
+  }
+  st_span(prm.out + 2 * d, s_rel, e_rel);
+}
+
+// ---------------------------------------------------------------------------------------------
 // class runs
 struct RunsShared {
   DevProg prog;
@@ -1338,6 +1413,16 @@ void launch_scan(const ScanParams &p, int grid, cudaStream_t st) {
     case FILT_ALL: launch_scan_t<FILT_ALL>(p, grid, st); break;
     default: launch_scan_t<FILT_LUT>(p, grid, st); break;
   }
+}
+void launch_lines(const LinesParams &p, cudaStream_t st) {
+  if (p.n_docs <= 0) return;
+  const int smem = (int)sizeof(LinesShared) + p.rev_bytes;
+  static int attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_smem = smem;
+  }
+  k_lines<<<(unsigned)((p.n_docs + kThreads - 1) / kThreads), kThreads, smem, st>>>(p);
 }
 template <int FILT>
 static void launch_runs_t(const RunsParams &p, int grid, cudaStream_t st) {

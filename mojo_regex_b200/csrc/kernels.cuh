@@ -94,6 +94,19 @@ struct DenseParams {
   int32_t debug_no_lookback;  // measurement only (MRX_DEBUG_NOLOOKBACK=1): results are NOT ordered
 };
 
+// Per-document search (k_lines): one thread per document.
+struct LinesParams {
+  const uint8_t *text;
+  int64_t n;
+  const DevProg *prog;         // forward automaton (longest accept from the winning start)
+  const uint8_t *rev;          // RevTable::tbl in HBM
+  int32_t rev_bytes;           // n_rev * 256
+  const int64_t *doc_offsets;  // n_docs + 1 entries, or nullptr for fixed-size documents
+  int64_t doc_stride;
+  int64_t n_docs;
+  int64_t *out;                // (start, end) relative to the document, (-1, -1) = no match
+};
+
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };
 
 constexpr int kMaxTplSegs = 32;
@@ -125,6 +138,7 @@ struct AsmParams {
 };
 
 void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
+void launch_lines(const LinesParams &p, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,

@@ -420,6 +420,51 @@ void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
   choose_filter(pl);
 }
 
+}  // namespace
+
+bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
+  rt = RevTable();
+  if (pl.unsupported || pl.shortcut || p.n_states <= 0 || p.n_states > 64 || p.start_accepting()) return false;
+  if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) return false;
+  if (pl.mode != MRX_MODE_FIRST_CLASS && pl.mode != MRX_MODE_EVERY_POS && pl.mode != MRX_MODE_UNIFORM_RUN) return false;
+  const int n = p.n_states, s0 = p.start_state;
+  uint64_t acc = 0;
+  for (int q = 0; q < n; ++q) if (p.accepting[q]) acc |= 1ull << q;
+  std::vector<uint64_t> sets{acc};
+  std::map<uint64_t, int> ids{{acc, 0}};
+  std::vector<uint8_t> tbl;
+  for (size_t i = 0; i < sets.size(); ++i) {
+    tbl.resize((i + 1) * 256);
+    const uint64_t S = sets[i];
+    for (int b = 0; b < 256; ++b) {
+      uint64_t T = 0;
+      for (int q = 0; q < n; ++q) {
+        const int nx = p.next(q, b);
+        if (nx != kDead && ((S >> nx) & 1)) T |= 1ull << q;
+      }
+      const bool flag = ((T >> s0) & 1) && pl.cand[b];
+      T |= acc;
+      auto it = ids.find(T);
+      int id;
+      if (it == ids.end()) {
+        if (sets.size() >= 128) return false;
+        id = (int)sets.size();
+        ids.emplace(T, id);
+        sets.push_back(T);
+      } else {
+        id = it->second;
+      }
+      tbl[i * 256 + b] = (uint8_t)(id | (flag ? 0x80 : 0));
+    }
+  }
+  rt.valid = true;
+  rt.n_rev = (int)sets.size();
+  rt.tbl = std::move(tbl);
+  return true;
+}
+
+namespace {
+
 void make_plans(Program &p) {
   Plan &fa = p.findall, &se = p.search;
   // _try_match_at_position consults _try_match_simd first whenever the engine has a matcher and
@@ -496,6 +541,7 @@ void make_plans(Program &p) {
   }
   try_dense(p, fa);
   try_dense(p, se);
+  build_reverse(p, se, se.rev);
 }
 
 }  // namespace

@@ -60,9 +60,21 @@ struct DenseTable {
   std::vector<uint8_t> out_len;  // n_states - acc_base
 };
 
+// Reverse search automaton for per-document search (k_lines).  Scanning a document from its last byte
+// to its first, the state after byte i is the set R(i) of forward states from which text[i..] reaches an
+// accepting state; an attempt of the reference at i succeeds exactly when the start state is in R(i).
+// Subset construction over those sets: entry (r, byte) = next set id | 0x80 when "an attempt starting
+// at this byte succeeds and the byte is a candidate of the plan".  At most 128 sets, 256 bytes per row.
+struct RevTable {
+  bool valid = false;
+  int32_t n_rev = 0;
+  std::vector<uint8_t> tbl;  // n_rev * 256
+};
+
 struct Plan {
   int32_t mode = -1;  // MRX_MODE_*
   DenseTable dense;
+  RevTable rev;
   bool direct = false;        // potential matches provably never overlap: emit them as final
   bool unsupported = false;   // plan cannot be executed faithfully
   std::string why;
@@ -92,6 +104,10 @@ struct Program {
   bool start_accepting() const { return n_states > 0 && accepting[start_state]; }
   int next(int s, int byte) const { return trans[(size_t)s * n_classes + byte_class[byte]]; }
 };
+
+// Reverse automaton of `p` for the attempts of plan `pl`; false when the plan is not an attempt plan
+// or the construction exceeds 128 sets.
+bool build_reverse(const Program &p, const Plan &pl, RevTable &rt);
 
 // RawDfa (+meta) -> blob.  Returns false (with err) when the automaton does not fit the format.
 bool pack_blob(const RawDfa &dfa, const RegexMeta &meta, std::string &blob, std::string &err);

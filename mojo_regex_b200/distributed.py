@@ -244,7 +244,7 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128)
         if shard.world > 1:
             _gather_for(1, dev).gather([shard.n_docs])
-        return OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_scan", None)
+        return OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_lines" if rx.info().search_rev_states > 0 else "k_scan", None)
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
         base = 0
@@ -265,6 +265,16 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
     raise ValueError(cfg["op"])
 
 
+_PINNED_OUT = {}
+
+
+def _pinned_i64(n: int):
+    """Page-locked int64 result buffer for batch search (allocated once per size)."""
+    if n not in _PINNED_OUT:
+        _PINNED_OUT[n] = torch.empty(n, dtype=torch.int64, pin_memory=True)
+    return _PINNED_OUT[n].numpy()
+
+
 def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
     """One step through the public API from a pinned host buffer; returns bytes copied back."""
     import mojo_regex_b200 as mr
@@ -281,13 +291,18 @@ def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
             ml = rx.match_all(t)
             return int(ml.spans.nbytes)
         if cfg["op"] == "search_batch":
-            out = rx.search_batch(t, doc_stride=128, n_docs=shard.n_docs)
-            return int(out.nbytes)
+            out = rx.search_batch(t, doc_stride=128, n_docs=shard.n_docs, out=_pinned_i64(2 * shard.n_docs))
+            return int(2 * shard.n_docs * 8)
         if cfg["op"] == "sub":
-            return len(rx.sub(cfg["repl"], t))
+            hb = rx.sub_view(cfg["repl"], t)
+            nb = hb.n
+            hb.close()
+            return nb
         if cfg["op"] == "split":
-            data, offs = rx.split_raw(t)
-            return len(data) + int(offs.nbytes)
+            hp = rx.split_view(t)
+            nb = int(hp.data.nbytes) + int(hp.offsets.nbytes)
+            hp.close()
+            return nb
     finally:
         t.close()
     raise ValueError(cfg["op"])

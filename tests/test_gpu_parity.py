@@ -326,3 +326,49 @@ def test_findall_host_small_and_unpipelined_plans():
     empty = np.zeros(0, dtype=np.uint8)
     assert len(rx.match_all(empty)) == 0
     assert len(mr.compile_regex(r"(hello|world|foo)").match_all(empty)) == 0
+
+
+# ---- batch search through the reverse-automaton kernel (k_lines) -------------------------------------
+BATCH_PATTERNS = [
+    (corpora.CONFIGS["c3"]["pattern"], "ab.@-_%+Z9 \n"),
+    (r"[a-z]+[0-9]+", "ab1 2-"),
+    (r"[A-Z]{2}-[0-9]{3}", "AZ-019 "),
+    (r"(hello|world|foo)", "helowrdf "),
+    (r"(\d{3})(\d{3})(\d{4})", "0123456789 a"),
+    (r"[89]00[0-9]+", "8900 1a"),
+    (r"a+b", "ab c"),
+]
+
+
+@pytest.mark.parametrize("pattern,alphabet", BATCH_PATTERNS, ids=[p for p, _ in BATCH_PATTERNS])
+def test_search_batch_lines_kernel_against_oracle(pattern, alphabet):
+    import os
+
+    rng = random.Random(hash(pattern) & 0xFFFF)
+    rx = mr.compile_regex(pattern)
+    orx = oracle.compile(pattern)
+    assert rx.info().search_rev_states > 0
+    alpha = alphabet.encode()
+    # fixed-size documents (vector path): 64-byte documents, 3000 of them
+    text = np.frombuffer(bytes(rng.choice(alpha) for _ in range(64 * 3000)), dtype=np.uint8)
+    got = rx.search_batch(text, doc_stride=64)
+    for i in range(3000):
+        r = orx.search(text[64 * i:64 * i + 64])
+        assert tuple(got[i]) == (r if r else (-1, -1)), (pattern, i, bytes(text[64 * i:64 * i + 64]))
+    # ragged documents, some of them empty, last one short; odd stride -> byte path
+    cuts = sorted(set([0, text.size] + [rng.randrange(text.size) for _ in range(2000)]))
+    cuts = np.array(cuts + [text.size], dtype=np.int64)  # repeated last offset = empty document
+    got2 = rx.search_batch(text, doc_offsets=cuts)
+    for k in range(len(cuts) - 1):
+        r = orx.search(text[cuts[k]:cuts[k + 1]])
+        assert tuple(got2[k]) == (r if r else (-1, -1))
+    got3 = rx.search_batch(text, doc_stride=37)
+    for i in range(0, text.size // 37, 7):
+        r = orx.search(text[37 * i:37 * i + 37])
+        assert tuple(got3[i]) == (r if r else (-1, -1))
+    # the candidate-queue kernel (k_scan) must agree with the reverse-automaton kernel
+    os.environ["MRX_NO_LINES"] = "1"
+    try:
+        assert np.array_equal(rx.search_batch(text, doc_stride=64), got)
+    finally:
+        del os.environ["MRX_NO_LINES"]
