@@ -111,8 +111,9 @@ void *mrx_stream(void);
 /* Number of kernels this library has launched since mrx_init (bench.py's gpu_launches). */
 uint64_t mrx_launch_count(void);
 int mrx_synchronize(void);
-/* Measurement aid: when enabled, the dominant kernel of each matching call (k_scan / k_runs) is
- * bracketed by CUDA events on the library stream; mrx_last_kernel_ms() returns its duration. */
+/* Measurement aid: when enabled, the kernel a matching call is dominated by (k_dense / k_scan / k_runs /
+ * k_lines; for sub and split the whole kernel sequence from match list to assembled output) is bracketed
+ * by CUDA events on the library stream; mrx_last_kernel_ms() returns its duration. */
 int mrx_set_profiling(int enabled);
 double mrx_last_kernel_ms(void);
 

@@ -414,9 +414,12 @@ class CompiledRegex:
         return out
 
     def search_batch_device(self, text: "Text", out_ptr: int, n_docs: int, doc_stride: int = 0,
-                            doc_offsets_ptr: int = 0) -> None:
-        """Batch search with offsets / results already in HBM (out: n_docs x 2 int64)."""
+                            doc_offsets_ptr: int = 0, sync: bool = True) -> None:
+        """Batch search with offsets / results already in HBM (out: n_docs x 2 int64).  The kernels run on
+        the library stream; with sync=False the caller orders its own reads after them (stream_handle())."""
         _check(lib.mrx_search_batch(self._h, text._h, doc_offsets_ptr or None, n_docs, doc_stride, OUT_DEVICE, out_ptr))
+        if sync:
+            synchronize()
 
     def sub_device(self, repl, text: "Text", count: int = 0) -> "_DeviceBytes":
         r = _as_bytes(repl)

@@ -38,6 +38,7 @@ struct Lib {
   unsigned long long *scalars = nullptr; // [0] total, [1] best, [2..4] attempt_one out
   unsigned long long *h_scalars = nullptr;  // pinned mirror
   bool profiling = false;
+  bool prof_outer = false;  // sub / split bracket their whole kernel sequence; list jobs then do not record
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
 };
@@ -332,7 +333,7 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS; p.dominated = 0;
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
-    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     if (job.dense && !want_keys) {
       DenseParams dp{};
       dp.text = job.t->d; dp.n = n; dp.tile_origin = origin; dp.key_lo = job.key_lo; dp.key_hi = job.key_hi;
@@ -344,7 +345,7 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     } else {
       launch_scan(p, (int)tiles, g.stream);
     }
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     rc = read_scalars(0, 1);
@@ -399,9 +400,9 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max;
     p.n_tiles = (int)tiles; p.tile_carry = d_carry; p.spans = (int64_t *)spans; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
-    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     launch_runs(p, (int)tiles, g.stream);
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     if ((rc = read_scalars(0, 1))) { dev_release(spans); return rc; }
@@ -1089,9 +1090,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     lp.text = t->d; lp.n = n; lp.prog = re->d_search; lp.rev = re->d_rev_search;
     lp.rev_bytes = (int32_t)pl.rev.tbl.size(); lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
     lp.n_docs = (int64_t)n_docs; lp.out = outp;
-    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     launch_lines(lp, g.stream);
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     if (location == MRX_OUT_HOST) {
@@ -1113,9 +1114,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   const int64_t tiles = n_tiles_for(0, n - 1);
   if (tiles > 0) {
     p.n_tiles = (int)tiles;
-    if (g.profiling) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     launch_scan(p, (int)tiles, g.stream);
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
   }
   int64_t *outp = out_start_end;
@@ -1197,7 +1198,10 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   }
   if ((rc = ensure_uploaded(re))) return bail(rc);
   DevSpans ms;
-  if ((rc = match_list(re, t, p.search, re->d_search, ms))) return bail(rc);
+  if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  rc = match_list(re, t, p.search, re->d_search, ms);
+  g.prof_outer = false;
+  if (rc) return bail(rc);
   int64_t M = ms.n;
   if (count > 0 && M > count) M = count;
   DevTmp d_tpl, d_offs, d_desc, d_bad, d_tseg;
@@ -1237,6 +1241,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
     ap.repl_len = repl_len; ap.tpl_src = d_tpl.as<int32_t>(); ap.total = total; ap.out = (uint8_t *)d_out;
     launch_assemble(ap, g.stream);
     g.launches += total > 0 ? 1 : 0;
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
   }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)total;
@@ -1267,7 +1272,10 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "split on a windowed text: assemble per shard on whole buffers");
   if ((rc = ensure_uploaded(re))) return rc;
   DevSpans ms;
-  if ((rc = match_list(re, t, re->prog.findall, re->d_findall, ms))) return rc;
+  if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  rc = match_list(re, t, re->prog.findall, re->d_findall, ms);
+  g.prof_outer = false;
+  if (rc) return rc;
   struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
   int64_t M = ms.n;
   if (maxsplit < 0) M = 0;  // matcher.mojo:1386-1387 with splits_done(0) >= maxsplit
@@ -1307,6 +1315,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
     ap.repl_len = 0; ap.tpl_src = nullptr; ap.total = total; ap.out = (uint8_t *)d_bytes;
     launch_assemble(ap, g.stream);
     g.launches += total > 0 ? 1 : 0;
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
   }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)(M + 1);

@@ -241,10 +241,12 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         return OpResult(ds.n, n + 16 * ds.n, kernel, ds, base)
     if cfg["op"] == "search_batch":
         out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
-        rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128)
+        rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128, sync=False)
         if shard.world > 1:
             _gather_for(1, dev).gather([shard.n_docs])
-        return OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_lines" if rx.info().search_rev_states > 0 else "k_scan", None)
+        res = OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_lines" if rx.info().search_rev_states > 0 else "k_scan", None)
+        res.out = out  # keeps the result tensor alive until the caller drops the OpResult
+        return res
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
         base = 0
@@ -252,7 +254,7 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
             g = _gather_for(1, dev)
             g.gather([ob.n])
             base = g.base_offset()
-        return OpResult(n, n + ob.n, "k_runs", ob, base)
+        return OpResult(n, n + ob.n, "k_runs+k_seg_lengths+k_assemble", ob, base)
     if cfg["op"] == "split":
         pc = rx.split_device(shard.text)
         total = int(pc.offsets_tensor()[-1].item())
@@ -261,7 +263,7 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
             g = _gather_for(2, dev)
             g.gather([pc.n, total])
             base = g.base_offset()
-        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan", pc, base)
+        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan+k_seg_lengths+k_assemble", pc, base)
     raise ValueError(cfg["op"])
 
 
