@@ -223,10 +223,12 @@ int ensure_uploaded(mrx_regex *re) {
   if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
   if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
   if (re->prog.search.rev.valid && !re->d_rev_search) {
-    const std::vector<uint8_t> &tb = re->prog.search.rev.tbl;
+    const RevTable &rt = re->prog.search.rev;
+    std::vector<uint16_t> tb(rt.rev);
+    tb.insert(tb.end(), rt.fwd.begin(), rt.fwd.end());
     void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, tb.size()));
-    CUDA_TRY(cudaMemcpyAsync(d, tb.data(), tb.size(), cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMalloc(&d, tb.size() * 2));
+    CUDA_TRY(cudaMemcpyAsync(d, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     re->d_rev_search = static_cast<uint8_t *>(d);
   }
@@ -1087,8 +1089,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
       outp = d_out.as<int64_t>();
     }
     LinesParams lp{};
-    lp.text = t->d; lp.n = n; lp.prog = re->d_search; lp.rev = re->d_rev_search;
-    lp.rev_bytes = (int32_t)pl.rev.tbl.size(); lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
+    lp.text = t->d; lp.n = n; lp.tables = re->d_rev_search;
+    lp.rev_bytes = (int32_t)(pl.rev.rev.size() * 2); lp.fwd_bytes = (int32_t)(pl.rev.fwd.size() * 2);
+    lp.fwd_start = pl.rev.fwd_start; lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
     lp.n_docs = (int64_t)n_docs; lp.out = outp;
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     launch_lines(lp, g.stream);

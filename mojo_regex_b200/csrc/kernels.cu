@@ -651,76 +651,112 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
 // ---------------------------------------------------------------------------------------------
 // per-document search: match_next(doc, 0) for every document of a batch (the reference's
 // callers loop over dfa.mojo:2241-2253).  One thread per document.  Pass 1 walks the document BACKWARDS
-// through the reverse automaton (program.hpp: RevTable) -- one shared-memory lookup per byte, address
-// formed by a single PRMT (set id in byte 1, text byte in byte 0) -- and remembers the last flagged
-// position it sees, which is the leftmost position whose attempt succeeds: exactly the start the
-// reference's ascending loop over candidates returns.  Pass 2 runs that one attempt forwards for the
-// longest accept.  No candidate queue, no atomics, no divergence in pass 1.
+// through the reverse automaton (program.hpp: RevTable) -- one shared-memory lookup per byte, the same
+// 4-instruction step as k_dense -- and remembers the last flagged position it sees, which is the leftmost
+// position whose attempt succeeds: exactly the start the reference's ascending loop over candidates
+// returns.  Pass 2 runs that one attempt forwards through the dense forward table for the longest accept.
+// No candidate queue, no atomics, no divergence in pass 1.
+//
+// Fixed-size, 16-byte aligned documents are staged by TMA: every thread issues one bulk copy of its own
+// document into a row of `line_pitch` bytes (an odd number of 16-byte units, so the LDS.128 of a
+// quarter-warp hit 8 distinct bank groups); CTAs are persistent over batches of 256 documents so that the
+// tables are loaded once.  Ragged or unaligned documents are read from HBM byte by byte.
 struct LinesShared {
-  DevProg prog;
-  alignas(16) uint8_t rev[16];  // the whole table follows
+  alignas(8) uint64_t bar;
+  alignas(16) uint8_t tables[16];  // rev | fwd | staged documents follow
 };
+
+__device__ __forceinline__ void lines_emit(const uint8_t *fwd, uint32_t fwd_start, const uint8_t *doc_s,
+                                           const uint8_t *doc_g, int64_t len, int64_t best, int64_t *out) {
+  int64_t s_rel = -1, e_rel = -1;
+  if (best >= 0) {
+    // the attempt at `best` (dfa.mojo:1979-2026): longest accept, stop at the first dead transition
+    uint32_t s = fwd_start;
+    int64_t q = best, last = -1;
+    while (q < len) {
+      const uint32_t b = doc_s ? doc_s[q] : doc_g[q];
+      s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * b);
+      if (s == 0) break;
+      ++q;
+      if (s & 4u) last = q;
+    }
+    if (last >= 0) { s_rel = best; e_rel = last; }
+  }
+  st_span(out, s_rel, e_rel);
+}
 
 __global__ void __launch_bounds__(kThreads) k_lines(const LinesParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
-  load_prog(&sh.prog, prm.prog);
+  const int tid = threadIdx.x;
   {
-    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.rev);
-    uint4 *d4 = reinterpret_cast<uint4 *>(sh.rev);
-    for (int i = threadIdx.x; i < prm.rev_bytes / 16; i += kThreads) d4[i] = s4[i];
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.tables);
+    uint4 *d4 = reinterpret_cast<uint4 *>(sh.tables);
+    for (int i = tid; i < (prm.rev_bytes + prm.fwd_bytes) / 16; i += kThreads) d4[i] = s4[i];
+  }
+  if (tid == 0 && prm.staged) {
+    mbar_init(&sh.bar, 1);
+    fence_proxy_async();
   }
   __syncthreads();
-  const int64_t d = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (d >= prm.n_docs) return;
-  const int64_t lo = prm.doc_offsets ? prm.doc_offsets[d] : d * prm.doc_stride;
-  const int64_t hi = prm.doc_offsets ? prm.doc_offsets[d + 1] : min(lo + prm.doc_stride, prm.n);
-  const uint8_t *rev = sh.rev;
-  int64_t best = -1;
-  uint32_t r = 0;  // last table entry: set id (bits 0..6) | flag (bit 7); set 0 = the accepting states
-  const bool vec = prm.doc_offsets == nullptr && (prm.doc_stride & 15) == 0 && hi - lo == prm.doc_stride &&
-                   (reinterpret_cast<uintptr_t>(prm.text + lo) & 15) == 0;
-  if (vec) {
-    const uint4 *v = reinterpret_cast<const uint4 *>(prm.text + lo);
-    const int nv = (int)(prm.doc_stride >> 4);
-    uint32_t best_pk = 0;
-    int best_word = -1;  // index of the 4-byte word (from lo) that holds the leftmost flagged byte
+  const uint8_t *rev = sh.tables, *fwd = sh.tables + prm.rev_bytes;
+  const int64_t n_batches = (prm.n_docs + kThreads - 1) / kThreads;
+
+  if (prm.staged) {
+    uint8_t *lines = sh.tables + prm.rev_bytes + prm.fwd_bytes;
+    uint8_t *mine = lines + (size_t)tid * prm.line_pitch;
+    const int stride = (int)prm.doc_stride, nv = stride >> 4;
+    int it = 0;
+    for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
+      const int64_t d = batch * kThreads + tid;
+      const int in_batch = (int)min((int64_t)kThreads, prm.n_docs - batch * kThreads);
+      if (tid == 0) mbar_expect_tx(&sh.bar, (uint32_t)in_batch * (uint32_t)stride);
+      __syncthreads();  // expect_tx is posted before any copy can complete
+      if (d < prm.n_docs) tma_bulk_g2s(mine, prm.text + d * stride, (uint32_t)stride, &sh.bar);
+      mbar_wait(&sh.bar, (uint32_t)(it & 1));
+      if (d < prm.n_docs) {
+        uint32_t r = 0, best_pk = 0;
+        int best_word = -1;  // index of the 4-byte word that holds the leftmost flagged byte
 #pragma unroll 2
-    for (int k = nv - 1; k >= 0; --k) {
-      const uint4 w4 = __ldg(v + k);
-      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+        for (int k = nv - 1; k >= 0; --k) {
+          const uint4 w4 = *reinterpret_cast<const uint4 *>(mine + 16 * k);
+          const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-      for (int wi = 3; wi >= 0; --wi) {
-        uint32_t pk = 0;
+          for (int wi = 3; wi >= 0; --wi) {
+            uint32_t pk = 0;
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-          const uint32_t addr = __byte_perm(ws[wi], r, 0x5540 + j) & 0x7fffu;  // (set id << 8) | byte j
-          r = rev[addr];
-          pk = __byte_perm(pk, r, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);
+            for (int j = 3; j >= 0; --j) {
+              const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + j);
+              uint32_t addr;
+              asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(r));
+              r = *reinterpret_cast<const uint16_t *>(rev + addr);
+              pk = __byte_perm(pk, r, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);
+            }
+            if (pk & 0x04040404u) { best_pk = pk; best_word = 4 * k + wi; }
+          }
         }
-        if (pk & 0x80808080u) { best_pk = pk; best_word = 4 * k + wi; }
+        const int64_t best = best_word >= 0 ? 4 * best_word + ((__ffs(best_pk & 0x04040404u) - 1) >> 3) : -1;
+        lines_emit(fwd, (uint32_t)prm.fwd_start, mine, nullptr, stride, best, prm.out + 2 * d);
       }
+      __syncthreads();  // every thread is done with its row before the next batch lands in it
     }
-    if (best_word >= 0) best = lo + 4 * best_word + ((__ffs(best_pk & 0x80808080u) - 1) >> 3);
-  } else {
-    for (int64_t q = hi - 1; q >= lo; --q) {
-      r = rev[((r & 0x7fu) << 8) | prm.text[q]];
-      if (r & 0x80u) best = q;
+    return;
+  }
+
+  for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
+    const int64_t d = batch * kThreads + tid;
+    if (d >= prm.n_docs) break;
+    const int64_t lo = prm.doc_offsets ? prm.doc_offsets[d] : d * prm.doc_stride;
+    const int64_t hi = prm.doc_offsets ? prm.doc_offsets[d + 1] : min(lo + prm.doc_stride, prm.n);
+    const uint8_t *doc = prm.text + lo;
+    int64_t best = -1;
+    uint32_t r = 0;
+    for (int64_t q = hi - lo - 1; q >= 0; --q) {
+      r = *reinterpret_cast<const uint16_t *>(rev + r + 2u * doc[q]);
+      if (r & 4u) best = q;
     }
+    lines_emit(fwd, (uint32_t)prm.fwd_start, nullptr, doc, hi - lo, best, prm.out + 2 * d);
   }
-  int64_t s_rel = -1, e_rel = -1;
-  if (best >= 0) {
-    Attempt at;
-    at.p = &sh.prog;
-    at.tv.g = prm.text;
-    at.tv.s = nullptr;
-    at.tv.s_begin = at.tv.s_end = 0;
-    at.lo = lo;
-    at.n = hi;
-    const int64_t e = at.dfa(best);
-    if (e >= 0) { s_rel = best - lo; e_rel = e - lo; }
-  }
-  st_span(prm.out + 2 * d, s_rel, e_rel);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1414,15 +1450,30 @@ void launch_scan(const ScanParams &p, int grid, cudaStream_t st) {
     default: launch_scan_t<FILT_LUT>(p, grid, st); break;
   }
 }
-void launch_lines(const LinesParams &p, cudaStream_t st) {
+void launch_lines(LinesParams p, cudaStream_t st) {
   if (p.n_docs <= 0) return;
-  const int smem = (int)sizeof(LinesShared) + p.rev_bytes;
+  // staging: fixed-size documents, 16-byte aligned, all of them complete, rows fit next to the tables
+  int pitch = (int)p.doc_stride;
+  if (((pitch >> 4) & 1) == 0) pitch += 16;  // odd number of 16-byte units per row
+  const int tables = p.rev_bytes + p.fwd_bytes;
+  const bool staged = p.doc_offsets == nullptr && p.doc_stride >= 16 && (p.doc_stride & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(p.text) & 15) == 0 && p.n_docs * p.doc_stride <= p.n &&
+                      tables + kThreads * pitch <= 56 * 1024;
+  p.staged = staged ? 1 : 0;
+  p.line_pitch = pitch;
+  const int smem = (int)sizeof(LinesShared) + tables + (staged ? kThreads * pitch : 0);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
   }
-  k_lines<<<(unsigned)((p.n_docs + kThreads - 1) / kThreads), kThreads, smem, st>>>(p);
+  int per_sm = 0, dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lines, kThreads, smem);
+  const int64_t n_batches = (p.n_docs + kThreads - 1) / kThreads;
+  const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+  k_lines<<<(unsigned)(n_batches < resident ? n_batches : resident), kThreads, smem, st>>>(p);
 }
 template <int FILT>
 static void launch_runs_t(const RunsParams &p, int grid, cudaStream_t st) {

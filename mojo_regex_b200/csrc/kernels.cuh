@@ -98,13 +98,15 @@ struct DenseParams {
 struct LinesParams {
   const uint8_t *text;
   int64_t n;
-  const DevProg *prog;         // forward automaton (longest accept from the winning start)
-  const uint8_t *rev;          // RevTable::tbl in HBM
-  int32_t rev_bytes;           // n_rev * 256
+  const uint8_t *tables;       // RevTable::rev followed by RevTable::fwd, in HBM (16-byte aligned sizes)
+  int32_t rev_bytes, fwd_bytes;
+  int32_t fwd_start;           // row offset of the forward start state
   const int64_t *doc_offsets;  // n_docs + 1 entries, or nullptr for fixed-size documents
   int64_t doc_stride;
   int64_t n_docs;
   int64_t *out;                // (start, end) relative to the document, (-1, -1) = no match
+  int32_t staged;              // 1: fixed-size, 16-byte aligned documents staged through shared memory by TMA
+  int32_t line_pitch;          // shared-memory bytes per staged document (odd multiple of 16)
 };
 
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };
@@ -138,7 +140,7 @@ struct AsmParams {
 };
 
 void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
-void launch_lines(const LinesParams &p, cudaStream_t st);
+void launch_lines(LinesParams p, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,

@@ -424,17 +424,18 @@ void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
 
 bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
   rt = RevTable();
-  if (pl.unsupported || pl.shortcut || p.n_states <= 0 || p.n_states > 64 || p.start_accepting()) return false;
+  if (pl.unsupported || pl.shortcut || p.n_states <= 0 || p.n_states > 32 || p.start_accepting()) return false;
   if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) return false;
   if (pl.mode != MRX_MODE_FIRST_CLASS && pl.mode != MRX_MODE_EVERY_POS && pl.mode != MRX_MODE_UNIFORM_RUN) return false;
   const int n = p.n_states, s0 = p.start_state;
+  constexpr int kMaxRev = 48;
   uint64_t acc = 0;
   for (int q = 0; q < n; ++q) if (p.accepting[q]) acc |= 1ull << q;
   std::vector<uint64_t> sets{acc};
   std::map<uint64_t, int> ids{{acc, 0}};
-  std::vector<uint8_t> tbl;
+  std::vector<int> next;  // next[i * 256 + b] = set id
   for (size_t i = 0; i < sets.size(); ++i) {
-    tbl.resize((i + 1) * 256);
+    next.resize((i + 1) * 256);
     const uint64_t S = sets[i];
     for (int b = 0; b < 256; ++b) {
       uint64_t T = 0;
@@ -442,24 +443,38 @@ bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
         const int nx = p.next(q, b);
         if (nx != kDead && ((S >> nx) & 1)) T |= 1ull << q;
       }
-      const bool flag = ((T >> s0) & 1) && pl.cand[b];
+      // "an attempt at this byte succeeds" must coincide with "the start state is in the new set": the
+      // reference only attempts at candidate bytes, so a live first byte that is not a candidate cannot
+      // be expressed as a row flag
+      if (((T >> s0) & 1) && !pl.cand[b]) return false;
       T |= acc;
       auto it = ids.find(T);
       int id;
       if (it == ids.end()) {
-        if (sets.size() >= 128) return false;
+        if ((int)sets.size() >= kMaxRev) return false;
         id = (int)sets.size();
         ids.emplace(T, id);
         sets.push_back(T);
       } else {
         id = it->second;
       }
-      tbl[i * 256 + b] = (uint8_t)(id | (flag ? 0x80 : 0));
+      next[i * 256 + b] = id;
     }
   }
-  rt.valid = true;
+  auto rev_off = [&](int id) { return 520 * id + (((sets[id] >> s0) & 1) ? 4 : 0); };
   rt.n_rev = (int)sets.size();
-  rt.tbl = std::move(tbl);
+  rt.rev.assign(((size_t)(520 * rt.n_rev + 8 + 15) & ~(size_t)15) / 2, 0);
+  for (int i = 0; i < rt.n_rev; ++i)
+    for (int b = 0; b < 256; ++b) rt.rev[(size_t)rev_off(i) / 2 + b] = (uint16_t)rev_off(next[(size_t)i * 256 + b]);
+  auto fwd_off = [&](int q) { return 520 * (q + 1) + (p.accepting[q] ? 4 : 0); };
+  rt.fwd.assign(((size_t)(520 * (n + 1) + 8 + 15) & ~(size_t)15) / 2, 0);  // row 0 = dead: every entry 0
+  for (int q = 0; q < n; ++q)
+    for (int b = 0; b < 256; ++b) {
+      const int nx = p.next(q, b);
+      rt.fwd[(size_t)fwd_off(q) / 2 + b] = nx == kDead ? 0 : (uint16_t)fwd_off(nx);
+    }
+  rt.fwd_start = (uint16_t)fwd_off(s0);
+  rt.valid = true;
   return true;
 }
 

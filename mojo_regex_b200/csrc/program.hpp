@@ -60,15 +60,20 @@ struct DenseTable {
   std::vector<uint8_t> out_len;  // n_states - acc_base
 };
 
-// Reverse search automaton for per-document search (k_lines).  Scanning a document from its last byte
-// to its first, the state after byte i is the set R(i) of forward states from which text[i..] reaches an
-// accepting state; an attempt of the reference at i succeeds exactly when the start state is in R(i).
-// Subset construction over those sets: entry (r, byte) = next set id | 0x80 when "an attempt starting
-// at this byte succeeds and the byte is a candidate of the plan".  At most 128 sets, 256 bytes per row.
+// Automata of the per-document search kernel (k_lines), both in the layout of DenseTable: uint16 entries
+// holding the byte offset of the next row, rows 520 bytes apart (bank skew), flag in bit 2 of a row offset.
+//  rev: scanning a document from its last byte to its first, the state after byte i is the set R(i) of
+//       forward states from which text[i..] reaches an accepting state (subset construction over those
+//       sets).  An attempt of the reference at i succeeds exactly when the start state is in R(i); rows of
+//       such sets carry the flag.  Row 0 (offset 0) is the set of accepting states = the state at the
+//       document's end.
+//  fwd: the reference's automaton itself, one row per state plus a dead row at offset 0; rows of accepting
+//       states carry the flag.  fwd_start = row offset of the start state.
 struct RevTable {
   bool valid = false;
   int32_t n_rev = 0;
-  std::vector<uint8_t> tbl;  // n_rev * 256
+  std::vector<uint16_t> rev, fwd;  // whole tables (bytes / 2 entries each)
+  uint16_t fwd_start = 0;
 };
 
 struct Plan {

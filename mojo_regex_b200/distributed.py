@@ -240,13 +240,15 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
         return OpResult(ds.n, n + 16 * ds.n, kernel, ds, base)
     if cfg["op"] == "search_batch":
-        out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
+        # the caller-provided result array lives with the shard (allocated once, like the text)
+        out = getattr(shard, "_batch_out", None)
+        if out is None:
+            out = shard._batch_out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
+            shard._batch_kernel = "k_lines" if rx.info().search_rev_states > 0 else "k_scan"
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128, sync=False)
         if shard.world > 1:
             _gather_for(1, dev).gather([shard.n_docs])
-        res = OpResult(shard.n_docs, n + 16 * shard.n_docs, "k_lines" if rx.info().search_rev_states > 0 else "k_scan", None)
-        res.out = out  # keeps the result tensor alive until the caller drops the OpResult
-        return res
+        return OpResult(shard.n_docs, n + 16 * shard.n_docs, shard._batch_kernel, None)
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
         base = 0
