@@ -1296,50 +1296,46 @@ __global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mo
   }
 }
 
-// Output-stationary assembly: thread = 16 consecutive output bytes, one aligned STG.128 each (a warp
-// writes 512 contiguous bytes).  The segment holding the chunk's first byte is found by a binary search
-// over `offs`, restricted by `tile_seg` to the handful of segments that touch this CTA's output tile
-// (they stay in L1); the chunk is then filled byte by byte, walking segments: gap bytes come from the
-// text, replacement bytes from the flattened template (tpl_src[r] >= 0: text[match_start + tpl_src[r]],
-// < 0: the literal byte -1 - tpl_src[r]), then the extra byte of a zero-width match.  Text bytes are
-// read through a one-word cache (consecutive bytes of a gap share an aligned 32-bit load).
+// Output-stationary assembly, one CTA per 16 KiB of output.
+//
+// The segments that touch the tile (tile_seg gives the window) are read once, in blocks of consecutive
+// segments per thread; those with output bytes are compacted into records {output offset, search position,
+// gap length} in shared memory, and a bitmap over the tile's 16384 output positions gets a bit where each of
+// them starts.  Then every lane produces 4 consecutive output bytes per step (a warp writes 128 contiguous
+// bytes, STG.32): the record of an output byte is rank(bitmap, position) -- one popcount for the first byte
+// of the word, the next bit for each following byte -- so there is no search and no per-lane walk, and the
+// lanes of a warp read consecutive text bytes.  Gap bytes come from the text, replacement bytes from the
+// flattened template (tpl_src[r] >= 0: text[match_start + tpl_src[r]], < 0: the literal byte -1 - tpl_src[r]),
+// then the extra byte of a zero-width match.  Tiles whose window exceeds the record capacity, or whose
+// relative coordinates do not fit 32 bits, take the generic per-thread walk (assemble_tile_slow).
 struct SegCursor {
   int64_t j, O, O_next, pos, s, gap;
 };
-// Segment records of one output tile, staged in shared memory by coalesced loads: output offset, search
-// position and match start of segment lo_seg + k, relative to the first segment's (32 bits each).
 struct AsmShared {
-  uint32_t O[kAsmSegCap + 1];
-  uint32_t pos[kAsmSegCap];
-  uint32_t s[kAsmSegCap];
+  uint4 rec[kAsmSegCap];          // segment lo_seg + k: x = output offset (relative to O_base), y = search
+                                  //    position (relative to x_base), z = gap length
+  uint16_t nzk[kAsmSegCap];       // k of the r-th segment that has output bytes (in output order)
+  uint32_t bits[kAsmTile / 32];   // a set bit = such a segment starts at this output position of the tile
+  uint32_t wprefix[kAsmTile / 32];
+  int32_t tpl[kAsmTplCap];        // flattened replacement template
+  int scan_ws[kThreads / 32 + 2];
 };
 __device__ __forceinline__ int64_t seg_pos_ldg(const AsmParams &p, int64_t j) {
   if (j == 0) return 0;
   const int64_t ps = __ldg(p.spans + 2 * (j - 1)), pe = __ldg(p.spans + 2 * (j - 1) + 1);
   return (p.mode == SEG_SPLIT) ? pe : (pe == ps ? pe + 1 : pe);
 }
-template <bool FAST>
-__device__ __forceinline__ void seg_load(const AsmParams &p, const AsmShared &sh, int64_t lo_seg, int64_t O_base,
-                                         int64_t x_base, int64_t j, SegCursor &c) {
+__device__ __forceinline__ void seg_load(const AsmParams &p, int64_t j, SegCursor &c) {
   c.j = j;
-  if (FAST) {
-    const int k = (int)(j - lo_seg);
-    c.O = O_base + sh.O[k];
-    c.O_next = O_base + sh.O[k + 1];
-    c.pos = x_base + sh.pos[k];
-    c.s = x_base + sh.s[k];
-  } else {
-    c.O = __ldg(p.offs + j);
-    c.O_next = __ldg(p.offs + j + 1);
-    c.pos = seg_pos_ldg(p, j);
-    c.s = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
-  }
+  c.O = __ldg(p.offs + j);
+  c.O_next = __ldg(p.offs + j + 1);
+  c.pos = seg_pos_ldg(p, j);
+  c.s = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
   c.gap = c.s > c.pos ? c.s - c.pos : 0;
 }
 
-template <bool FAST>
-__device__ __forceinline__ void assemble_tile(const AsmParams &p, const AsmShared &sh, int64_t tile, int64_t lo_seg,
-                                              int64_t hi_seg, int64_t O_base, int64_t x_base) {
+// generic path: thread = 16 consecutive output bytes, binary search over offs, byte-by-byte walk
+__device__ __forceinline__ void assemble_tile_slow(const AsmParams &p, int64_t tile, int64_t lo_seg, int64_t hi_seg) {
   uint32_t cw = 0;         // cached aligned text word (aligned in the address space: the text itself
   uintptr_t cw_addr = 1;   // may start at any byte of a wrapped tensor); a word that holds a valid byte
                            // never leaves that byte's 32-byte sector, so the over-read is harmless
@@ -1356,33 +1352,20 @@ __device__ __forceinline__ void assemble_tile(const AsmParams &p, const AsmShare
   for (int r = 0; r < kAsmRounds; ++r) {
     const int64_t o0 = tile * kAsmTile + ((int64_t)r * kThreads + threadIdx.x) * 16;
     if (o0 >= p.total) return;
-    // largest j in [lo_seg, hi_seg] with offs[j] <= o0
-    int64_t j0;
-    if (FAST) {
-      const uint32_t key = (uint32_t)(o0 - O_base);
-      int lo = 0, hi = (int)(hi_seg - lo_seg);
-      while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (sh.O[mid] <= key) lo = mid; else hi = mid - 1;
-      }
-      j0 = lo_seg + lo;
-    } else {
-      int64_t lo = lo_seg, hi = hi_seg;
-      while (lo < hi) {
-        const int64_t mid = (lo + hi + 1) >> 1;
-        if (__ldg(p.offs + mid) <= o0) lo = mid; else hi = mid - 1;
-      }
-      j0 = lo;
+    int64_t lo = lo_seg, hi = hi_seg;  // largest j in [lo_seg, hi_seg] with offs[j] <= o0
+    while (lo < hi) {
+      const int64_t mid = (lo + hi + 1) >> 1;
+      if (__ldg(p.offs + mid) <= o0) lo = mid; else hi = mid - 1;
     }
     SegCursor c;
-    seg_load<FAST>(p, sh, lo_seg, O_base, x_base, j0, c);
+    seg_load(p, lo, c);
     uint32_t w[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
       const int64_t o = o0 + k;
       uint32_t b = 0;
       if (o < p.total) {
-        while (o >= c.O_next) seg_load<FAST>(p, sh, lo_seg, O_base, x_base, c.j + 1, c);
+        while (o >= c.O_next) seg_load(p, c.j + 1, c);
         const int64_t d = o - c.O;
         if (d < c.gap) {
           b = rd(c.pos + d);
@@ -1405,6 +1388,7 @@ __device__ __forceinline__ void assemble_tile(const AsmParams &p, const AsmShare
 __global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AsmShared &sh = *reinterpret_cast<AsmShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31;
   const int64_t tile = blockIdx.x;
   const int64_t lo_seg = __ldg(p.tile_seg + tile);
   const int64_t hi_seg = (tile + 1 < p.n_tiles) ? __ldg(p.tile_seg + tile + 1) : p.M;
@@ -1412,22 +1396,97 @@ __global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
   const int64_t O_base = __ldg(p.offs + lo_seg), O_end = __ldg(p.offs + hi_seg + 1);
   const int64_t x_base = seg_pos_ldg(p, lo_seg);
   const int64_t x_last = hi_seg < p.M ? __ldg(p.spans + 2 * hi_seg + 1) + 1 : p.n + 1;  // bounds every pos / s of the window
-  const bool fast = cnt <= kAsmSegCap && O_end - O_base < 0xfffffff0ll && x_last - x_base < 0xfffffff0ll;
-  if (fast) {
-    for (int k = threadIdx.x; k < (int)cnt; k += kThreads) {
-      const int64_t j = lo_seg + k;
-      const int64_t pj = seg_pos_ldg(p, j);
-      int64_t sj = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
-      if (sj < pj) sj = pj;  // tail segment after a zero-width match at n: empty gap
-      sh.O[k] = (uint32_t)(__ldg(p.offs + j) - O_base);
-      sh.pos[k] = (uint32_t)(pj - x_base);
-      sh.s[k] = (uint32_t)(sj - x_base);
+  const bool fast = cnt <= kAsmSegCap && p.repl_len <= kAsmTplCap && O_end - O_base < 0xfffffff0ll &&
+                    x_last - x_base < 0xfffffff0ll;
+  if (!fast) {
+    assemble_tile_slow(p, tile, lo_seg, hi_seg);
+    return;
+  }
+  const int64_t tile_lo = tile * kAsmTile;
+  const uint32_t tile_rel = (uint32_t)(tile_lo - O_base);  // tile start in record coordinates (>= 0: lo_seg owns it)
+  const int n = (int)cnt;
+  {  // the tile's text is first touched in the output loop: start pulling it into L2 now (one line per thread)
+    const int64_t x = x_base + tile_rel + (int64_t)tid * 128;  // the tile starts about tile_rel bytes into lo_seg's gap
+    if (x < x_last && x < p.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.text + x));
+  }
+  for (int i = tid; i < kAsmTile / 32; i += kThreads) sh.bits[i] = 0;
+  for (int i = tid; i < (int)p.repl_len; i += kThreads) sh.tpl[i] = __ldg(p.tpl_src + i);
+  // ---- records, one per segment of the window, loaded round-robin (coalesced)
+  for (int k = tid; k < n; k += kThreads) {
+    const int64_t j = lo_seg + k;
+    const int64_t pj = seg_pos_ldg(p, j);
+    const int64_t sj = j < p.M ? __ldg(p.spans + 2 * j) : p.n;
+    sh.rec[k] = make_uint4((uint32_t)(__ldg(p.offs + j) - O_base), (uint32_t)(pj - x_base),
+                           (uint32_t)(sj > pj ? sj - pj : 0), 0u);
+  }
+  __syncthreads();
+  // ---- a bit where every segment with output bytes starts (the owner of the tile's first byte: bit 0)
+  const uint32_t end_rel = (uint32_t)(O_end - O_base);
+  for (int k = tid; k < n; k += kThreads) {
+    const uint32_t Ok = sh.rec[k].x, On = (k + 1 < n) ? sh.rec[k + 1].x : end_rel;
+    if (On > Ok && Ok < tile_rel + (uint32_t)kAsmTile) {
+      const uint32_t bpos = Ok > tile_rel ? Ok - tile_rel : 0u;
+      atomicOr(&sh.bits[bpos >> 5], 1u << (bpos & 31u));
     }
-    if (threadIdx.x == 0) sh.O[cnt] = (uint32_t)(O_end - O_base);
-    __syncthreads();
-    assemble_tile<true>(p, sh, tile, lo_seg, hi_seg, O_base, x_base);
-  } else {
-    assemble_tile<false>(p, sh, tile, lo_seg, hi_seg, O_base, x_base);
+  }
+  __syncthreads();
+  // ---- exclusive prefix popcount of the bitmap words (512 words, two per thread)
+  {
+    const int c0 = __popc(sh.bits[2 * tid]), c1 = __popc(sh.bits[2 * tid + 1]);
+    int tot;
+    const int ex = block_exclusive_scan(c0 + c1, sh.scan_ws, &tot);
+    sh.wprefix[2 * tid] = (uint32_t)ex;
+    sh.wprefix[2 * tid + 1] = (uint32_t)(ex + c0);
+  }
+  __syncthreads();
+  // ---- rank of every marked segment -> its k
+  for (int k = tid; k < n; k += kThreads) {
+    const uint32_t Ok = sh.rec[k].x, On = (k + 1 < n) ? sh.rec[k + 1].x : end_rel;
+    if (On > Ok && Ok < tile_rel + (uint32_t)kAsmTile) {
+      const uint32_t bpos = Ok > tile_rel ? Ok - tile_rel : 0u;
+      const int r = (int)sh.wprefix[bpos >> 5] + __popc(sh.bits[bpos >> 5] & ((1u << (bpos & 31u)) - 1u));
+      sh.nzk[r] = (uint16_t)k;
+    }
+  }
+  __syncthreads();
+  // ---- output: lane = 4 consecutive bytes per step, straight-line code, one text load per byte
+  const uint8_t *xb = p.text + x_base;
+  const uint32_t repl = (uint32_t)p.repl_len;
+  const uint32_t total_rel = (uint32_t)min((int64_t)kAsmTile, p.total - tile_lo);  // live bytes of this tile
+#pragma unroll 1
+  for (int st = 0; st < kAsmTile / (4 * kThreads); ++st) {
+    const uint32_t t0 = (uint32_t)(st * kThreads + tid) * 4u;  // tile-relative position of this lane's word
+    if (t0 >= total_rel) break;
+    const uint32_t bw = sh.bits[t0 >> 5];
+    const int sh5 = (int)(t0 & 31u);
+    int rk = (int)sh.wprefix[t0 >> 5] + __popc(bw & ((2u << sh5) - 1u)) - 1;  // record of byte 0 (>= 0)
+    uint4 rc = sh.rec[sh.nzk[rk]];
+    uint32_t off[4], lit[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (b > 0 && ((bw >> (sh5 + b)) & 1u)) rc = sh.rec[sh.nzk[++rk]];
+      const uint32_t d = tile_rel + t0 + b - rc.x;  // offset inside the segment
+      uint32_t o = rc.y + d;                        // gap byte
+      uint32_t l = 0x100u;                          // >= 0x100: take the loaded text byte
+      if (d >= rc.z) {
+        const uint32_t q = d - rc.z;
+        o = rc.y;                                   // zero-width match: the byte at the search position
+        if (q < repl) {
+          const int32_t src = sh.tpl[q];
+          if (src >= 0) o = rc.y + rc.z + (uint32_t)src; else l = (uint32_t)(-1 - src);
+        }
+      }
+      if (t0 + b >= total_rel) { o = rc.y; l = 0; }  // past the end of the output: zero
+      off[b] = o;
+      lit[b] = l;
+    }
+    uint32_t word = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const uint32_t by = lit[b] < 0x100u ? lit[b] : (uint32_t)__ldg(xb + off[b]);
+      word |= by << (8 * b);
+    }
+    *reinterpret_cast<uint32_t *>(p.out + tile_lo + t0) = word;
   }
 }
 

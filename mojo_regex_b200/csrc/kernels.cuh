@@ -123,7 +123,8 @@ struct SubTemplate {
 // sub / split output assembly (k_assemble): one CTA per kAsmTile output bytes
 constexpr int kAsmRounds = 4;
 constexpr int kAsmTile = kThreads * 16 * kAsmRounds;  // 16 KiB
-constexpr int kAsmSegCap = 4096;                       // segment records staged per tile (48 KiB)
+constexpr int kAsmSegCap = 2560;                       // segment records staged per tile (40 KiB)
+constexpr int kAsmTplCap = 256;                        // replacement bytes staged per tile
 struct AsmParams {
   const uint8_t *text;
   int64_t n;
