@@ -195,7 +195,10 @@ def run_gpu(args):
     torch.cuda.set_device(local_rank)
     mr.init(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
     cfg = corpora.CONFIGS[args.config]
     size = args.size or default_size(args.config)
@@ -238,6 +241,7 @@ def run_gpu(args):
             units = res.units
             alg_bytes = res.algorithmic_bytes
             res.close()
+        mrd.join_exchanges(lib_stream)  # the count all-gathers run on their own stream: include them
         ev1.record(lib_stream)
     sync_all()
     dev_ms = ev0.elapsed_time(ev1)
@@ -246,11 +250,13 @@ def run_gpu(args):
     mr.set_profiling(False)
     if t_end - t_begin < 1.0:
         # the timed region is shorter than nvidia-smi's sampling period: keep the GPU under the very same
-        # load (untimed) for ~1.2 s so that the clock record is taken under load, not around it
+        # kernels (untimed, and WITHOUT the count all-gather: the number of iterations is time based and
+        # differs between ranks) for ~1.2 s so that the clock record is taken under load, not around it
         t_begin = time.time()
         while time.time() - t_begin < 1.2:
-            step_device().close()
-        sync_all()
+            mrd.run_op_local(rx, cfg, shard).close()
+        torch.cuda.synchronize()
+        mr.synchronize()
         t_end = time.time()
     clk = clocks.stop(t_begin, t_end)
 

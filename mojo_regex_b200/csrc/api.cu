@@ -1217,7 +1217,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
       flat.push_back(tpl.group_off[k] >= 0 ? tpl.group_off[k] + i : -1 - (int32_t)repl[tpl.lit_off[k] + i]);
   if ((rc = d_tpl.get(sizeof(int32_t) * (flat.size() + 4)))) return bail(rc);
   if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(d_tpl.p, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, g.stream));
-  const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
+  const int64_t seg_tiles = (M + 1 + kSegTile - 1) / kSegTile;
   const int64_t out_bound = n + M * (repl_len + 1) + 1;
   if ((rc = d_offs.get(sizeof(int64_t) * (M + 2)))) return bail(rc);
   if ((rc = d_desc.get(sizeof(unsigned long long) * seg_tiles))) return bail(rc);
@@ -1287,7 +1287,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   out->_owner = own;
   auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
   DevTmp d_desc, d_bad, d_tseg;
-  const int64_t seg_tiles = (M + 1 + kThreads - 1) / kThreads;
+  const int64_t seg_tiles = (M + 1 + kSegTile - 1) / kSegTile;
   void *d_offs = nullptr;
   if ((rc = dev_alloc(sizeof(int64_t) * (M + 2), &d_offs))) return bail(rc);
   own->dev[1] = d_offs;

@@ -1245,37 +1245,56 @@ __device__ __forceinline__ int64_t seg_pos(const int64_t *spans, int64_t j, int 
   return e == s ? e + 1 : e;
 }
 
-__global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
-                              unsigned long long *desc, unsigned int *ticket, int64_t *offs /* M+2 */,
-                              int *bad, int n_tiles, int64_t *tile_seg) {
+// Output offset of every segment = exclusive scan of the segment lengths.  A CTA owns kSegTile = 2048
+// consecutive segments: warp w takes the 256 from w * 256 on, in 8 rounds of 32 (lane = segment, so the
+// span loads and the offset stores are coalesced); a shuffle scan per round with a running carry, a scan of
+// the 8 warp totals, one decoupled look-back per CTA.
+__global__ void __launch_bounds__(kThreads) k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode,
+                                                          int64_t repl_len, unsigned long long *desc,
+                                                          unsigned int *ticket, int64_t *offs /* M+2 */, int *bad,
+                                                          int n_tiles, int64_t *tile_seg) {
   __shared__ int s_tile;
   __shared__ long long s_warp[kThreads / 32];
   __shared__ unsigned long long s_base;
   if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
   __syncthreads();
   const int tile = s_tile;
-  const int64_t j = (int64_t)tile * kThreads + threadIdx.x;  // 0..M (M = tail gap)
-  long long len = 0;
-  if (j <= M) {
-    const int64_t pos = seg_pos(spans, j, mode);
-    const int64_t gap_end = (j < M) ? spans[2 * j] : n;
-    long long gap = gap_end - pos;
-    if (j == M && gap < 0) gap = 0;  // pos may be n + 1 after a zero-width match at n
-    if (gap < 0) { if (mode == SEG_SPLIT) *bad = 1; gap = 0; }
-    len = gap;
-    if (j < M && mode == SEG_SUB) {
-      len += repl_len;
-      if (spans[2 * j] == spans[2 * j + 1] && pos < n) len += 1;
-    }
-  }
-  long long inc = len;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t j0 = (int64_t)tile * kSegTile + (int64_t)warp * (32 * kSegRounds) + lane;  // 0..M (M = tail gap)
+  long long len[kSegRounds], excl[kSegRounds];
+  long long carry = 0;  // sum of this warp's earlier rounds
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
+  for (int r = 0; r < kSegRounds; ++r) {
+    const int64_t j = j0 + 32 * r;
+    long long l = 0;
+    if (j <= M) {
+      int64_t pos = 0;
+      if (j > 0) {
+        const longlong2 pv = __ldg(reinterpret_cast<const longlong2 *>(spans) + (j - 1));
+        pos = (mode == SEG_SPLIT) ? pv.y : (pv.y == pv.x ? pv.y + 1 : pv.y);
+      }
+      longlong2 cur = make_longlong2(n, n);
+      if (j < M) cur = __ldg(reinterpret_cast<const longlong2 *>(spans) + j);
+      long long gap = cur.x - pos;
+      if (j == M && gap < 0) gap = 0;  // pos may be n + 1 after a zero-width match at n
+      if (gap < 0) { if (mode == SEG_SPLIT) *bad = 1; gap = 0; }
+      l = gap;
+      if (j < M && mode == SEG_SUB) {
+        l += repl_len;
+        if (cur.x == cur.y && pos < n) l += 1;
+      }
+    }
+    long long inc = l;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    len[r] = l;
+    excl[r] = carry + inc - l;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
   }
-  if (lane == 31) s_warp[warp] = inc;
+  if (lane == 0) s_warp[warp] = carry;
   __syncthreads();
   long long before = 0, tot = 0;
   for (int w = 0; w < kThreads / 32; ++w) { if (w < warp) before += s_warp[w]; tot += s_warp[w]; }
@@ -1287,12 +1306,17 @@ __global__ void k_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mo
     }
   }
   __syncthreads();
-  if (j <= M) {
-    const int64_t O = (int64_t)(s_base + before + inc - len);
-    offs[j] = O;
-    // segment that owns the first byte of every output tile it covers (k_assemble's search window)
-    if (tile_seg && len > 0)
-      for (int64_t t = (O + kAsmTile - 1) / kAsmTile; t * kAsmTile < O + len; ++t) tile_seg[t] = j;
+  const long long base = (long long)s_base + before;
+#pragma unroll
+  for (int r = 0; r < kSegRounds; ++r) {
+    const int64_t j = j0 + 32 * r;
+    if (j <= M) {
+      const int64_t O = base + excl[r];
+      offs[j] = O;
+      // segment that owns the first byte of every output tile it covers (k_assemble's window)
+      if (tile_seg && len[r] > 0)
+        for (int64_t t = (O + kAsmTile - 1) / kAsmTile; t * kAsmTile < O + len[r]; ++t) tile_seg[t] = j;
+    }
   }
 }
 
@@ -1610,7 +1634,7 @@ void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, 
 void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,
                         unsigned long long *desc, unsigned int *ticket, int64_t *offs, int *bad, int64_t *tile_seg,
                         cudaStream_t st) {
-  const int tiles = (int)((M + 1 + kThreads - 1) / kThreads);
+  const int tiles = (int)((M + 1 + kSegTile - 1) / kSegTile);
   k_seg_lengths<<<tiles, kThreads, 0, st>>>(spans, M, n, mode, repl_len, desc, ticket, offs, bad, tiles, tile_seg);
 }
 void launch_assemble(const AsmParams &p, cudaStream_t st) {

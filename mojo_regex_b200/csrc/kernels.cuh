@@ -124,7 +124,9 @@ struct SubTemplate {
 constexpr int kAsmRounds = 4;
 constexpr int kAsmTile = kThreads * 16 * kAsmRounds;  // 16 KiB
 constexpr int kAsmSegCap = 2560;                       // segment records staged per tile (40 KiB)
-constexpr int kAsmTplCap = 256;                        // replacement bytes staged per tile
+constexpr int kAsmTplCap = 256;
+constexpr int kSegRounds = 8;                          // k_seg_lengths: segments per thread
+constexpr int kSegTile = kThreads * kSegRounds;        // ... and per CTA                        // replacement bytes staged per tile
 struct AsmParams {
   const uint8_t *text;
   int64_t n;

@@ -91,36 +91,62 @@ def gather_records(rec: List[int], device) -> List[List[int]]:
 
 
 class DeviceGather:
-    """All-gather of a small int64 record that never leaves the device: the record and the gathered
-    table live in preallocated HBM tensors and the exclusive scan is a device op, so a step pays one
-    NCCL launch and no host synchronisation."""
+    """All-gather of a small int64 record that never blocks the scan stream.
+
+    The record (match count, output bytes) is known on the host when a matching call returns, so the
+    exchange has no dependency on the kernels: it runs on its own CUDA stream (H2D of the record from a
+    ring of pinned slots, one NCCL all-gather, an exclusive scan on the device) and overlaps the next
+    step's scan.  Consumers of `base_offset()` -- and anything that times the steps -- order themselves
+    after `self.stream` (`join(stream)`)."""
+
+    RING = 64
 
     def __init__(self, width: int, device):
         import torch.distributed as dist
 
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
+        self.cuda = torch.device(device).type == "cuda"
         self.rec = torch.zeros(width, dtype=torch.int64, device=device)
         self.table = torch.zeros((self.world, width), dtype=torch.int64, device=device)
-        self.host = torch.zeros(width, dtype=torch.int64).pin_memory() if torch.device(device).type == "cuda" else torch.zeros(width, dtype=torch.int64)
+        self.host = torch.zeros((self.RING, width), dtype=torch.int64)
+        if self.cuda:
+            self.host = self.host.pin_memory()
+        self.stream = torch.cuda.Stream(device=device) if self.cuda else None
+        self.i = 0
 
     def gather(self, values: List[int]) -> torch.Tensor:
-        """-> (world, width) device tensor; row r is rank r's record."""
+        """-> (world, width) device tensor; row r is rank r's record (valid on self.stream)."""
+        import contextlib
+
         import torch.distributed as dist
 
-        for i, v in enumerate(values):
-            self.host[i] = int(v)
-        self.rec.copy_(self.host, non_blocking=True)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.table, self.rec)
-        else:
-            self.table[0].copy_(self.rec)
+        slot = self.host[self.i % self.RING]
+        self.i += 1
+        for k, v in enumerate(values):
+            slot[k] = int(v)
+        ctx = torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
+        with ctx:
+            self.rec.copy_(slot, non_blocking=True)
+            if self.world > 1:
+                dist.all_gather_into_tensor(self.table, self.rec)
+            else:
+                self.table[0].copy_(self.rec)
         return self.table
 
     def base_offset(self, column: int = 0) -> torch.Tensor:
-        """Exclusive prefix of `column` at this rank (0-d device tensor)."""
-        col = self.table[:, column]
-        return torch.cumsum(col, 0)[self.rank] - col[self.rank]
+        """Exclusive prefix of `column` at this rank (0-d device tensor, valid on self.stream)."""
+        import contextlib
+
+        ctx = torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
+        with ctx:
+            col = self.table[:, column]
+            return torch.cumsum(col, 0)[self.rank] - col[self.rank]
+
+    def join(self, stream) -> None:
+        """Make `stream` wait for every exchange issued so far."""
+        if self.cuda:
+            stream.wait_stream(self.stream)
 
 
 def global_offsets(counts: List[int]) -> List[int]:
@@ -204,6 +230,12 @@ def finish_findall(spans, records: List[List[int]], rank: int, class_runs: bool)
 _GATHERS = {}
 
 
+def join_exchanges(stream) -> None:
+    """Order `stream` after every count exchange issued so far (end of a timed region, or a consumer)."""
+    for g in _GATHERS.values():
+        g.join(stream)
+
+
 def _gather_for(width: int, device) -> DeviceGather:
     key = (width, str(device))
     if key not in _GATHERS:
@@ -225,14 +257,20 @@ class OpResult:
         self.holder = None
 
 
-def run_op_device(rx, cfg, shard: Shard) -> OpResult:
+def run_op_local(rx, cfg, shard: Shard) -> OpResult:
+    """run_op_device without the cross-rank exchange (safe to call a rank-dependent number of times)."""
+    return run_op_device(rx, cfg, shard, exchange=False)
+
+
+def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
     """One step with the shard resident in HBM and the result left in HBM."""
     n = shard.core_bytes
     dev = shard.buffer.device
+    multi = exchange and shard.world > 1
     if cfg["op"] == "findall":
         ds = rx.match_all_device(shard.text)
         base = 0
-        if shard.world > 1:
+        if multi:
             g = _gather_for(1, dev)
             g.gather([ds.n])
             base = g.base_offset()
@@ -246,13 +284,13 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
             out = shard._batch_out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
             shard._batch_kernel = "k_lines" if rx.info().search_rev_states > 0 else "k_scan"
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128, sync=False)
-        if shard.world > 1:
+        if multi:
             _gather_for(1, dev).gather([shard.n_docs])
         return OpResult(shard.n_docs, n + 16 * shard.n_docs, shard._batch_kernel, None)
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
         base = 0
-        if shard.world > 1:
+        if multi:
             g = _gather_for(1, dev)
             g.gather([ob.n])
             base = g.base_offset()
@@ -261,7 +299,7 @@ def run_op_device(rx, cfg, shard: Shard) -> OpResult:
         pc = rx.split_device(shard.text)
         total = int(pc.offsets_tensor()[-1].item())
         base = 0
-        if shard.world > 1:
+        if multi:
             g = _gather_for(2, dev)
             g.gather([pc.n, total])
             base = g.base_offset()
