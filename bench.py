@@ -28,6 +28,19 @@ sys.path.insert(0, ROOT)
 GiB = 1 << 30
 
 
+def load_traffic(config: str, n_bytes: int, kernel: str):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload
+    (profiles/r01_traffic.json); None when there is no capture for this config / size / kernel."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f).get(config)
+        if t and int(t["bytes_per_gpu"]) == int(n_bytes) and t["kernel"] == kernel:
+            return float(t["traffic_bytes"])
+    except Exception:
+        pass
+    return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -301,7 +314,8 @@ def run_gpu(args):
                        if n_bytes > 256 << 20 else "input re-read every step; smaller than 2x L2",
                        "sharding": "byte ranges + halo, count all-gather over NCCL" if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": args.traffic,
+                         "frac": (achieved / peak) if achieved else None,
+                         "traffic": args.traffic if args.traffic is not None else load_traffic(args.config, n_bytes, res.kernel),
                          "kernel": res.kernel, "algorithmic_bytes_per_launch": int(alg_bytes),
                          "kernel_ms": k_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,

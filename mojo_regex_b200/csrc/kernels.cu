@@ -657,25 +657,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
 // returns.  Pass 2 runs that one attempt forwards through the dense forward table for the longest accept.
 // No candidate queue, no atomics, no divergence in pass 1.
 //
-// Fixed-size, 16-byte aligned documents are staged by TMA: every thread issues one bulk copy of its own
-// document into a row of `line_pitch` bytes (an odd number of 16-byte units, so the LDS.128 of a
-// quarter-warp hit 8 distinct bank groups); CTAs are persistent over batches of 256 documents so that the
-// tables are loaded once.  Ragged or unaligned documents are read from HBM byte by byte.
+// Fixed-size, 16-byte aligned documents are staged warp by warp: a warp owns 32 consecutive documents, reads
+// them with coalesced 16-byte loads (8 lanes per document row) and parks them in rows of `line_pitch` bytes
+// (an odd number of 16-byte units, so both the staging stores and each lane's LDS.128 of its own row hit 8
+// distinct bank groups).  Warps are independent -- no block barrier, no mbarrier -- and persistent over
+// batches so that the tables are loaded once.  (A TMA bulk copy per document was tried first: UBLKCP takes
+// uniform operands, so the 32 copies of a warp are issued by a 32-iteration ELECT loop that cost 18 % of
+// the kernel's instructions, profiles/r01_k_lines_ncu.txt.)  Ragged or unaligned documents are read from
+// HBM byte by byte.
 struct LinesShared {
-  alignas(8) uint64_t bar;
   alignas(16) uint8_t tables[16];  // rev | fwd | staged documents follow
 };
 
-__device__ __forceinline__ void lines_emit(const uint8_t *fwd, uint32_t fwd_start, const uint8_t *doc_s,
-                                           const uint8_t *doc_g, int64_t len, int64_t best, int64_t *out) {
+// the attempt at `best` (dfa.mojo:1979-2026): longest accept, stop at the first dead transition
+template <class ByteAt>
+__device__ __forceinline__ void lines_emit(const uint8_t *fwd, uint32_t fwd_start, ByteAt byte_at, int len, int best,
+                                           int64_t *out) {
   int64_t s_rel = -1, e_rel = -1;
   if (best >= 0) {
-    // the attempt at `best` (dfa.mojo:1979-2026): longest accept, stop at the first dead transition
     uint32_t s = fwd_start;
-    int64_t q = best, last = -1;
+    int q = best, last = -1;
     while (q < len) {
-      const uint32_t b = doc_s ? doc_s[q] : doc_g[q];
-      s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * b);
+      s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * byte_at(q));
       if (s == 0) break;
       ++q;
       if (s & 4u) last = q;
@@ -688,33 +691,44 @@ __device__ __forceinline__ void lines_emit(const uint8_t *fwd, uint32_t fwd_star
 __global__ void __launch_bounds__(kThreads) k_lines(const LinesParams prm) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   {
     const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.tables);
     uint4 *d4 = reinterpret_cast<uint4 *>(sh.tables);
     for (int i = tid; i < (prm.rev_bytes + prm.fwd_bytes) / 16; i += kThreads) d4[i] = s4[i];
   }
-  if (tid == 0 && prm.staged) {
-    mbar_init(&sh.bar, 1);
-    fence_proxy_async();
-  }
   __syncthreads();
   const uint8_t *rev = sh.tables, *fwd = sh.tables + prm.rev_bytes;
-  const int64_t n_batches = (prm.n_docs + kThreads - 1) / kThreads;
+  constexpr int kWarpsPerCta = kThreads / 32;
 
   if (prm.staged) {
-    uint8_t *lines = sh.tables + prm.rev_bytes + prm.fwd_bytes;
-    uint8_t *mine = lines + (size_t)tid * prm.line_pitch;
-    const int stride = (int)prm.doc_stride, nv = stride >> 4;
-    int it = 0;
-    for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x, ++it) {
-      const int64_t d = batch * kThreads + tid;
-      const int in_batch = (int)min((int64_t)kThreads, prm.n_docs - batch * kThreads);
-      if (tid == 0) mbar_expect_tx(&sh.bar, (uint32_t)in_batch * (uint32_t)stride);
-      __syncthreads();  // expect_tx is posted before any copy can complete
-      if (d < prm.n_docs) tma_bulk_g2s(mine, prm.text + d * stride, (uint32_t)stride, &sh.bar);
-      mbar_wait(&sh.bar, (uint32_t)(it & 1));
-      if (d < prm.n_docs) {
+    const int pitch = prm.line_pitch, stride = (int)prm.doc_stride, nv = stride >> 4;
+    uint8_t *rows = sh.tables + prm.rev_bytes + prm.fwd_bytes + (size_t)warp * 32 * pitch;  // this warp's 32 rows
+    const uint8_t *mine = rows + (size_t)lane * pitch;
+    const int64_t n_groups = (prm.n_docs + 31) / 32;  // a group = 32 consecutive documents = one warp batch
+    for (int64_t grp = (int64_t)blockIdx.x * kWarpsPerCta + warp; grp < n_groups; grp += (int64_t)gridDim.x * kWarpsPerCta) {
+      const int64_t d0 = grp * 32;
+      const int in_grp = (int)min((int64_t)32, prm.n_docs - d0);
+      // ---- stage: the group's documents are contiguous in HBM; chunk c (16 bytes) of that range belongs to
+      //      row c / nv, column c % nv
+      const uint4 *src = reinterpret_cast<const uint4 *>(prm.text + d0 * stride);
+      const int chunks = in_grp * nv;
+      __syncwarp();  // the previous batch's rows are no longer read
+      for (int c0 = 0; c0 < chunks; c0 += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + 32 * u + lane;
+          if (c < chunks) v[u] = __ldg(src + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int c = c0 + 32 * u + lane;
+          if (c < chunks) *reinterpret_cast<uint4 *>(rows + (size_t)(c / nv) * pitch + 16 * (c % nv)) = v[u];
+        }
+      }
+      __syncwarp();
+      if (lane < in_grp) {
         uint32_t r = 0, best_pk = 0;
         int best_word = -1;  // index of the 4-byte word that holds the leftmost flagged byte
 #pragma unroll 2
@@ -735,32 +749,35 @@ __global__ void __launch_bounds__(kThreads) k_lines(const LinesParams prm) {
             if (pk & 0x04040404u) { best_pk = pk; best_word = 4 * k + wi; }
           }
         }
-        const int64_t best = best_word >= 0 ? 4 * best_word + ((__ffs(best_pk & 0x04040404u) - 1) >> 3) : -1;
-        lines_emit(fwd, (uint32_t)prm.fwd_start, mine, nullptr, stride, best, prm.out + 2 * d);
+        const int best = best_word >= 0 ? 4 * best_word + ((__ffs(best_pk & 0x04040404u) - 1) >> 3) : -1;
+        lines_emit(fwd, (uint32_t)prm.fwd_start, [&](int q) { return (uint32_t)mine[q]; }, stride, best,
+                   prm.out + 2 * (d0 + lane));
       }
-      __syncthreads();  // every thread is done with its row before the next batch lands in it
     }
     return;
   }
 
+  const int64_t n_batches = (prm.n_docs + kThreads - 1) / kThreads;
   for (int64_t batch = blockIdx.x; batch < n_batches; batch += gridDim.x) {
     const int64_t d = batch * kThreads + tid;
     if (d >= prm.n_docs) break;
     const int64_t lo = prm.doc_offsets ? prm.doc_offsets[d] : d * prm.doc_stride;
     const int64_t hi = prm.doc_offsets ? prm.doc_offsets[d + 1] : min(lo + prm.doc_stride, prm.n);
     const uint8_t *doc = prm.text + lo;
-    int64_t best = -1;
+    const int len = (int)min(hi - lo, (int64_t)0x7fffffff);
+    int best = -1;
     uint32_t r = 0;
-    for (int64_t q = hi - lo - 1; q >= 0; --q) {
+    for (int q = len - 1; q >= 0; --q) {
       r = *reinterpret_cast<const uint16_t *>(rev + r + 2u * doc[q]);
       if (r & 4u) best = q;
     }
-    lines_emit(fwd, (uint32_t)prm.fwd_start, nullptr, doc, hi - lo, best, prm.out + 2 * d);
+    lines_emit(fwd, (uint32_t)prm.fwd_start, [&](int q) { return (uint32_t)doc[q]; }, len, best, prm.out + 2 * d);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // class runs
+constexpr int kRunTok = 12;  // matches a thread buffers before it has to walk its chunk a second time
 struct RunsShared {
   DevProg prog;
   alignas(16) uint8_t text[kTile + kHalo];
@@ -770,6 +787,7 @@ struct RunsShared {
   unsigned long long base;
   long long warp_len[kThreads / 32];
   int warp_all[kThreads / 32];
+  uint16_t tok[kThreads * kRunTok];  // UNIFORM_RUN: (start in chunk) | (length << 8) of a thread's matches
 };
 
 // membership bits of 16 bytes
@@ -957,6 +975,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
 
   int cnt = 0;
   unsigned long long out_idx = 0;
+  uint16_t *tok = sh.tok + tid * kRunTok;
+  const bool tokens_ok = K <= 255;  // a match length fits the token
   for (int pass = 0; pass < 2; ++pass) {
     cnt = 0;
     int i = 0;
@@ -981,6 +1001,8 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
         if (pass == 1) {
           const unsigned long long o = out_idx + cnt;
           if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, pos + prm.rebase, pos + L + prm.rebase);
+        } else if (cnt < kRunTok) {
+          tok[cnt] = (uint16_t)(s | (L << 8));
         }
         ++cnt;
       }
@@ -998,6 +1020,14 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
       }
       __syncthreads();
       out_idx = sh.base + (unsigned long long)rank;
+      if (tokens_ok && cnt <= kRunTok) {  // the usual case: emit from the buffered tokens, no second walk
+        for (int k = 0; k < cnt; ++k) {
+          const unsigned long long o = out_idx + k;
+          const int64_t pos = chunk0 + (tok[k] & 0xff);
+          if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, pos + prm.rebase, pos + (tok[k] >> 8) + prm.rebase);
+        }
+        return;
+      }
     }
   }
 }
