@@ -208,7 +208,7 @@ int upload_dense(const DenseTable &dt, uint8_t **out) {
   if (dt.out_len.size() > sizeof(h->out_len)) return fail(MRX_E_UNSUPPORTED, "too many literals for the dense table");
   std::memcpy(h->out_len, dt.out_len.data(), dt.out_len.size());
   if (dt.out_len.size() > 32) return fail(MRX_E_UNSUPPORTED, "too many literals for the dense table");
-  for (size_t j = 0; j < dt.out_len.size(); ++j) h->len_lut[(dt.acc_base + j) & 31] = dt.out_len[j];
+  std::memcpy(h->len_lut, dt.len_lut.data(), 32);
   std::memcpy(raw.data() + sizeof(DenseHdr), dt.next.data(), dt.next.size() * 2);
   void *d = nullptr;
   CUDA_TRY(cudaMalloc(&d, raw.size()));

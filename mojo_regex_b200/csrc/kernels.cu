@@ -399,102 +399,145 @@ struct DenseShared {
   alignas(16) uint16_t table[8];    // the whole table follows
 };
 
-// Walk this thread's 144 bytes of the staged tile.  SPANS: tokens (end - chunk start) | len << 8 go to
-// `mine`, returns the number of matches (which may exceed kPriv: the caller then takes the recompute
-// path).  FIRST: atomicMin on best.  The packed state bytes (low byte of the row offset = row mod 32 and
-// the accept flag) are written back over the consumed text, so the literal that ended at a hit is one
-// byte load + one LUT load away instead of a replay of max_len dependent lookups.  All threads of the
-// block must call this (it contains a barrier).
+// Walk this thread's 144 bytes of the staged tile as TWO independent chains -- A = bytes [0, 80), B = bytes
+// [80, 144), each warmed up on the max_len - 1 bytes before it -- interleaved instruction by instruction,
+// so that every warp has two dependent shared-memory lookups in flight instead of one (with 8 warps per
+// scheduler a single chain leaves the issue slots 37 % idle, profiles/r01_k_dense_g_ncu.txt).
+// SPANS: tokens (end - chunk start) | len << 8 go to `mine`: chain A's fill it from slot 0 upwards, chain
+// B's from slot kPriv - 1 downwards (one shared budget of kPriv); returns the number of matches, cnt_a =
+// those of chain A, ovf = the budget was exceeded (the caller then takes the recompute path).  FIRST: atomicMin on best.  The packed state bytes (low byte of the
+// row offset = row mod 32 and the accept flag) are written back over the consumed text, so the literal that
+// ended at a hit is one byte load + one LUT load away instead of a replay of max_len dependent lookups.
+// All threads of the block must call this (it contains a barrier).
+constexpr int kChainA = 80;            // bytes of chain A (5 vectors); chain B takes the other 4
+
 template <bool FIRST>
 __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseShared &sh, const TextView &tv,
-                                                int64_t tile_start, uint16_t *mine) {
+                                                int64_t tile_start, uint16_t *mine, int &cnt_a, bool &ovf) {
   const int tid = threadIdx.x;
   const uint8_t *tbl = reinterpret_cast<const uint8_t *>(sh.table);
   const int chunk_rel = tid * kChunk;
   // start positions are filtered against the key window only in tiles that touch its edges
   const bool edge_tile = tile_start - 256 < prm.key_lo || tile_start + kTile > prm.key_hi;
   const int valid = (int)min((int64_t)kTile, prm.n - tile_start);  // text bytes in this tile
-  // warm-up: the state after the max_len - 1 bytes preceding the chunk is exact
-  uint32_t s = 0;
+  // warm-up: the state after the max_len - 1 bytes preceding a chain is exact
+  uint32_t sa = 0, sb = 0;
   {
     const int w = sh.hdr.max_len - 1;
     if (tid > 0 && w <= kChunk) {
       if (chunk_rel <= valid)
-        for (int r = chunk_rel - w; r < chunk_rel; ++r) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * sh.text[r]);
+        for (int r = chunk_rel - w; r < chunk_rel; ++r) sa = *reinterpret_cast<const uint16_t *>(tbl + sa + 2u * sh.text[r]);
     } else {
       const int64_t chunk0 = tile_start + chunk_rel;
       int64_t q = chunk0 - w;
       if (q < 0) q = 0;
       const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
-      for (; q < stop; ++q) s = *reinterpret_cast<const uint16_t *>(tbl + s + 2u * tv.at(q));
+      for (; q < stop; ++q) sa = *reinterpret_cast<const uint16_t *>(tbl + sa + 2u * tv.at(q));
+    }
+    if (w <= kChainA) {
+      for (int r = chunk_rel + kChainA - w; r < chunk_rel + kChainA; ++r)
+        sb = *reinterpret_cast<const uint16_t *>(tbl + sb + 2u * sh.text[r]);
+    } else {  // literals longer than chain A: B's history reaches back past this chunk
+      const int64_t b0 = tile_start + chunk_rel + kChainA;
+      int64_t q = b0 - w;
+      if (q < 0) q = 0;
+      const int64_t stop = b0 < prm.n ? b0 : prm.n;
+      for (; q < stop; ++q) sb = *reinterpret_cast<const uint16_t *>(tbl + sb + 2u * tv.at(q));
     }
   }
   __syncthreads();  // every warm-up has read its predecessor's tail: the text may now be overwritten
-  int cnt = 0;
-#pragma unroll 1
-  for (int v3 = 0; v3 < kVecs / 3; ++v3) {
-    const int rel0 = chunk_rel + 48 * v3;
-    if (rel0 >= valid) break;
-    // ---- hot loop over 48 bytes: per byte PRMT (extract), IMAD (address), LDS.U16 (next row),
-    //      PRMT (pack byte 0 of the row offset; its bit 2 is the "a literal ends here" flag)
-    uint32_t pk[12];
+  int ca = 0, cb = 0;
+  constexpr uint32_t kF = 0x04040404u;  // bit 2 of every packed byte = accept flag
+  // one step of a chain: PRMT (extract), IMAD (address), LDS.U16 (next row), PRMT (pack the low byte)
+#define MRX_DENSE_STEP(S, W, ACC, K)                                                                      \
+  {                                                                                                       \
+    const uint32_t b_ = __byte_perm(W, 0, 0x4440 + K);                                                    \
+    uint32_t addr_;                                                                                       \
+    asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr_) : "r"(b_), "r"(S));                                     \
+    S = *reinterpret_cast<const uint16_t *>(tbl + addr_);                                                 \
+    ACC = __byte_perm(ACC, S, K == 0 ? 0x3214 : K == 1 ? 0x3240 : K == 2 ? 0x3410 : 0x4210);              \
+  }
+  // hits of 32 consecutive bytes starting at chunk offset `base`; chain A stores upwards, chain B downwards
+  auto take_hits = [&](uint32_t f, int base, bool is_b, int &cnt) {
+    const int live = valid - (chunk_rel + base);  // bytes of these 32 that exist in the text
+    if (live < 32) f = live <= 0 ? 0u : (f & ((1u << live) - 1u));
+    while (f) {
+      const int i = __ffs(f) - 1;
+      f &= f - 1;
+      const int off = base + i;  // byte of the chunk the literal ends on
+      const uint32_t len = sh.hdr.len_lut[sh.text[chunk_rel + off] >> 3];
+      if (edge_tile || FIRST) {
+        const int64_t start = tile_start + chunk_rel + off + 1 - (int64_t)len;
+        if (start < prm.key_lo || start >= prm.key_hi) continue;
+        if (FIRST) {
+          atomicMin(prm.best, ((unsigned long long)start << 8) | len);
+          continue;
+        }
+      }
+      if (ca + cb < kPriv) mine[is_b ? kPriv - 1 - cnt : cnt] = (uint16_t)((off + 1) | (len << 8));
+      ++cnt;
+    }
+  };
+  auto mask8 = [&](const uint32_t *pk) {  // 8 packed words (32 state bytes) -> 32-bit hit mask
+    uint32_t m = 0;
 #pragma unroll
-    for (int vv = 0; vv < 3; ++vv) {
-      uint4 *slot = reinterpret_cast<uint4 *>(sh.text + rel0 + 16 * vv);
-      const uint4 w4 = *slot;
-      const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+    for (int j = 0; j < 8; ++j) m |= (((pk[j] & kF) * 0x04081020u) >> 28) << (4 * j);
+    return m;
+  };
+#pragma unroll 1
+  for (int bt = 0; bt < 2; ++bt) {  // two double batches: A vectors 2bt, 2bt+1 with B vectors 5+2bt, 6+2bt
+    const int ra = chunk_rel + 32 * bt, rb = chunk_rel + kChainA + 32 * bt;
+    uint32_t pa[8], pb[8];
+#pragma unroll
+    for (int vv = 0; vv < 2; ++vv) {
+      uint4 *slot_a = reinterpret_cast<uint4 *>(sh.text + ra + 16 * vv);
+      uint4 *slot_b = reinterpret_cast<uint4 *>(sh.text + rb + 16 * vv);
+      const uint4 a4 = *slot_a, b4 = *slot_b;
+      const uint32_t wa[4] = {a4.x, a4.y, a4.z, a4.w}, wb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int wi = 0; wi < 4; ++wi) {
-        uint32_t acc = 0;
+        uint32_t acc_a = 0, acc_b = 0;
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + k);
-          uint32_t addr;
-          asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(s));
-          s = *reinterpret_cast<const uint16_t *>(tbl + addr);
-          acc = __byte_perm(acc, s, k == 0 ? 0x3214 : k == 1 ? 0x3240 : k == 2 ? 0x3410 : 0x4210);
+          MRX_DENSE_STEP(sa, wa[wi], acc_a, k)
+          MRX_DENSE_STEP(sb, wb[wi], acc_b, k)
         }
-        pk[4 * vv + wi] = acc;
+        pa[4 * vv + wi] = acc_a;
+        pb[4 * vv + wi] = acc_b;
       }
-      *slot = make_uint4(pk[4 * vv], pk[4 * vv + 1], pk[4 * vv + 2], pk[4 * vv + 3]);
+      *slot_a = make_uint4(pa[4 * vv], pa[4 * vv + 1], pa[4 * vv + 2], pa[4 * vv + 3]);
+      *slot_b = make_uint4(pb[4 * vv], pb[4 * vv + 1], pb[4 * vv + 2], pb[4 * vv + 3]);
     }
-    // ---- 48-bit hit mask (bit i = a literal ends after byte i of these 48)
-    uint32_t any = 0;
+    uint32_t any_a = 0, any_b = 0;
 #pragma unroll
-    for (int j = 0; j < 12; ++j) any |= pk[j];
-    constexpr uint32_t kF = 0x04040404u;  // bit 2 of every packed byte = accept flag
-    if ((any & kF) == 0) continue;
-    uint32_t mlo = 0, mhi = 0;  // bytes 0..31, 32..47
+    for (int j = 0; j < 8; ++j) { any_a |= pa[j]; any_b |= pb[j]; }
+    if (any_a & kF) take_hits(mask8(pa), 32 * bt, false, ca);
+    if (any_b & kF) take_hits(mask8(pb), kChainA + 32 * bt, true, cb);
+  }
+  {  // the last vector of chain A (bytes 64..79) on its own
+    uint4 *slot = reinterpret_cast<uint4 *>(sh.text + chunk_rel + 64);
+    const uint4 a4 = *slot;
+    const uint32_t wa[4] = {a4.x, a4.y, a4.z, a4.w};
+    uint32_t pa[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mlo |= (((pk[j] & kF) * 0x04081020u) >> 28) << (4 * j);
+    for (int wi = 0; wi < 4; ++wi) {
+      uint32_t acc = 0;
 #pragma unroll
-    for (int j = 8; j < 12; ++j) mhi |= (((pk[j] & kF) * 0x04081020u) >> 28) << (4 * (j - 8));
-    if (rel0 + 48 > valid) {  // drop flags produced by bytes past the end of the text
-      const int live = valid - rel0;  // 1..47
-      if (live < 32) { mlo &= (1u << live) - 1u; mhi = 0; } else mhi &= (1u << (live - 32)) - 1u;
+      for (int k = 0; k < 4; ++k) MRX_DENSE_STEP(sa, wa[wi], acc, k)
+      pa[wi] = acc;
     }
+    *slot = make_uint4(pa[0], pa[1], pa[2], pa[3]);
+    if ((pa[0] | pa[1] | pa[2] | pa[3]) & kF) {
+      uint32_t m = 0;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
-      uint32_t f = half ? mhi : mlo;
-      while (f) {
-        const int i = __ffs(f) - 1;
-        f &= f - 1;
-        const int off = 48 * v3 + 32 * half + i;   // byte of the chunk the literal ends on
-        const uint32_t len = sh.hdr.len_lut[sh.text[chunk_rel + off] >> 3];
-        if (edge_tile || FIRST) {
-          const int64_t start = tile_start + chunk_rel + off + 1 - (int64_t)len;
-          if (start < prm.key_lo || start >= prm.key_hi) continue;
-          if (FIRST) {
-            atomicMin(prm.best, ((unsigned long long)start << 8) | len);
-            continue;
-          }
-        }
-        if (cnt < kPriv) mine[cnt] = (uint16_t)((off + 1) | (len << 8));
-        ++cnt;
-      }
+      for (int j = 0; j < 4; ++j) m |= (((pa[j] & kF) * 0x04081020u) >> 28) << (4 * j);
+      take_hits(m, 64, false, ca);
     }
   }
-  return cnt;
+#undef MRX_DENSE_STEP
+  cnt_a = ca;
+  ovf = ca + cb > kPriv;
+  return ca + cb;
 }
 
 // search variant: one CTA per tile, no output list
@@ -517,7 +560,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense_first(const DenseParams p
   if (tile_start + stage_bytes > prm.n) stage_bytes = (int)(prm.n - tile_start > 0 ? prm.n - tile_start : 0);
   stage_tile(sh.text, prm.text, tile_start, stage_bytes, &sh.bar);
   TextView tv{prm.text, sh.text, tile_start, tile_start + stage_bytes};
-  dense_scan_chunk<true>(prm, sh, tv, tile_start, nullptr);
+  int ca;
+  bool ovf;
+  dense_scan_chunk<true>(prm, sh, tv, tile_start, nullptr, ca, ovf);
 }
 
 // findall variant: persistent CTAs.  Per iteration: take a ticket, start the TMA of that tile, and while
@@ -543,7 +588,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
 
   // state of the tile whose flush is pending
   bool pending = false;
-  int p_tile = 0, p_cnt = 0, p_rank = 0, p_total = 0, p_gen = 0;
+  int p_tile = 0, p_cnt = 0, p_cnt_a = 0, p_rank = 0, p_total = 0, p_gen = 0;
   int64_t p_start = 0;
 
   auto take_ticket_and_load = [&]() {  // thread 0 only
@@ -568,7 +613,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     const int room = o < (unsigned long long)prm.cap ? (int)min((unsigned long long)p_cnt, (unsigned long long)prm.cap - o) : 0;
     int64_t *dst = prm.spans + 2 * o;
     for (int i = 0; i < room; ++i, dst += 2) {
-      const uint32_t r = rec[i];
+      const uint32_t r = rec[i < p_cnt_a ? i : kPriv - 1 - (i - p_cnt_a)];  // chain A's tokens, then chain B's
       const int64_t end = cbase + (r & 0xffu);
       st_span(dst, end - (int64_t)(r >> 8), end);
     }
@@ -592,7 +637,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     const int gen = it & 1;
     uint16_t *mine = sh.priv[gen] + tid * kPriv;
     // ---- scan (never waits on other CTAs), ranks inside the tile, publish the aggregate
-    const int cnt = dense_scan_chunk<false>(prm, sh, tv, tile_start, mine);
+    int cnt_a;
+    bool ovf;
+    const int cnt = dense_scan_chunk<false>(prm, sh, tv, tile_start, mine, cnt_a, ovf);
     int inc = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -601,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     }
     const int lane_prefix = inc - cnt;
     const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
-    const int overflow = __syncthreads_or(cnt > kPriv);
+    const int overflow = __syncthreads_or(ovf);
     int total;
     const int wrank = block_exclusive_scan(lane == 0 ? warp_total : 0, sh.scan_ws, &total);
     const int rank = __shfl_sync(0xffffffffu, wrank, 0) + lane_prefix;
@@ -624,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
       for (int i = 0; i < kChunk && chunk_rel + i < valid; ++i) {  // (the staged copy now holds state bytes)
         s2 = *reinterpret_cast<const uint16_t *>(tbl + s2 + 2u * prm.text[chunk0 + i]);
         if (s2 & 4u) {
-          const uint32_t len = sh.hdr.out_len[(int)((s2 - 4u) / 520u) - sh.hdr.acc_base];
+          const uint32_t len = sh.hdr.len_lut[(s2 >> 3) & 31u];
           const int64_t start = chunk0 + i + 1 - (int64_t)len;
           if (start >= prm.key_lo && start < prm.key_hi) {
             if (o < (unsigned long long)prm.cap) st_span(prm.spans + 2 * o, start + prm.rebase, start + len + prm.rebase);
@@ -640,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_dense(const DenseParams prm) {
     if (pending) flush_pending();
     if (!overflow) {
       pending = true;
-      p_tile = tile; p_cnt = cnt; p_rank = rank; p_total = total; p_gen = gen; p_start = tile_start;
+      p_tile = tile; p_cnt = cnt; p_cnt_a = cnt_a; p_rank = rank; p_total = total; p_gen = gen; p_start = tile_start;
     }
     __syncthreads();
     tile = sh.tile;

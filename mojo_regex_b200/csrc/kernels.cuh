@@ -70,8 +70,8 @@ struct DenseHdr {
   int32_t n_states, acc_base, max_len, table_bytes;
   int32_t uniform_len, pad0, pad1, pad2;  // > 0 when every literal has this length
   uint8_t out_len[64];
-  uint8_t len_lut[32];  // literal length by (row mod 32) of the accept row; rows are 520 B apart, so
-                        // bits 3..7 of a row offset's low byte are exactly row mod 32
+  uint8_t len_lut[32];  // literal length by (row offset >> 3) & 31 of the accept row (rows are 520 B apart,
+                        // so consecutive rows differ by 1 there)
 };
 
 struct DenseParams {

@@ -58,6 +58,7 @@ struct DenseTable {
   int32_t n_states = 0, acc_base = 0, max_len = 0;
   std::vector<uint16_t> next;    // whole table, table_bytes / 2 entries
   std::vector<uint8_t> out_len;  // n_states - acc_base
+  std::vector<uint8_t> len_lut;  // literal length by (row offset >> 3) & 31 of an accept row
 };
 
 // Automata of the per-document search kernel (k_lines), both in the layout of DenseTable: uint16 entries
