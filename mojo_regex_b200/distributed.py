@@ -244,12 +244,18 @@ def _gather_for(width: int, device) -> DeviceGather:
 
 
 class OpResult:
-    def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, global_base=0):
+    def __init__(self, units: int, algorithmic_bytes: int, kernel: str, holder=None, gather=None):
         self.units = units
         self.algorithmic_bytes = algorithmic_bytes
         self.kernel = kernel
         self.holder = holder
-        self.global_base = global_base
+        self._gather = gather
+
+    @property
+    def global_base(self):
+        """Global index / byte offset of this rank's slice of the result (0-d device tensor on the exchange
+        stream, computed on demand from the gathered counts)."""
+        return self._gather.base_offset() if self._gather is not None else 0
 
     def close(self):
         if self.holder is not None and hasattr(self.holder, "close"):
@@ -269,14 +275,16 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
     multi = exchange and shard.world > 1
     if cfg["op"] == "findall":
         ds = rx.match_all_device(shard.text)
-        base = 0
+        g = None
         if multi:
             g = _gather_for(1, dev)
             g.gather([ds.n])
-            base = g.base_offset()
-        info = rx.info()
-        kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
-        return OpResult(ds.n, n + 16 * ds.n, kernel, ds, base)
+        kernel = getattr(shard, "_findall_kernel", None)
+        if kernel is None:
+            info = rx.info()
+            kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
+            shard._findall_kernel = kernel
+        return OpResult(ds.n, n + 16 * ds.n, kernel, ds, g)
     if cfg["op"] == "search_batch":
         # the caller-provided result array lives with the shard (allocated once, like the text)
         out = getattr(shard, "_batch_out", None)
@@ -289,21 +297,19 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
         return OpResult(shard.n_docs, n + 16 * shard.n_docs, shard._batch_kernel, None)
     if cfg["op"] == "sub":
         ob = rx.sub_device(cfg["repl"], shard.text)
-        base = 0
+        g = None
         if multi:
             g = _gather_for(1, dev)
             g.gather([ob.n])
-            base = g.base_offset()
-        return OpResult(n, n + ob.n, "k_runs+k_seg_lengths+k_assemble", ob, base)
+        return OpResult(n, n + ob.n, "k_runs+k_seg_lengths+k_assemble", ob, g)
     if cfg["op"] == "split":
         pc = rx.split_device(shard.text)
         total = int(pc.offsets_tensor()[-1].item())
-        base = 0
+        g = None
         if multi:
             g = _gather_for(2, dev)
             g.gather([pc.n, total])
-            base = g.base_offset()
-        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan+k_seg_lengths+k_assemble", pc, base)
+        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan+k_seg_lengths+k_assemble", pc, g)
     raise ValueError(cfg["op"])
 
 
