@@ -1531,13 +1531,17 @@ __global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
     }
   }
   __syncthreads();
-  // ---- exclusive prefix popcount of the bitmap words (512 words, two per thread)
+  // ---- exclusive prefix popcount of the bitmap words (kAsmTile / 32 words, kWpt consecutive ones per thread)
   {
-    const int c0 = __popc(sh.bits[2 * tid]), c1 = __popc(sh.bits[2 * tid + 1]);
+    constexpr int kWpt = kAsmTile / 32 / kThreads;
+    static_assert(kWpt >= 1 && kWpt * kThreads * 32 == kAsmTile, "tile must be a multiple of 32 bits per thread");
+    int c[kWpt], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kWpt; ++i) { c[i] = __popc(sh.bits[kWpt * tid + i]); sum += c[i]; }
     int tot;
-    const int ex = block_exclusive_scan(c0 + c1, sh.scan_ws, &tot);
-    sh.wprefix[2 * tid] = (uint32_t)ex;
-    sh.wprefix[2 * tid + 1] = (uint32_t)(ex + c0);
+    int ex = block_exclusive_scan(sum, sh.scan_ws, &tot);
+#pragma unroll
+    for (int i = 0; i < kWpt; ++i) { sh.wprefix[kWpt * tid + i] = (uint32_t)ex; ex += c[i]; }
   }
   __syncthreads();
   // ---- rank of every marked segment -> its k

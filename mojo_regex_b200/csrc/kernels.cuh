@@ -121,9 +121,9 @@ struct SubTemplate {
 };
 
 // sub / split output assembly (k_assemble): one CTA per kAsmTile output bytes
-constexpr int kAsmRounds = 4;
-constexpr int kAsmTile = kThreads * 16 * kAsmRounds;  // 16 KiB
-constexpr int kAsmSegCap = 2560;                       // segment records staged per tile (40 KiB)
+constexpr int kAsmRounds = 2;
+constexpr int kAsmTile = kThreads * 16 * kAsmRounds;  // 8 KiB
+constexpr int kAsmSegCap = 1536;                       // segment records staged per tile (24 KiB)
 constexpr int kAsmTplCap = 256;
 constexpr int kSegRounds = 8;                          // k_seg_lengths: segments per thread
 constexpr int kSegTile = kThreads * kSegRounds;        // ... and per CTA                        // replacement bytes staged per tile
