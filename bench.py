@@ -162,10 +162,7 @@ def run_reference(args):
             return len(rx.sub(cfg["repl"].encode(), sh))
         if cfg["op"] == "split":
             return len(rx.split_raw(sh)[1])
-        n = 0
-        for j in range(0, sh.size, 128):
-            n += rx.search(sh[j:j + 128]) is not None
-        return n
+        return int((rx.search_batch(sh, 128)[:, 0] >= 0).sum())
 
     pool = ThreadPoolExecutor(max_workers=len(shards))
     times = []

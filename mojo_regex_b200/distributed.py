@@ -372,8 +372,7 @@ def cpu_baseline(config: str, cfg, shard: Shard, seconds: float = 10.0) -> dict:
         elif cfg["op"] == "split":
             rx.split_raw(sample)
         else:
-            for j in range(0, sample.size, 128):
-                rx.search(sample[j:j + 128])
+            rx.search_batch(sample, 128)
         return time.perf_counter() - t0
 
     probe_n = min(core.numel(), 8 << 20 if cfg["op"] != "search_batch" else 128 * 20000)

@@ -80,6 +80,9 @@ def _load():
         lib.orx_split.argtypes = [P(_CRegex), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                   P(ctypes.c_void_p), P(ctypes.c_void_p)]
         lib.orx_split.restype = ctypes.c_int64
+        lib.orx_search_batch.argtypes = [P(_CRegex), ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                         ctypes.c_void_p]
+        lib.orx_search_batch.restype = None
         _lib = lib
     return _lib
 
@@ -177,6 +180,14 @@ class OracleRegex:
     # -- module-level API semantics (matcher.mojo:1325-1415, 1857-1917)
     def search(self, text) -> Optional[Tuple[int, int]]:
         return self.match_next(text, 0)
+
+    def search_batch(self, text, stride: int) -> np.ndarray:
+        """search() per fixed-size document, looped in C (the reference's callers loop in compiled Mojo)."""
+        t = _as_u8(text)
+        n_docs = (t.size + stride - 1) // stride
+        out = np.empty((n_docs, 2), dtype=np.int64)
+        self._lib.orx_search_batch(ctypes.byref(self._c), t.ctypes.data, t.size, stride, n_docs, out.ctypes.data)
+        return out
 
     def match_first(self, text) -> Optional[Tuple[int, int]]:
         r = self.match_first_at(text, 0)

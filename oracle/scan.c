@@ -304,6 +304,19 @@ int orx_match_next(const orx_regex *re, const uint8_t *t, int64_t n, int64_t sta
   return dfa_match_next(re, t, n, start, &out[0], &out[1]);
 }
 
+/* The reference has no batch API: its callers loop `search(pattern, line)` over the documents
+ * (matcher.mojo:1325-1338).  This is that loop, compiled, so that the CPU baseline is not a
+ * Python-overhead measurement.  Document i = t[i*stride, min((i+1)*stride, n)); out[2i..2i+1] relative to
+ * the document, (-1,-1) = None. */
+void orx_search_batch(const orx_regex *re, const uint8_t *t, int64_t n, int64_t stride, int64_t n_docs, int64_t *out) {
+  for (int64_t i = 0; i < n_docs; ++i) {
+    const int64_t lo = i * stride, hi = lo + stride < n ? lo + stride : n;
+    int64_t se[2];
+    if (hi >= lo && orx_match_next(re, t + lo, hi - lo, 0, se)) { out[2 * i] = se[0]; out[2 * i + 1] = se[1]; }
+    else { out[2 * i] = -1; out[2 * i + 1] = -1; }
+  }
+}
+
 /* HybridMatcher._match_all_required_byte, matcher.mojo:864-898 */
 static void match_all_required_byte(const orx_regex *re, const uint8_t *t, int64_t n, orx_spans *out) {
   uint8_t needle = (uint8_t)re->required_byte;
