@@ -91,22 +91,29 @@ def gather_records(rec: List[int], device) -> List[List[int]]:
 
 
 class DeviceGather:
-    """All-gather of a small int64 record that never blocks the scan stream.
+    """All-gather of a small int64 record that never blocks the scan stream -- nor the thread that launches
+    the scans.
 
     The record (match count, output bytes) is known on the host when a matching call returns, so the
-    exchange has no dependency on the kernels: it runs on its own CUDA stream (H2D of the record from a
-    ring of pinned slots, one NCCL all-gather, an exclusive scan on the device) and overlaps the next
-    step's scan.  Consumers of `base_offset()` -- and anything that times the steps -- order themselves
-    after `self.stream` (`join(stream)`)."""
+    exchange has no dependency on the kernels.  It is issued by a worker thread (FIFO, so every rank issues
+    its collectives in the same order) on the gather's own CUDA stream: H2D of the record from a ring of
+    pinned slots, one NCCL all-gather, and, on demand, an exclusive scan on the device.  The launching
+    thread goes straight on to the next step's scan -- which spends its time inside the C library with the
+    GIL released -- so neither the ~0.1 ms of host work per collective nor its latency sits between two
+    scans.  Consumers of `base_offset()`, and anything that times the steps, call `join(stream)`."""
 
     RING = 64
 
     def __init__(self, width: int, device):
+        import queue
+        import threading
+
         import torch.distributed as dist
 
         self.world = dist.get_world_size() if (dist.is_available() and dist.is_initialized()) else 1
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.cuda = torch.device(device).type == "cuda"
+        self.device = device
         self.rec = torch.zeros(width, dtype=torch.int64, device=device)
         self.table = torch.zeros((self.world, width), dtype=torch.int64, device=device)
         self.host = torch.zeros((self.RING, width), dtype=torch.int64)
@@ -114,30 +121,63 @@ class DeviceGather:
             self.host = self.host.pin_memory()
         self.stream = torch.cuda.Stream(device=device) if self.cuda else None
         self.i = 0
+        self._q = queue.Queue()
+        self._err = None
+        self._worker = threading.Thread(target=self._run, name="mrx-exchange", daemon=True)
+        self._worker.start()
 
-    def gather(self, values: List[int]) -> torch.Tensor:
-        """-> (world, width) device tensor; row r is rank r's record (valid on self.stream)."""
+    def _issue(self, slot) -> None:
         import contextlib
 
         import torch.distributed as dist
 
-        slot = self.host[self.i % self.RING]
-        self.i += 1
-        for k, v in enumerate(values):
-            slot[k] = int(v)
         ctx = torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
         with ctx:
             self.rec.copy_(slot, non_blocking=True)
             if self.world > 1:
-                dist.all_gather_into_tensor(self.table, self.rec)
+                dist.all_gather_into_tensor(self.table.view(-1), self.rec)
             else:
                 self.table[0].copy_(self.rec)
+
+    def _run(self) -> None:
+        if self.cuda:
+            torch.cuda.set_device(self.device)
+        while True:
+            slot = self._q.get()
+            try:
+                if slot is not None and self._err is None:
+                    self._issue(slot)
+            except Exception as e:  # surfaced by the next drain()
+                self._err = e
+            finally:
+                self._q.task_done()
+
+    def gather(self, values: List[int]) -> torch.Tensor:
+        """Queue one exchange; -> the (world, width) device table (valid on self.stream after drain())."""
+        if self.i - self._done_floor() >= self.RING - 1:
+            self.drain()  # never overwrite a pinned slot whose copy may still be pending
+        slot = self.host[self.i % self.RING]
+        self.i += 1
+        for k, v in enumerate(values):
+            slot[k] = int(v)
+        self._q.put(slot)
         return self.table
+
+    def _done_floor(self) -> int:
+        return self.i - self._q.unfinished_tasks
+
+    def drain(self) -> None:
+        """Wait until every queued exchange has been ISSUED (not necessarily finished on the device)."""
+        self._q.join()
+        if self._err is not None:
+            err, self._err = self._err, None
+            raise err
 
     def base_offset(self, column: int = 0) -> torch.Tensor:
         """Exclusive prefix of `column` at this rank (0-d device tensor, valid on self.stream)."""
         import contextlib
 
+        self.drain()
         ctx = torch.cuda.stream(self.stream) if self.cuda else contextlib.nullcontext()
         with ctx:
             col = self.table[:, column]
@@ -145,6 +185,7 @@ class DeviceGather:
 
     def join(self, stream) -> None:
         """Make `stream` wait for every exchange issued so far."""
+        self.drain()
         if self.cuda:
             stream.wait_stream(self.stream)
 

@@ -104,3 +104,33 @@ def test_shard_bounds_and_offsets():
     # halos are the neighbours' bytes
     left = mrd._core("c2", 100_000, 0, "cpu")
     assert torch.equal(sh.buffer[:sh.core_begin], left[-sh.core_begin:])
+
+
+def _gather_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = mrd.DeviceGather(2, "cpu")
+        bases = []
+        for step in range(200):  # more exchanges than pinned slots: the ring must not be overrun
+            g.gather([10 * step + rank + 1, 1000 + step])
+            if step % 50 == 49:
+                bases.append(int(g.base_offset(0)))
+        g.join(None)
+        np.save(os.path.join(out_dir, f"table_{rank}.npy"), g.table.numpy().copy())
+        np.save(os.path.join(out_dir, f"bases_{rank}.npy"), np.array(bases))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_device_gather_worker_thread_two_rank_gloo(tmp_path):
+    """The count exchange is issued by a worker thread (FIFO): after 200 of them both ranks hold the same
+    table, and the exclusive offsets seen along the way are those of the step they were read at."""
+    world = 2
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    t0, t1 = np.load(tmp_path / "table_0.npy"), np.load(tmp_path / "table_1.npy")
+    assert np.array_equal(t0, t1)
+    assert t0.tolist() == [[10 * 199 + 1, 1199], [10 * 199 + 2, 1199]]
+    b0, b1 = np.load(tmp_path / "bases_0.npy"), np.load(tmp_path / "bases_1.npy")
+    assert b0.tolist() == [0, 0, 0, 0]
+    assert b1.tolist() == [10 * s + 1 for s in (49, 99, 149, 199)]
