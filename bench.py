@@ -224,6 +224,7 @@ def run_gpu(args):
         return mrd.run_op_device(rx, cfg, shard)
 
     def sync_all():
+        mrd.join_exchanges(lib_stream)  # queued count exchanges are issued before any other collective
         torch.cuda.synchronize()
         mr.synchronize()
         if world > 1:
