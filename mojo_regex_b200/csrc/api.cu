@@ -166,7 +166,13 @@ Filter make_filter(const Plan &pl) {
 }
 
 int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
-  if ((size_t)p.n_states * p.n_classes > (size_t)kMaxTrans)
+  // attempts walk a dense forward table (one lookup per byte) when it fits the table budget, else the
+  // class-compressed one (byte -> class, (state, class) -> state, state -> accepting)
+  std::vector<uint16_t> fwd;
+  uint16_t fwd_start = 0;
+  if (p.n_states > 0) build_forward_table(p, fwd, fwd_start);
+  const bool dense_fwd = p.n_states > 0 && fwd.size() * 2 <= (size_t)kMaxTrans;
+  if (!dense_fwd && (size_t)p.n_states * p.n_classes > (size_t)kMaxTrans)
     return fail(MRX_E_UNSUPPORTED, "automaton too large for the shared-memory table (" + std::to_string(p.n_states) + " states x " +
                                        std::to_string(p.n_classes) + " classes)");
   if (pl.literal.size() > (size_t)kMaxLiteral) return fail(MRX_E_UNSUPPORTED, "literal longer than 256 bytes");
@@ -176,16 +182,19 @@ int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
   h->n_classes = p.n_classes;
   h->start_state = p.start_state;
   h->flags = (p.flag(BF_END_ANCHOR) ? DF_END_ANCHOR : 0) | (p.flag(BF_START_ANCHOR) ? DF_START_ANCHOR : 0) |
-             (p.start_accepting() ? DF_START_ACCEPTING : 0) | (pl.shortcut ? DF_SHORTCUT : 0);
+             (p.start_accepting() ? DF_START_ACCEPTING : 0) | (pl.shortcut ? DF_SHORTCUT : 0) |
+             (dense_fwd ? DF_DENSE_FWD : 0);
+  h->fwd_start = fwd_start;
   h->literal_len = (int32_t)pl.literal.size();
   h->required_byte = p.required_byte;
-  h->trans_len = p.n_states * p.n_classes;
+  h->trans_len = dense_fwd ? (int32_t)(fwd.size() * 2) : p.n_states * p.n_classes;
   std::memcpy(h->byte_class, p.byte_class.data(), 256);
   std::memcpy(h->lookup, p.lookup.data(), 256);
   std::memcpy(h->cand, pl.cand.data(), 256);
   if (!p.accepting.empty()) std::memcpy(h->accepting, p.accepting.data(), p.accepting.size());
   if (!pl.literal.empty()) std::memcpy(h->literal, pl.literal.data(), pl.literal.size());
-  if (!p.trans.empty()) std::memcpy(h->trans, p.trans.data(), p.trans.size());
+  if (dense_fwd) std::memcpy(h->trans, fwd.data(), fwd.size() * 2);
+  else if (!p.trans.empty()) std::memcpy(h->trans, p.trans.data(), p.trans.size());
   void *d = nullptr;
   CUDA_TRY(cudaMalloc(&d, sizeof(DevProg)));
   CUDA_TRY(cudaMemcpyAsync(d, h, sizeof(DevProg), cudaMemcpyHostToDevice, g.stream));

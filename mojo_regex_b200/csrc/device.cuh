@@ -25,11 +25,13 @@ enum DevFlags : int32_t {
   DF_START_ANCHOR = 1 << 1,
   DF_START_ACCEPTING = 1 << 2,
   DF_SHORTCUT = 1 << 3,  // _try_match_simd is live inside attempts (dfa.mojo:1956-1968)
+  DF_DENSE_FWD = 1 << 4, // `trans` holds the dense forward table (uint16 row offsets, see RevTable::fwd)
+                         // instead of the class-compressed one; `fwd_start` = row of the start state
 };
 
 struct DevProg {
   int32_t n_states, n_classes, start_state, flags;
-  int32_t literal_len, required_byte, trans_len, pad;
+  int32_t literal_len, required_byte, trans_len, fwd_start;
   uint8_t byte_class[256];
   uint8_t lookup[256];    // CharacterClassSIMD.lookup_table of the engine's matcher
   uint8_t cand[256];      // candidate predicate of the active plan

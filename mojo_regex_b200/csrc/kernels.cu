@@ -101,9 +101,34 @@ struct Attempt {
       int64_t e = simd_shortcut(start);
       if (e >= 0) return e;
     }
-    int state = p->start_state;
     int64_t last = (p->flags & DF_START_ACCEPTING) ? start : -1;
     int64_t q = start;
+    if (p->flags & DF_DENSE_FWD) {
+      // one lookup per byte: row offset -> next row offset (0 = dead, bit 2 = accepting)
+      const uint8_t *fwd = p->trans;
+      uint32_t s = (uint32_t)p->fwd_start;
+      if (start >= tv.s_begin && start < tv.s_end) {  // walk inside the staged tile with 32-bit indices
+        const int lim = (int)((n < tv.s_end ? n : tv.s_end) - tv.s_begin);
+        int r = (int)(start - tv.s_begin), last_r = -1;
+        while (r < lim) {
+          s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * tv.s[r]);
+          if (s == 0) break;
+          ++r;
+          if (s & 4u) last_r = r;
+        }
+        if (last_r >= 0) last = tv.s_begin + last_r;
+        q = s == 0 ? n : tv.s_begin + r;
+      }
+      while (q < n) {  // continuation past the staged window (rare) or start outside it
+        s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * tv.at(q));
+        if (s == 0) break;
+        ++q;
+        if (s & 4u) last = q;
+      }
+      if (last >= 0 && (p->flags & DF_END_ANCHOR) && last != n) return -1;
+      return last;
+    }
+    int state = p->start_state;
     const int nc = p->n_classes;
     // fast path: walk inside the staged tile with 32-bit indices
     if (start >= tv.s_begin && start < tv.s_end) {

@@ -472,16 +472,21 @@ bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
   rt.rev.assign(((size_t)(520 * rt.n_rev + 8 + 15) & ~(size_t)15) / 2, 0);
   for (int i = 0; i < rt.n_rev; ++i)
     for (int b = 0; b < 256; ++b) rt.rev[(size_t)rev_off(i) / 2 + b] = (uint16_t)rev_off(next[(size_t)i * 256 + b]);
+  build_forward_table(p, rt.fwd, rt.fwd_start);
+  rt.valid = true;
+  return true;
+}
+
+void build_forward_table(const Program &p, std::vector<uint16_t> &fwd, uint16_t &start) {
+  const int n = p.n_states;
   auto fwd_off = [&](int q) { return 520 * (q + 1) + (p.accepting[q] ? 4 : 0); };
-  rt.fwd.assign(((size_t)(520 * (n + 1) + 8 + 15) & ~(size_t)15) / 2, 0);  // row 0 = dead: every entry 0
+  fwd.assign(((size_t)(520 * (n + 1) + 8 + 15) & ~(size_t)15) / 2, 0);  // row 0 = dead: every entry 0
   for (int q = 0; q < n; ++q)
     for (int b = 0; b < 256; ++b) {
       const int nx = p.next(q, b);
-      rt.fwd[(size_t)fwd_off(q) / 2 + b] = nx == kDead ? 0 : (uint16_t)fwd_off(nx);
+      fwd[(size_t)fwd_off(q) / 2 + b] = nx == kDead ? 0 : (uint16_t)fwd_off(nx);
     }
-  rt.fwd_start = (uint16_t)fwd_off(s0);
-  rt.valid = true;
-  return true;
+  start = (uint16_t)fwd_off(p.start_state);
 }
 
 namespace {

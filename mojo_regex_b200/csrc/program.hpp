@@ -114,6 +114,9 @@ struct Program {
 // Reverse automaton of `p` for the attempts of plan `pl`; false when the plan is not an attempt plan
 // or the construction exceeds 128 sets.
 bool build_reverse(const Program &p, const Plan &pl, RevTable &rt);
+// The reference's automaton as a dense table in the RevTable::fwd layout (one row per state plus a dead row
+// at offset 0, rows of accepting states flagged in bit 2 of their offset).
+void build_forward_table(const Program &p, std::vector<uint16_t> &fwd, uint16_t &start);
 
 // RawDfa (+meta) -> blob.  Returns false (with err) when the automaton does not fit the format.
 bool pack_blob(const RawDfa &dfa, const RegexMeta &meta, std::string &blob, std::string &err);
