@@ -180,7 +180,16 @@ __device__ __forceinline__ bool try_candidate(const ScanParams &prm, const Attem
       return true;
     case MRX_MODE_REQUIRED_BYTE: {  // matcher.mojo:876-897
       int64_t start = pos;
+      if (pos > at.tv.s_begin && pos <= at.tv.s_end) {
+        // back-scan inside the staged tile with 32-bit indices; leaves the tile only for runs that reach its start
+        const int floor_r = (int)((at.lo > at.tv.s_begin ? at.lo : at.tv.s_begin) - at.tv.s_begin);
+        int r = (int)(pos - at.tv.s_begin);
+        while (r > floor_r && at.p->lookup[at.tv.s[r - 1]]) --r;
+        start = at.tv.s_begin + r;
+        if (r > floor_r || start <= at.lo) goto scanned;  // stopped on a byte outside the class, or at the text start
+      }
       while (start > at.lo && at.p->lookup[at.tv.at(start - 1)]) --start;
+    scanned:
       if ((at.p->flags & DF_START_ANCHOR) && start > at.lo) return false;  // match_first, dfa.mojo:1866-1867
       int64_t e = at.dfa(start);
       if (e < 0 || e <= pos) return false;
