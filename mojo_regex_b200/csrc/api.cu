@@ -50,10 +50,14 @@ Lib g;
     if (_e != cudaSuccess) return fail(MRX_E_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
   } while (0)
 
+// Pool bucket sizes: powers of two up to 64 MiB, then eighths of the enclosing power of two (at most
+// 12.5 % over-allocation for the multi-gigabyte text, span and output buffers).
 size_t bucket(size_t n) {
   size_t b = 256;
   while (b < n) b <<= 1;
-  return b;
+  if (b <= (64u << 20)) return b;
+  const size_t step = b >> 4;  // b/2 < n <= b: steps of (b/2)/8
+  return (n + step - 1) / step * step;
 }
 int dev_alloc(size_t n, void **out) {
   const size_t b = bucket(n ? n : 1);
