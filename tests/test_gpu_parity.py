@@ -372,3 +372,94 @@ def test_search_batch_lines_kernel_against_oracle(pattern, alphabet):
         assert np.array_equal(rx.search_batch(text, doc_stride=64), got)
     finally:
         del os.environ["MRX_NO_LINES"]
+
+
+# ---- assembly kernels (k_seg_lengths / k_assemble) on shapes that stress the tile logic ---------------------
+def _rand_text(alphabet: bytes, n: int, seed: int) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)].copy()
+
+
+ASSEMBLE_CASES = [
+    # (pattern, replacement, alphabet, bytes)        what it stresses
+    (r"a", b"", b"ab", 300_000),                     # half of the segments have no output bytes, output shrinks
+    (r"a", b"", b"a", 70_000),                       # empty output
+    (r"a", b"X" * 300, b"abbbbbbb", 60_000),         # replacement longer than the staged template -> generic path
+    (r"[0-9]+", b"<>", b"0123456789 abc", 500_000),  # class runs
+    (r"a*", b"-", b"ab", 120_000),                   # zero-width matches: the extra byte after the replacement
+    (r"(\d{3})(\d{4})", rb"\2.\1", b"0123456789 x", 400_000),   # fixed-width groups, reordered
+    (r"hello", b"HELLO WORLD", b"helo ", 600_000),   # sparse matches, long gaps (segments spanning many tiles)
+    (r"b", b"bb", b"b", 40_000),                     # every byte a match: more segments per tile than records staged
+]
+
+
+@pytest.mark.parametrize("pattern,repl,alphabet,n", ASSEMBLE_CASES, ids=[c[0] + "->" + c[1][:6].decode() for c in ASSEMBLE_CASES])
+def test_sub_assembly_shapes_against_oracle(pattern, repl, alphabet, n):
+    text = _rand_text(alphabet, n, len(pattern) * 7919 + n)
+    want = oracle.compile(pattern).sub(repl, text)
+    got = mr.compile_regex(pattern).sub(repl, text)
+    assert len(got) == len(want)
+    assert got == want
+    w2 = oracle.compile(pattern).sub(repl, text, 1000)
+    assert mr.compile_regex(pattern).sub(repl, text, 1000) == w2
+
+
+@pytest.mark.parametrize("pattern,alphabet,n", [(r",", b"a,", 200_000), (r"[;,]", b"abc;,", 333_333), (r"\s*,\s*", b"ab, ", 0),
+                                                (r",", b",", 50_000), (r"x", b"abc", 100_000)])
+def test_split_assembly_shapes_against_oracle(pattern, alphabet, n):
+    if n == 0:   # blanks only next to commas (the reference is undefined on `, ,`): build "ab , ab,ab ,  ab ..."
+        rng = np.random.default_rng(5)
+        parts = []
+        for _ in range(40_000):
+            parts.append(b"ab"[: rng.integers(1, 3)])
+            parts.append(b" " * rng.integers(0, 3) + b"," + b" " * rng.integers(0, 3))
+        text = np.frombuffer(b"".join(parts) + b"ab", dtype=np.uint8)
+    else:
+        text = _rand_text(alphabet, n, n)
+    wd, wo = oracle.compile(pattern).split_raw(text)
+    gd, go = mr.compile_regex(pattern).split_raw(text)
+    assert np.array_equal(go, wo)
+    assert gd == wd
+    wd2, wo2 = oracle.compile(pattern).split_raw(text, 77)
+    gd2, go2 = mr.compile_regex(pattern).split_raw(text, 77)
+    assert np.array_equal(go2, wo2) and gd2 == wd2
+
+
+# ---- k_dense corner cases: token overflow (recompute path), long literals, many literals -------------------
+def test_dense_overflow_and_long_literals_against_oracle():
+    # more hits per 144-byte chunk than a thread buffers -> recompute path
+    t1 = np.frombuffer(b"foo" * 70_000 + b"fo" + b"foo" * 1000, dtype=np.uint8)
+    for pat in (r"foo", r"(foo|oof)"):
+        rx = mr.compile_regex(pat)
+        assert rx.info().findall_dense
+        assert np.array_equal(rx.match_all(t1).spans, oracle.compile(pat).findall(t1))
+    # a literal longer than chain A (80 bytes): chain B's warm-up reaches back past the thread's own chunk
+    lit = bytes(range(97, 123)) * 4            # 104 bytes
+    rng = np.random.default_rng(9)
+    parts = []
+    for _ in range(3000):
+        parts.append(bytes(rng.integers(97, 123, rng.integers(0, 200)).astype(np.uint8)))
+        parts.append(lit[: rng.integers(90, 105)])      # complete and truncated copies
+    t2 = np.frombuffer(b"".join(parts), dtype=np.uint8)
+    pat2 = lit.decode()
+    rx2 = mr.compile_regex(pat2)
+    assert rx2.info().findall_dense
+    want2 = oracle.compile(pat2).findall(t2)
+    assert len(want2) > 100
+    assert np.array_equal(rx2.match_all(t2).spans, want2)
+    m = rx2.match_next(t2, 12345)
+    assert (m.span() if m else None) == oracle.compile(pat2).match_next(t2, 12345)
+    # 24 literals of mixed lengths
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa", "lambda", "mu",
+             "nu", "xi", "omicron", "pi", "rho", "sigma", "tau", "upsilon", "phi", "chi", "psi", "omega"]
+    pat3 = "(" + "|".join(words) + ")"
+    t3 = _rand_text(b"abcdefghiklmnoprstuxyz ", 400_000, 3)
+    inject = np.frombuffer(" ".join(words * 50).encode(), dtype=np.uint8)
+    t3[1000:1000 + inject.size] = inject
+    try:
+        rx3 = mr.compile_regex(pat3)
+    except mr.UnsupportedPattern:
+        with pytest.raises(oracle.Unsupported):
+            oracle.compile(pat3)
+        return
+    assert np.array_equal(rx3.match_all(t3).spans, oracle.compile(pat3).findall(t3))
