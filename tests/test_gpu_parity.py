@@ -429,17 +429,18 @@ def test_split_assembly_shapes_against_oracle(pattern, alphabet, n):
 def test_dense_overflow_and_long_literals_against_oracle():
     # more hits per 144-byte chunk than a thread buffers -> recompute path
     t1 = np.frombuffer(b"foo" * 70_000 + b"fo" + b"foo" * 1000, dtype=np.uint8)
-    for pat in (r"foo", r"(foo|oof)"):
+    for pat, dense in ((r"foo", True), (r"(foo|bar)", True), (r"(foo|oof)", False)):  # foo/oof can overlap: k_scan + selection
         rx = mr.compile_regex(pat)
-        assert rx.info().findall_dense
+        assert bool(rx.info().findall_dense) == dense
         assert np.array_equal(rx.match_all(t1).spans, oracle.compile(pat).findall(t1))
-    # a literal longer than chain A (80 bytes): chain B's warm-up reaches back past the thread's own chunk
-    lit = bytes(range(97, 123)) * 4            # 104 bytes
+    # the longest literal the DFA path accepts (20 elements; longer ones classify MEDIUM, SURVEY B-6):
+    # complete and truncated copies at every alignment relative to the 80/64-byte chains
+    lit = bytes(range(97, 117))                # 20 bytes
     rng = np.random.default_rng(9)
     parts = []
-    for _ in range(3000):
-        parts.append(bytes(rng.integers(97, 123, rng.integers(0, 200)).astype(np.uint8)))
-        parts.append(lit[: rng.integers(90, 105)])      # complete and truncated copies
+    for _ in range(6000):
+        parts.append(bytes(rng.integers(97, 123, rng.integers(0, 120)).astype(np.uint8)))
+        parts.append(lit[: rng.integers(15, 21)])
     t2 = np.frombuffer(b"".join(parts), dtype=np.uint8)
     pat2 = lit.decode()
     rx2 = mr.compile_regex(pat2)
