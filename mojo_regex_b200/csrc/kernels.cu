@@ -870,6 +870,7 @@ struct RunsShared {
   long long warp_len[kThreads / 32];
   int warp_all[kThreads / 32];
   uint16_t tok[kThreads * kRunTok];  // UNIFORM_RUN: (start in chunk) | (length << 8) of a thread's matches
+  uint32_t head_bits[kThreads + 1];  // UNIFORM_RUN: membership bits of the first 32 bytes of every chunk (+ the halo's)
 };
 
 // membership bits of 16 bytes
@@ -1043,6 +1044,20 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
     }
   }
   if (lane == 31) { sh.warp_len[warp] = len; sh.warp_all[warp] = allf; }
+  // the in-class bytes that FOLLOW a chunk are the head bits of the next one (the last chunk looks into the halo)
+  sh.head_bits[tid] = cb.w[0];
+  if (tid == kThreads - 1) {
+    uint32_t hb = 0;
+    const int64_t h0 = tile_start + kTile;
+    if (h0 < prm.n && stage_bytes >= kTile + 32) {
+      const uint4 a = *reinterpret_cast<const uint4 *>(sh.text + kTile), b = *reinterpret_cast<const uint4 *>(sh.text + kTile + 16);
+      hb = class_bits16<FILT>(a, prm.filt, lut) | (class_bits16<FILT>(b, prm.filt, lut) << 16);
+    } else {
+      for (int i = 0; i < 32 && h0 + i < prm.n; ++i) hb |= (lut[tv.at(h0 + i)] ? 1u : 0u) << i;
+    }
+    if (h0 + 32 > prm.n) hb &= h0 < prm.n ? ((1u << (int)(prm.n - h0)) - 1u) : 0u;
+    sh.head_bits[kThreads] = hb;
+  }
   __syncthreads();
   // carry entering this thread = combine(tile carry, warps before, lanes before)
   long long carry = prm.tile_carry ? prm.tile_carry[tile] : 0;  // distance at tile start (0 if not in a run)
@@ -1059,6 +1074,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
   unsigned long long out_idx = 0;
   uint16_t *tok = sh.tok + tid * kRunTok;
   const bool tokens_ok = K <= 255;  // a match length fits the token
+  const uint32_t next_head = sh.head_bits[tid + 1];
   for (int pass = 0; pass < 2; ++pass) {
     cnt = 0;
     int i = 0;
@@ -1070,10 +1086,20 @@ __global__ void __launch_bounds__(kThreads, 3) k_runs(const RunsParams prm) {
       const long long d0 = (i0 == 0) ? carry : 0;  // distance of byte i0 from its run start
       int ext = 0;                                 // in-class bytes following the chunk, capped at K
       if (i1 == kChunk) {
-        int64_t q = chunk0 + kChunk;
-        while (ext < K && q < prm.n && lut[tv.at(q)]) { ++ext; ++q; }
+        if (K <= 32) {
+          const int run = __ffs(~next_head) - 1;  // leading in-class bytes of the next chunk (32 if all)
+          ext = run < 0 ? 32 : run;
+          if (ext > K) ext = K;
+        } else {
+          int64_t q = chunk0 + kChunk;
+          while (ext < K && q < prm.n && lut[tv.at(q)]) { ++ext; ++q; }
+        }
       }
-      int first = i0 + (int)((K - (d0 % K)) % K);
+      int first = i0;  // a run that starts inside the chunk starts a match; one that continues from before
+      if (d0 != 0) {   // the chunk start resumes at its phase (64-bit modulo only for runs longer than 2 GiB)
+        const int ph = d0 < 0x7fffffffll ? (int)((unsigned)d0 % (unsigned)K) : (int)(d0 % K);
+        first = i0 + (ph ? K - ph : 0);
+      }
       for (int s = first; s < i1; s += K) {
         const int rem = (i1 - s) + ext;  // exact when < K
         const int L = rem >= K ? K : rem;
