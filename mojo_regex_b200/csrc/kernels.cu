@@ -458,7 +458,20 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
   uint32_t sa = 0, sb = 0;
   {
     const int w = sh.hdr.max_len - 1;
-    if (tid > 0 && w <= kChunk) {
+    // history bytes of a chain that lie in this tile: for w <= 16 they sit in the one aligned 16-byte vector
+    // before the chain (one conflict-free LDS.128 instead of w byte loads that collide 4-way across lanes)
+    auto warm16 = [&](const uint8_t *vec_end, uint32_t s0) {
+      const uint4 v = *reinterpret_cast<const uint4 *>(vec_end - 16);
+      const uint32_t ws[4] = {v.x, v.y, v.z, v.w};
+      uint32_t st = s0;
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (i >= 16 - w) st = *reinterpret_cast<const uint16_t *>(tbl + st + 2u * ((ws[i >> 2] >> (8 * (i & 3))) & 0xffu));
+      return st;
+    };
+    if (tid > 0 && w <= 16) {
+      if (chunk_rel <= valid) sa = warm16(sh.text + chunk_rel, 0u);
+    } else if (tid > 0 && w <= kChunk) {
       if (chunk_rel <= valid)
         for (int r = chunk_rel - w; r < chunk_rel; ++r) sa = *reinterpret_cast<const uint16_t *>(tbl + sa + 2u * sh.text[r]);
     } else {
@@ -468,7 +481,9 @@ __device__ __forceinline__ int dense_scan_chunk(const DenseParams &prm, DenseSha
       const int64_t stop = chunk0 < prm.n ? chunk0 : prm.n;
       for (; q < stop; ++q) sa = *reinterpret_cast<const uint16_t *>(tbl + sa + 2u * tv.at(q));
     }
-    if (w <= kChainA) {
+    if (w <= 16) {
+      sb = warm16(sh.text + chunk_rel + kChainA, 0u);
+    } else if (w <= kChainA) {
       for (int r = chunk_rel + kChainA - w; r < chunk_rel + kChainA; ++r)
         sb = *reinterpret_cast<const uint16_t *>(tbl + sb + 2u * sh.text[r]);
     } else {  // literals longer than chain A: B's history reaches back past this chunk
