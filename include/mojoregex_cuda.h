@@ -195,6 +195,15 @@ int mrx_sub(const mrx_regex *re, const uint8_t *repl, size_t repl_n, int64_t cou
 int mrx_split(const mrx_regex *re, const mrx_text *t, int64_t maxsplit, int location,
               mrx_pieces *out);
 
+/* sub / split with the text in HOST memory (what the reference's callers pass).  Equivalent to
+ * mrx_text_upload + mrx_sub / mrx_split (MRX_OUT_HOST) + mrx_text_free; large texts are cut after bytes that
+ * cannot be part of any match and the chunks are uploaded, processed and downloaded as a three-stream
+ * pipeline (count != 0 / maxsplit != 0, or a pattern without such bytes, take the plain path).  `host`
+ * should be page-locked for the copies to overlap. */
+int mrx_sub_host(const mrx_regex *re, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
+                 size_t n, mrx_bytes *out);
+int mrx_split_host(const mrx_regex *re, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out);
+
 void mrx_spans_free(mrx_spans *s);
 void mrx_bytes_free(mrx_bytes *b);
 void mrx_pieces_free(mrx_pieces *p);

@@ -84,7 +84,7 @@ EXPORTS = [
     "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
     "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
-    "mrx_split", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
+    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
 ]
 
 
@@ -125,6 +125,8 @@ def _load() -> ctypes.CDLL:
     lib.mrx_search_batch.argtypes = [vp, vp, vp, sz, i64, c.c_int, vp]
     lib.mrx_sub.argtypes = [vp, c.c_char_p, sz, i64, vp, c.c_int, P(_Bytes)]
     lib.mrx_split.argtypes = [vp, vp, i64, c.c_int, P(_Pieces)]
+    lib.mrx_sub_host.argtypes = [vp, c.c_char_p, sz, i64, vp, sz, P(_Bytes)]
+    lib.mrx_split_host.argtypes = [vp, vp, sz, i64, P(_Pieces)]
     lib.mrx_spans_free.argtypes = [P(_Spans)]
     lib.mrx_spans_free.restype = None
     lib.mrx_bytes_free.argtypes = [P(_Bytes)]
@@ -375,6 +377,7 @@ class CompiledRegex:
         """findall over `nbytes` at host address `ptr` (page-locked for full speed): upload, scan and span
         download are pipelined inside the library.  The returned MatchList views the library's pinned
         result buffer (no copy); it is released when the MatchList is garbage collected."""
+        _ensure_init()
         sp = _Spans()
         _check(lib.mrx_findall_host_shard(self._h, ptr, nbytes, core_begin, nbytes if core_end is None else core_end,
                                           global_offset, ctypes.byref(sp)))
@@ -456,6 +459,22 @@ class CompiledRegex:
         t, _ = _text_of(text)
         pc = _Pieces()
         _check(lib.mrx_split(self._h, t._h, maxsplit, OUT_HOST, ctypes.byref(pc)))
+        return HostPieces(pc)
+
+    def sub_host(self, repl, ptr: int, nbytes: int, count: int = 0) -> "HostBytes":
+        """sub() over `nbytes` at host address `ptr` (page-locked for full speed): chunked upload / rewrite /
+        download pipeline inside the library; the result stays in the library's pinned buffer."""
+        _ensure_init()
+        r = _as_bytes(repl)
+        ob = _Bytes()
+        _check(lib.mrx_sub_host(self._h, r, len(r), count, ptr, nbytes, ctypes.byref(ob)))
+        return HostBytes(ob)
+
+    def split_host(self, ptr: int, nbytes: int, maxsplit: int = 0) -> "HostPieces":
+        """split() over a host buffer, pipelined like sub_host; pieces stay in the library's pinned buffers."""
+        _ensure_init()
+        pc = _Pieces()
+        _check(lib.mrx_split_host(self._h, ptr, nbytes, maxsplit, ctypes.byref(pc)))
         return HostPieces(pc)
 
     def split_raw(self, text, maxsplit: int = 0):

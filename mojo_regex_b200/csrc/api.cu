@@ -1356,6 +1356,217 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   return MRX_OK;
 }
 
+}  // extern "C"
+
+// ---- sub / split over a host buffer, pipelined chunk by chunk ----------------------------------------
+// A byte that no state of the automaton can consume, that is in neither the matcher class (back-scans) nor
+// a candidate of either plan, and that occurs in none of the literals cannot be part of any match.  Cutting
+// the text right after such "dead" bytes gives chunks no match can straddle, so sub(text) is the
+// concatenation of sub(chunk) and split(text) is the concatenation of the chunks' pieces with the piece
+// around every cut glued together.  Chunks are uploaded on the H2D stream, processed on the compute
+// stream as they land (mrx_sub / mrx_split on a view of the chunk) and their results travel back on the
+// D2H stream: the call costs about max(upload, download) instead of their sum.
+namespace {
+
+bool dead_bytes(const Program &p, bool dead[256]) {
+  if (p.flag(BF_WILDCARD_ANY) || p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR) || p.start_accepting()) return false;
+  if (p.findall.unsupported || p.search.unsupported) return false;
+  bool any = false;
+  for (int b = 0; b < 256; ++b) {
+    bool d = !p.lookup[b] && !p.findall.cand[b] && !p.search.cand[b];
+    for (int q = 0; d && q < p.n_states; ++q) d = p.next(q, b) == kDead;
+    for (const std::string *lit : {&p.literal, &p.exact, &p.prefilter, &p.findall.literal, &p.search.literal})
+      if (d && lit->find((char)b) != std::string::npos) d = false;
+    dead[b] = d;
+    any = any || d;
+  }
+  return any;
+}
+
+// chunk starts: 0 = c[0] < c[1] < ... < c.back() = n; every inner cut follows a dead byte
+std::vector<int64_t> chunk_cuts(const uint8_t *host, int64_t n, const bool dead[256]) {
+  std::vector<int64_t> c{0};
+  constexpr int64_t kSearch = 1ll << 20;
+  while (true) {
+    const int64_t nominal = c.back() + kPipeChunk;
+    if (nominal + kPipeChunk / 2 >= n) break;  // the last chunk takes a tail shorter than half a chunk as well
+    int64_t cut = -1;
+    for (int64_t q = nominal; q < std::min(n, nominal + kSearch); ++q)
+      if (dead[host[q]]) { cut = q + 1; break; }
+    if (cut < 0 || cut >= n) break;
+    c.push_back(cut);
+  }
+  c.push_back(n);
+  return c;
+}
+
+struct ChunkedUpload {
+  DevTmp buf;
+  std::vector<int64_t> dev_off;  // 16-byte aligned device offset of every chunk
+  int start(const uint8_t *host, const std::vector<int64_t> &cuts) {
+    const size_t k = cuts.size() - 1;
+    int rc = buf.get((size_t)cuts.back() + 16 * k + 512);
+    if (rc) return rc;
+    int64_t a = 0;
+    for (size_t i = 0; i < k; ++i) {
+      const int64_t len = cuts[i + 1] - cuts[i];
+      dev_off.push_back(a);
+      CUDA_TRY(cudaMemcpyAsync(buf.as<uint8_t>() + a, host + cuts[i], (size_t)len, cudaMemcpyHostToDevice, g.s_in));
+      CUDA_TRY(cudaEventRecord(pipe_event(i), g.s_in));
+      a = (a + len + 15) & ~15ll;
+    }
+    CUDA_TRY(cudaMemsetAsync(buf.as<uint8_t>() + a, 0, 512, g.s_in));
+    return MRX_OK;
+  }
+};
+
+// pinned result buffer that can grow (copies what has been received so far)
+struct GrowHost {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t need, size_t used) {
+    if (need <= cap) return MRX_OK;
+    CUDA_TRY(cudaStreamSynchronize(g.s_out));
+    void *q = nullptr;
+    const size_t ncap = need + need / 4 + 4096;
+    int rc = host_alloc(ncap, &q);
+    if (rc) return rc;
+    if (p && used) std::memcpy(q, p, used);
+    host_release(p);
+    p = q;
+    cap = ncap;
+    return MRX_OK;
+  }
+};
+
+}  // namespace
+
+extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
+                            size_t n, mrx_bytes *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !out || (!host && n) || (!repl && repl_n)) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  bool dead[256];
+  std::vector<int64_t> cuts;
+  if (count == 0 && (int64_t)n >= 2 * kPipeChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
+  if (cuts.size() < 3) {  // small text, a replacement limit, or no cut points: upload, then one call
+    mrx_text *t = nullptr;
+    if ((rc = mrx_text_upload(host, n, &t))) return rc;
+    rc = mrx_sub(re_c, repl, repl_n, count, t, MRX_OUT_HOST, out);
+    mrx_text_free(t);
+    return rc;
+  }
+  if ((rc = ensure_uploaded(re))) return rc;
+  ChunkedUpload up;
+  if ((rc = up.start(host, cuts))) return rc;
+  const size_t k = cuts.size() - 1;
+  std::vector<mrx_bytes> parts(k);
+  GrowHost res;
+  size_t off = 0;
+  auto cleanup = [&](size_t upto) { for (size_t i = 0; i < upto; ++i) mrx_bytes_free(&parts[i]); };
+  for (size_t i = 0; i < k; ++i) {
+    const int64_t len = cuts[i + 1] - cuts[i];
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event(i), 0));
+    mrx_text view;
+    view.d = up.buf.as<uint8_t>() + up.dev_off[i]; view.n = (size_t)len; view.owned = false; view.core_begin = 0; view.core_end = (size_t)len;
+    rc = mrx_sub(re_c, repl, repl_n, 0, &view, MRX_OUT_DEVICE, &parts[i]);  // returns with the chunk's output complete
+    if (rc) { cudaStreamSynchronize(g.s_out); cudaStreamSynchronize(g.s_in); cleanup(i); host_release(res.p); return rc; }
+    // size the result from the expansion seen so far
+    const double ratio = (double)(off + parts[i].n) / (double)cuts[i + 1];
+    const size_t guess = (size_t)((double)n * ratio * 1.02) + (1u << 20);
+    if ((rc = res.reserve(std::max(off + parts[i].n, i + 1 < k ? guess : off + parts[i].n), off))) { cleanup(i + 1); return rc; }
+    if (parts[i].n) CUDA_TRY(cudaMemcpyAsync((uint8_t *)res.p + off, parts[i].bytes, parts[i].n, cudaMemcpyDeviceToHost, g.s_out));
+    off += parts[i].n;
+  }
+  CUDA_TRY(cudaStreamSynchronize(g.s_out));
+  CUDA_TRY(cudaStreamSynchronize(g.s_in));
+  cleanup(k);
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = res.p;
+  out->_owner = own;
+  out->bytes = (uint8_t *)res.p;
+  out->n = off;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
+extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !out || (!host && n)) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  bool dead[256];
+  std::vector<int64_t> cuts;
+  if (maxsplit == 0 && (int64_t)n >= 2 * kPipeChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
+  if (cuts.size() < 3) {
+    mrx_text *t = nullptr;
+    if ((rc = mrx_text_upload(host, n, &t))) return rc;
+    rc = mrx_split(re_c, t, maxsplit, MRX_OUT_HOST, out);
+    mrx_text_free(t);
+    return rc;
+  }
+  if ((rc = ensure_uploaded(re))) return rc;
+  ChunkedUpload up;
+  if ((rc = up.start(host, cuts))) return rc;
+  const size_t k = cuts.size() - 1;
+  std::vector<mrx_pieces> parts(k);
+  GrowHost bytes, offs;
+  size_t nbytes = 0;    // output bytes received so far
+  size_t nsep = 0;      // separators (= inner piece boundaries) so far
+  auto cleanup = [&](size_t upto) { for (size_t i = 0; i < upto; ++i) mrx_pieces_free(&parts[i]); };
+  auto bail = [&](int code, size_t upto) {
+    cudaStreamSynchronize(g.s_out); cudaStreamSynchronize(g.s_in);
+    cleanup(upto); host_release(bytes.p); host_release(offs.p);
+    return code;
+  };
+  for (size_t i = 0; i < k; ++i) {
+    const int64_t len = cuts[i + 1] - cuts[i];
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event(i), 0));
+    mrx_text view;
+    view.d = up.buf.as<uint8_t>() + up.dev_off[i]; view.n = (size_t)len; view.owned = false; view.core_begin = 0; view.core_end = (size_t)len;
+    rc = mrx_split(re_c, &view, 0, MRX_OUT_DEVICE, &parts[i]);
+    if (rc) return bail(rc, i);
+    const size_t m = parts[i].n - 1;  // separators in this chunk
+    // bytes of this chunk's pieces = its last offset; then shift its inner boundaries into the whole output
+    CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 10, parts[i].offsets + (m + 1), 8, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    const size_t cb = (size_t)g.h_scalars[10];
+    launch_add_i64(parts[i].offsets + 1, (int64_t)m, (int64_t)nbytes, g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaEventRecord(pipe_event(k + i), g.stream));
+    const double done = (double)cuts[i + 1];
+    const size_t gb = (size_t)((double)n * ((double)(nbytes + cb) / done) * 1.02) + (1u << 20);
+    const size_t go = (size_t)((double)n * ((double)(nsep + m) / done) * 1.02) + 4096;
+    const bool last = i + 1 == k;
+    if ((rc = bytes.reserve(std::max(nbytes + cb, last ? nbytes + cb : gb), nbytes))) return bail(rc, i + 1);
+    if ((rc = offs.reserve(sizeof(int64_t) * (std::max(nsep + m, last ? nsep + m : go) + 2), sizeof(int64_t) * (nsep + 1)))) return bail(rc, i + 1);
+    CUDA_TRY(cudaStreamWaitEvent(g.s_out, pipe_event(k + i), 0));
+    if (cb) CUDA_TRY(cudaMemcpyAsync((uint8_t *)bytes.p + nbytes, parts[i].bytes, cb, cudaMemcpyDeviceToHost, g.s_out));
+    if (m) CUDA_TRY(cudaMemcpyAsync((int64_t *)offs.p + 1 + nsep, parts[i].offsets + 1, sizeof(int64_t) * m, cudaMemcpyDeviceToHost, g.s_out));
+    nbytes += cb;
+    nsep += m;
+  }
+  CUDA_TRY(cudaStreamSynchronize(g.s_out));
+  CUDA_TRY(cudaStreamSynchronize(g.s_in));
+  cleanup(k);
+  ((int64_t *)offs.p)[0] = 0;
+  ((int64_t *)offs.p)[nsep + 1] = (int64_t)nbytes;
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = bytes.p;
+  own->host[1] = offs.p;
+  out->_owner = own;
+  out->bytes = (uint8_t *)bytes.p;
+  out->offsets = (int64_t *)offs.p;
+  out->n = nsep + 1;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
+extern "C" {
+
 void mrx_spans_free(mrx_spans *s) {
   if (!s) return;
   release_owner(s->_owner);

@@ -1272,6 +1272,11 @@ __global__ void k_fill_u64(unsigned long long *p, int64_t n, unsigned long long 
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
 }
+// p[i] += v (piece offsets of one chunk of a chunked split -> offsets in the whole output)
+__global__ void k_add_i64(int64_t *p, int64_t n, int64_t v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] += v;
+}
 
 // ---------------------------------------------------------------------------------------------
 // greedy selection over a potential list sorted by key (= the reference's `pos = end` restart
@@ -1771,6 +1776,10 @@ void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, c
                            int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st) {
   k_batch_finalize<<<(unsigned)((n_docs + 255) / 256), 256, 0, st>>>(doc_best, n_docs, doc_offsets, doc_stride, n,
                                                                      empty_at_end, out);
+}
+void launch_add_i64(int64_t *p, int64_t n, int64_t v, cudaStream_t st) {
+  if (n <= 0) return;
+  k_add_i64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);
 }
 void launch_fill_u64(unsigned long long *p, int64_t n, unsigned long long v, cudaStream_t st) {
   k_fill_u64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, n, v);

@@ -154,6 +154,7 @@ void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int6
 void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
                            int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st);
 void launch_fill_u64(unsigned long long *p, int64_t n, unsigned long long v, cudaStream_t st);
+void launch_add_i64(int64_t *p, int64_t n, int64_t v, cudaStream_t st);
 void launch_select_prefix_max(const int64_t *spans, int64_t m, unsigned long long *desc, unsigned int *ticket,
                               int64_t *pmax, cudaStream_t st);
 void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel,

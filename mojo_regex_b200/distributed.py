@@ -373,6 +373,16 @@ def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
         ml = rx.match_all_host(host_pinned.data_ptr(), host_pinned.numel(), shard.core_begin, shard.core_end,
                                shard.global_offset)
         return int(ml.spans.nbytes)
+    if cfg["op"] == "sub" and shard.core_begin == 0 and shard.core_end == host_pinned.numel():
+        hb = rx.sub_host(cfg["repl"], host_pinned.data_ptr(), host_pinned.numel())
+        nb = hb.n
+        hb.close()
+        return nb
+    if cfg["op"] == "split" and shard.core_begin == 0 and shard.core_end == host_pinned.numel():
+        hp = rx.split_host(host_pinned.data_ptr(), host_pinned.numel())
+        nb = int(hp.data.nbytes) + int(hp.offsets.nbytes)
+        hp.close()
+        return nb
     t = mr.Text.from_pinned(host_pinned.data_ptr(), host_pinned.numel())
     t.set_window(shard.core_begin, shard.core_end, shard.global_offset)
     try:

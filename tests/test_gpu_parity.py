@@ -464,3 +464,49 @@ def test_dense_overflow_and_long_literals_against_oracle():
             oracle.compile(pat3)
         return
     assert np.array_equal(rx3.match_all(t3).spans, oracle.compile(pat3).findall(t3))
+
+
+# ---- host-buffer sub / split (mrx_sub_host / mrx_split_host): chunked three-stream pipeline ----------------
+def test_sub_host_pipelined_matches_oracle():
+    cfg = corpora.CONFIGS["c4"]
+    n = 3 * PIPE_CHUNK + 4321
+    text = corpora.make("c4", n)
+    for b in (PIPE_CHUNK, 2 * PIPE_CHUNK):      # a long digit run right where a cut would nominally fall
+        text[b - 15:b + 25] = torch.tensor(list(b"1234567890" * 4), dtype=torch.uint8)
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    host.copy_(text)
+    rx = mr.compile_regex(cfg["pattern"])
+    want = oracle.compile(cfg["pattern"]).sub(cfg["repl"].encode(), text.numpy())
+    hb = rx.sub_host(cfg["repl"], host.data_ptr(), n)
+    assert hb.n == len(want)
+    assert hb.tobytes() == want
+    hb.close()
+    # a replacement limit takes the plain path through the same entry point
+    w1 = oracle.compile(cfg["pattern"]).sub(cfg["repl"].encode(), text.numpy()[: 1 << 20], 5)
+    h1 = rx.sub_host(cfg["repl"], host.data_ptr(), 1 << 20, 5)
+    assert h1.tobytes() == w1
+    # no-group replacement, class-run pattern, shrinking output
+    w2 = oracle.compile(r"[0-9]+").sub(b"#", text.numpy())
+    h2 = mr.compile_regex(r"[0-9]+").sub_host(b"#", host.data_ptr(), n)
+    assert h2.tobytes() == w2
+
+
+def test_split_host_pipelined_matches_oracle():
+    n = 3 * PIPE_CHUNK + 999
+    text = corpora.make("c5", n)
+    host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    host.copy_(text)
+    rx = mr.compile_regex(r"\s*,\s*")
+    wd, wo = oracle.compile(r"\s*,\s*").split_raw(text.numpy())
+    hp = rx.split_host(host.data_ptr(), n)
+    assert hp.n == len(wo) - 1
+    assert np.array_equal(hp.offsets, wo)
+    assert hp.data.tobytes() == wd
+    hp.close()
+    # maxsplit and small texts take the plain path
+    wd2, wo2 = oracle.compile(r"\s*,\s*").split_raw(text.numpy()[:300_000], 7)
+    h2 = rx.split_host(host.data_ptr(), 300_000, 7)
+    assert np.array_equal(h2.offsets, wo2) and h2.data.tobytes() == wd2
+    # a pattern without "dead" bytes (every byte can be part of a match) is not chunked
+    t3 = np.frombuffer(b"ab" * 1000, dtype=np.uint8)
+    assert mr.compile_regex(r"a").split_raw(t3)[0] == oracle.compile(r"a").split_raw(t3)[0]
