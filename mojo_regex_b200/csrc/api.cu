@@ -1384,12 +1384,14 @@ bool dead_bytes(const Program &p, bool dead[256]) {
 }
 
 // chunk starts: 0 = c[0] < c[1] < ... < c.back() = n; every inner cut follows a dead byte
+// (sub / split run five kernels and three host synchronisations per chunk: larger chunks than findall's)
+constexpr int64_t kEditChunk = 128ll << 20;
 std::vector<int64_t> chunk_cuts(const uint8_t *host, int64_t n, const bool dead[256]) {
   std::vector<int64_t> c{0};
   constexpr int64_t kSearch = 1ll << 20;
   while (true) {
-    const int64_t nominal = c.back() + kPipeChunk;
-    if (nominal + kPipeChunk / 2 >= n) break;  // the last chunk takes a tail shorter than half a chunk as well
+    const int64_t nominal = c.back() + kEditChunk;
+    if (nominal + kEditChunk / 2 >= n) break;  // the last chunk takes a tail shorter than half a chunk as well
     int64_t cut = -1;
     for (int64_t q = nominal; q < std::min(n, nominal + kSearch); ++q)
       if (dead[host[q]]) { cut = q + 1; break; }
@@ -1450,7 +1452,7 @@ extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t r
   std::memset(out, 0, sizeof *out);
   bool dead[256];
   std::vector<int64_t> cuts;
-  if (count == 0 && (int64_t)n >= 2 * kPipeChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
+  if (count == 0 && (int64_t)n >= 2 * kEditChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
   if (cuts.size() < 3) {  // small text, a replacement limit, or no cut points: upload, then one call
     mrx_text *t = nullptr;
     if ((rc = mrx_text_upload(host, n, &t))) return rc;
@@ -1500,7 +1502,7 @@ extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t
   std::memset(out, 0, sizeof *out);
   bool dead[256];
   std::vector<int64_t> cuts;
-  if (maxsplit == 0 && (int64_t)n >= 2 * kPipeChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
+  if (maxsplit == 0 && (int64_t)n >= 2 * kEditChunk && dead_bytes(re->prog, dead)) cuts = chunk_cuts(host, (int64_t)n, dead);
   if (cuts.size() < 3) {
     mrx_text *t = nullptr;
     if ((rc = mrx_text_upload(host, n, &t))) return rc;

@@ -467,11 +467,14 @@ def test_dense_overflow_and_long_literals_against_oracle():
 
 
 # ---- host-buffer sub / split (mrx_sub_host / mrx_split_host): chunked three-stream pipeline ----------------
+EDIT_CHUNK = 128 << 20
+
+
 def test_sub_host_pipelined_matches_oracle():
     cfg = corpora.CONFIGS["c4"]
-    n = 3 * PIPE_CHUNK + 4321
+    n = 3 * EDIT_CHUNK + 4321
     text = corpora.make("c4", n)
-    for b in (PIPE_CHUNK, 2 * PIPE_CHUNK):      # a long digit run right where a cut would nominally fall
+    for b in (EDIT_CHUNK, 2 * EDIT_CHUNK):      # a long digit run right where a cut would nominally fall
         text[b - 15:b + 25] = torch.tensor(list(b"1234567890" * 4), dtype=torch.uint8)
     host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     host.copy_(text)
@@ -492,7 +495,7 @@ def test_sub_host_pipelined_matches_oracle():
 
 
 def test_split_host_pipelined_matches_oracle():
-    n = 3 * PIPE_CHUNK + 999
+    n = 3 * EDIT_CHUNK + 999
     text = corpora.make("c5", n)
     host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
     host.copy_(text)
@@ -510,3 +513,20 @@ def test_split_host_pipelined_matches_oracle():
     # a pattern without "dead" bytes (every byte can be part of a match) is not chunked
     t3 = np.frombuffer(b"ab" * 1000, dtype=np.uint8)
     assert mr.compile_regex(r"a").split_raw(t3)[0] == oracle.compile(r"a").split_raw(t3)[0]
+
+
+def test_findall_host_capacity_overflow_falls_back():
+    """More matches than the first capacity guess (one per 8 bytes): the pipelined call notices, finishes the
+    upload and repeats the list job with the exact count."""
+    mr.clear_regex_cache()      # a fresh regex: no remembered density
+    n = 2 * PIPE_CHUNK + 77
+    host = torch.full((n,), ord("a"), dtype=torch.uint8).pin_memory()
+    host[5::97] = ord("b")
+    rx = mr.compile_regex(r"a")
+    got = rx.match_all_host(host.data_ptr(), n).spans
+    t = host.numpy()
+    starts = np.flatnonzero(t == ord("a"))
+    assert got.shape[0] == starts.size
+    assert np.array_equal(got[:, 0], starts) and np.array_equal(got[:, 1], starts + 1)
+    got2 = rx.match_all_host(host.data_ptr(), n).spans      # now sized from the remembered density: pipelined
+    assert np.array_equal(got2, got)
