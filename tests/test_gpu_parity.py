@@ -530,3 +530,26 @@ def test_findall_host_capacity_overflow_falls_back():
     assert np.array_equal(got[:, 0], starts) and np.array_equal(got[:, 1], starts + 1)
     got2 = rx.match_all_host(host.data_ptr(), n).spans      # now sized from the remembered density: pipelined
     assert np.array_equal(got2, got)
+
+
+@pytest.mark.parametrize("pattern,alphabet", FUZZ, ids=[p or "<empty>" for p, _ in FUZZ])
+def test_fuzz_medium_texts_all_ops_against_oracle(pattern, alphabet):
+    """Every pattern of the fuzz table on ~200 KB (several scan tiles, dozens of assembly tiles, hundreds of
+    segment tiles): findall, search, match_first, sub, split -- and batch search through whichever kernel
+    the planner picks -- against the oracle."""
+    import zlib
+
+    rng = random.Random(zlib.crc32(pattern.encode()))
+    n = 200_000 + rng.randrange(0, 5000)
+    text = bytes(ord(rng.choice(alphabet)) for _ in range(n))
+    _compare_all_ops(pattern, text)
+    rx = mr.compile_regex(pattern)
+    info = rx.info()
+    if info.search_mode not in (-1, 0, 1):   # batch search: not for unsupported / `.*` / anchored plans
+        orx = oracle.compile(pattern)
+        arr = np.frombuffer(text, dtype=np.uint8)
+        for stride in (48, 100):
+            got = rx.search_batch(arr, doc_stride=stride)
+            for i in range(0, len(got), 17):
+                r = orx.search(arr[i * stride:(i + 1) * stride])
+                assert tuple(got[i]) == (r if r else (-1, -1)), (pattern, stride, i)
