@@ -1080,19 +1080,40 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
   if (n_docs == 0) return MRX_OK;
   const int64_t n = (int64_t)t->n;
-  if (pl.mode == MRX_MODE_WILDCARD_ANY || pl.mode == MRX_MODE_ANCHORED)
-    return fail(MRX_E_UNSUPPORTED, "batch search for `.*` / anchored patterns is not built yet");
+  const bool trivial = pl.mode == MRX_MODE_WILDCARD_ANY || pl.mode == MRX_MODE_ANCHORED;
   // offsets / results on the device
   DevTmp d_offs, d_best, d_out;
   const int64_t *offs_dev = nullptr;
   if (doc_offsets) {
     if (location == MRX_OUT_HOST) {
+      // host offsets are validated here (a bad table would send the kernels out of bounds)
+      if (doc_offsets[0] < 0 || doc_offsets[n_docs] > n) return fail(MRX_E_INVALID, "doc_offsets outside the text");
+      for (size_t i = 0; i < n_docs; ++i)
+        if (doc_offsets[i] > doc_offsets[i + 1]) return fail(MRX_E_INVALID, "doc_offsets must be non-decreasing");
       if ((rc = d_offs.get(sizeof(int64_t) * (n_docs + 1)))) return rc;
       CUDA_TRY(cudaMemcpyAsync(d_offs.p, doc_offsets, sizeof(int64_t) * (n_docs + 1), cudaMemcpyHostToDevice, g.stream));
       offs_dev = d_offs.as<int64_t>();
     } else {
       offs_dev = doc_offsets;
     }
+  }
+  if (trivial) {  // `.*`: every document whole; `^...`: one attempt at the document start
+    int64_t *outp = out_start_end;
+    if (location == MRX_OUT_HOST) {
+      if ((rc = d_out.get(sizeof(int64_t) * 2 * n_docs))) return rc;
+      outp = d_out.as<int64_t>();
+    }
+    ScanParams p{};
+    p.text = t->d; p.n = n; p.prog = re->d_search; p.mode = MRX_MODE_EVERY_POS;
+    p.doc_offsets = offs_dev; p.doc_stride = doc_stride; p.n_docs = (int64_t)n_docs;
+    launch_batch_trivial(p, pl.mode == MRX_MODE_WILDCARD_ANY ? 1 : 0, outp, g.stream);
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    if (location == MRX_OUT_HOST) {
+      CUDA_TRY(cudaMemcpyAsync(out_start_end, outp, sizeof(int64_t) * 2 * n_docs, cudaMemcpyDeviceToHost, g.stream));
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+    }
+    return MRX_OK;
   }
   if (re->d_rev_search && re->d_search && !getenv("MRX_NO_LINES")) {
     // reverse-automaton kernel: one thread per document, results written in place

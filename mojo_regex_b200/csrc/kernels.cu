@@ -1241,6 +1241,31 @@ __global__ void k_attempt_one(const ScanParams prm, int64_t pos, int64_t *out) {
   else { out[0] = out[1] = -1; out[2] = 0; }
 }
 
+// batch search for plans that need no scan: `.*` (every document matches whole, matcher.mojo:762-766) and
+// `^`-anchored patterns (one attempt at the document start, dfa.mojo:1888-1892).  One thread per document.
+__global__ void k_batch_trivial(const ScanParams prm, int wildcard, int64_t *out) {
+  const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= prm.n_docs) return;
+  const int64_t lo = prm.doc_offsets ? prm.doc_offsets[d] : d * prm.doc_stride;
+  const int64_t hi = prm.doc_offsets ? prm.doc_offsets[d + 1] : min(lo + prm.doc_stride, prm.n);
+  int64_t s_rel = -1, e_rel = -1;
+  if (wildcard) {
+    s_rel = 0;
+    e_rel = hi - lo;
+  } else {
+    Attempt at;
+    at.p = prm.prog;
+    at.tv.g = prm.text;
+    at.tv.s = nullptr;
+    at.tv.s_begin = at.tv.s_end = 0;
+    at.lo = lo;
+    at.n = hi;
+    Hit h;
+    if (try_candidate(prm, at, lo, h)) { s_rel = h.s - lo; e_rel = h.e - lo; }
+  }
+  st_span(out + 2 * d, s_rel, e_rel);
+}
+
 // first class run at or after `start` (dfa.mojo:2222-2239): OUT_FIRST found the first in-class byte
 __global__ void k_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
@@ -1765,6 +1790,10 @@ void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_
 }
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st) {
   k_carry_scan<<<1, 1024, 0, st>>>(n_tiles, trail, all, carry);
+}
+void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaStream_t st) {
+  if (p.n_docs <= 0) return;
+  k_batch_trivial<<<(unsigned)((p.n_docs + 255) / 256), 256, 0, st>>>(p, wildcard, out);
 }
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st) {
   k_attempt_one<<<1, 32, 0, st>>>(p, pos, out);

@@ -150,6 +150,7 @@ void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_
                           long long *trail, int *all, cudaStream_t st);
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st);
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st);
+void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaStream_t st);
 void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out, cudaStream_t st);
 void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
                            int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st);

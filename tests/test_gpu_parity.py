@@ -545,7 +545,7 @@ def test_fuzz_medium_texts_all_ops_against_oracle(pattern, alphabet):
     _compare_all_ops(pattern, text)
     rx = mr.compile_regex(pattern)
     info = rx.info()
-    if info.search_mode not in (-1, 0, 1):   # batch search: not for unsupported / `.*` / anchored plans
+    if info.search_mode != -1:   # batch search (also `^`-anchored plans: one attempt per document)
         orx = oracle.compile(pattern)
         arr = np.frombuffer(text, dtype=np.uint8)
         for stride in (48, 100):
@@ -553,3 +553,18 @@ def test_fuzz_medium_texts_all_ops_against_oracle(pattern, alphabet):
             for i in range(0, len(got), 17):
                 r = orx.search(arr[i * stride:(i + 1) * stride])
                 assert tuple(got[i]) == (r if r else (-1, -1)), (pattern, stride, i)
+
+
+def test_search_batch_wildcard_and_anchored():
+    text = np.frombuffer(b"abc xyz|ab||xabc ab".replace(b"|", bytes([10])), dtype=np.uint8)   # 19 bytes, | = newline
+    cuts = np.array([0, 8, 11, 12, 17, 19], dtype=np.int64)
+    for pat in (r".*", r"^ab", r"^abc", r"^", r"ab$"):
+        rx, orx = mr.compile_regex(pat), oracle.compile(pat)
+        got = rx.search_batch(text, doc_offsets=cuts)
+        for k in range(len(cuts) - 1):
+            r = orx.search(text[cuts[k]:cuts[k + 1]])
+            assert tuple(got[k]) == (r if r else (-1, -1)), (pat, k)
+        got = rx.search_batch(text, doc_stride=4)
+        for k in range(5):
+            r = orx.search(text[4 * k:4 * k + 4])
+            assert tuple(got[k]) == (r if r else (-1, -1)), (pat, k)
