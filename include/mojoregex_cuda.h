@@ -203,6 +203,10 @@ int mrx_split(const mrx_regex *re, const mrx_text *t, int64_t maxsplit, int loca
 int mrx_sub_host(const mrx_regex *re, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
                  size_t n, mrx_bytes *out);
 int mrx_split_host(const mrx_regex *re, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out);
+/* Batch search with the text, the offsets and the results in HOST memory: groups of documents are uploaded,
+ * searched and their results downloaded as a three-stream pipeline (documents are independent). */
+int mrx_search_batch_host(const mrx_regex *re, const uint8_t *host, size_t n, const int64_t *doc_offsets,
+                          size_t n_docs, int64_t doc_stride, int64_t *out_start_end);
 
 void mrx_spans_free(mrx_spans *s);
 void mrx_bytes_free(mrx_bytes *b);

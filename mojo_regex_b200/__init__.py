@@ -84,7 +84,7 @@ EXPORTS = [
     "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
     "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
-    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
+    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_search_batch_host", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
 ]
 
 
@@ -127,6 +127,7 @@ def _load() -> ctypes.CDLL:
     lib.mrx_split.argtypes = [vp, vp, i64, c.c_int, P(_Pieces)]
     lib.mrx_sub_host.argtypes = [vp, c.c_char_p, sz, i64, vp, sz, P(_Bytes)]
     lib.mrx_split_host.argtypes = [vp, vp, sz, i64, P(_Pieces)]
+    lib.mrx_search_batch_host.argtypes = [vp, vp, sz, vp, sz, i64, vp]
     lib.mrx_spans_free.argtypes = [P(_Spans)]
     lib.mrx_spans_free.restype = None
     lib.mrx_bytes_free.argtypes = [P(_Bytes)]
@@ -415,6 +416,24 @@ class CompiledRegex:
         assert out.dtype == np.int64 and out.size >= 2 * n_docs and out.flags["C_CONTIGUOUS"]
         _check(lib.mrx_search_batch(self._h, t._h, optr, n_docs, doc_stride, OUT_HOST, out.ctypes.data))
         return out
+
+    def search_batch_host(self, ptr: int, nbytes: int, out: np.ndarray, doc_offsets=None, doc_stride: int = 0,
+                          n_docs: Optional[int] = None) -> np.ndarray:
+        """Batch search over a host buffer (page-locked for full speed) into a caller-provided int64 array of
+        2 * n_docs elements: document groups are uploaded, searched and downloaded as a pipeline."""
+        _ensure_init()
+        if doc_offsets is not None:
+            offs = np.ascontiguousarray(doc_offsets, dtype=np.int64)
+            n_docs = offs.size - 1
+            optr = offs.ctypes.data
+        else:
+            assert doc_stride > 0
+            if n_docs is None:
+                n_docs = (nbytes + doc_stride - 1) // doc_stride
+            optr = None
+        assert out.dtype == np.int64 and out.size >= 2 * n_docs and out.flags["C_CONTIGUOUS"]
+        _check(lib.mrx_search_batch_host(self._h, ptr, nbytes, optr, n_docs, doc_stride, out.ctypes.data))
+        return out.reshape(-1)[: 2 * n_docs].reshape(n_docs, 2)
 
     def search_batch_device(self, text: "Text", out_ptr: int, n_docs: int, doc_stride: int = 0,
                             doc_offsets_ptr: int = 0, sync: bool = True) -> None:

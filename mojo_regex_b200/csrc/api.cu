@@ -1080,6 +1080,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
   if (n_docs == 0) return MRX_OK;
   const int64_t n = (int64_t)t->n;
+  if (!doc_offsets && (int64_t)(n_docs - 1) > n / doc_stride) return fail(MRX_E_INVALID, "more fixed-size documents than the text holds");
   const bool trivial = pl.mode == MRX_MODE_WILDCARD_ANY || pl.mode == MRX_MODE_ANCHORED;
   // offsets / results on the device
   DevTmp d_offs, d_best, d_out;
@@ -1463,6 +1464,78 @@ struct GrowHost {
 };
 
 }  // namespace
+
+extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host, size_t n, const int64_t *doc_offsets,
+                                     size_t n_docs, int64_t doc_stride, int64_t *out_start_end) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !out_start_end || (!host && n) || (!doc_offsets && doc_stride <= 0)) return fail(MRX_E_INVALID, "bad argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  if ((rc = ensure_uploaded(re))) return rc;
+  if (n_docs == 0) return MRX_OK;
+  if (doc_offsets) {
+    if (doc_offsets[0] < 0 || doc_offsets[n_docs] > (int64_t)n) return fail(MRX_E_INVALID, "doc_offsets outside the text");
+    for (size_t i = 0; i < n_docs; ++i)
+      if (doc_offsets[i] > doc_offsets[i + 1]) return fail(MRX_E_INVALID, "doc_offsets must be non-decreasing");
+  } else if ((int64_t)(n_docs - 1) > (int64_t)n / doc_stride) {
+    return fail(MRX_E_INVALID, "more fixed-size documents than the text holds");
+  }
+  // documents are independent: groups of documents of about kEditChunk bytes are uploaded, searched and
+  // their results downloaded as a three-stream pipeline
+  auto doc_begin = [&](size_t d) -> int64_t {
+    return doc_offsets ? doc_offsets[d] : std::min<int64_t>((int64_t)d * doc_stride, (int64_t)n);
+  };
+  std::vector<size_t> first{0};
+  while (first.back() < n_docs) {
+    size_t d = first.back();
+    const int64_t b0 = doc_begin(d);
+    size_t hi = n_docs;
+    if (doc_offsets) {  // first document that starts kEditChunk bytes further on
+      hi = std::upper_bound(doc_offsets + d, doc_offsets + n_docs, b0 + kEditChunk) - doc_offsets;
+      if (hi <= d) hi = d + 1;
+    } else {
+      hi = std::min(n_docs, d + (size_t)std::max<int64_t>(1, kEditChunk / doc_stride));
+    }
+    first.push_back(hi);
+  }
+  const size_t k = first.size() - 1;
+  DevTmp d_text, d_out, d_offs;
+  if ((rc = d_text.get(n + 512))) return rc;
+  if ((rc = d_out.get(sizeof(int64_t) * 2 * n_docs))) return rc;
+  if (doc_offsets && (rc = d_offs.get(sizeof(int64_t) * (n_docs + k + 1)))) return rc;
+  std::vector<int64_t> rebased;  // per group: offsets relative to the group's first byte (kept alive for the copies)
+  if (doc_offsets) rebased.resize(n_docs + k + 1);
+  uint8_t *dt = d_text.as<uint8_t>();
+  for (size_t i = 0; i < k; ++i) {
+    const int64_t b0 = doc_begin(first[i]), b1 = first[i + 1] < n_docs ? doc_begin(first[i + 1]) : (doc_offsets ? doc_offsets[n_docs] : (int64_t)n);
+    if (b1 > b0) CUDA_TRY(cudaMemcpyAsync(dt + b0, host + b0, (size_t)(b1 - b0), cudaMemcpyHostToDevice, g.s_in));
+    if (doc_offsets) {
+      const size_t base = first[i] + i;
+      for (size_t d = first[i]; d <= first[i + 1]; ++d) rebased[base + (d - first[i])] = doc_offsets[d] - b0;
+      CUDA_TRY(cudaMemcpyAsync(d_offs.as<int64_t>() + base, rebased.data() + base, sizeof(int64_t) * (first[i + 1] - first[i] + 1),
+                               cudaMemcpyHostToDevice, g.s_in));
+    }
+    CUDA_TRY(cudaEventRecord(pipe_event(i), g.s_in));
+  }
+  for (size_t i = 0; i < k; ++i) {
+    const int64_t b0 = doc_begin(first[i]), b1 = first[i + 1] < n_docs ? doc_begin(first[i + 1]) : (doc_offsets ? doc_offsets[n_docs] : (int64_t)n);
+    const size_t nd = first[i + 1] - first[i];
+    CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event(i), 0));
+    mrx_text view;
+    view.d = dt + b0; view.n = (size_t)(b1 - b0); view.owned = false; view.core_begin = 0; view.core_end = view.n;
+    rc = mrx_search_batch(re_c, &view, doc_offsets ? d_offs.as<int64_t>() + first[i] + i : nullptr, nd, doc_stride, MRX_OUT_DEVICE,
+                          d_out.as<int64_t>() + 2 * first[i]);
+    if (rc) { cudaStreamSynchronize(g.s_out); cudaStreamSynchronize(g.s_in); cudaStreamSynchronize(g.stream); return rc; }
+    CUDA_TRY(cudaEventRecord(pipe_event(k + i), g.stream));
+    CUDA_TRY(cudaStreamWaitEvent(g.s_out, pipe_event(k + i), 0));
+    CUDA_TRY(cudaMemcpyAsync(out_start_end + 2 * first[i], d_out.as<int64_t>() + 2 * first[i], sizeof(int64_t) * 2 * nd,
+                             cudaMemcpyDeviceToHost, g.s_out));
+  }
+  CUDA_TRY(cudaStreamSynchronize(g.s_out));
+  CUDA_TRY(cudaStreamSynchronize(g.s_in));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  return MRX_OK;
+}
 
 extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
                             size_t n, mrx_bytes *out) {

@@ -383,6 +383,10 @@ def run_op_host(rx, cfg, shard: Shard, host_pinned: torch.Tensor) -> int:
         nb = int(hp.data.nbytes) + int(hp.offsets.nbytes)
         hp.close()
         return nb
+    if cfg["op"] == "search_batch":
+        rx.search_batch_host(host_pinned.data_ptr(), host_pinned.numel(), _pinned_i64(2 * shard.n_docs), doc_stride=128,
+                             n_docs=shard.n_docs)
+        return int(2 * shard.n_docs * 8)
     t = mr.Text.from_pinned(host_pinned.data_ptr(), host_pinned.numel())
     t.set_window(shard.core_begin, shard.core_end, shard.global_offset)
     try:

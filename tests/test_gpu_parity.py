@@ -568,3 +568,32 @@ def test_search_batch_wildcard_and_anchored():
         for k in range(5):
             r = orx.search(text[4 * k:4 * k + 4])
             assert tuple(got[k]) == (r if r else (-1, -1)), (pat, k)
+
+
+def test_search_batch_host_pipelined():
+    """Three groups of documents through the upload / search / download pipeline: equal to the one-shot device
+    path for every document, and to the oracle on a sample; fixed-size and ragged documents."""
+    pat = corpora.CONFIGS["c3"]["pattern"]
+    n_lines = 2_300_000                      # 294 MB: more than two 128 MiB groups
+    text = corpora.make("c3", n_lines)
+    host = text.pin_memory()
+    rx, orx = mr.compile_regex(pat), oracle.compile(pat)
+    out = torch.empty(2 * n_lines, dtype=torch.int64).pin_memory()
+    got = rx.search_batch_host(host.data_ptr(), host.numel(), out.numpy(), doc_stride=128)
+    want = rx.search_batch(mr.Text(text.numpy()), doc_stride=128)
+    assert np.array_equal(got, want)
+    rng = np.random.default_rng(2)
+    arr = text.numpy()
+    for i in rng.integers(0, n_lines, 3000):
+        r = orx.search(arr[128 * i:128 * i + 128])
+        assert tuple(got[i]) == (r if r else (-1, -1))
+    # ragged documents (some empty), offsets on the host
+    cuts = np.unique(np.concatenate([[0, arr.size], rng.integers(0, arr.size, 1_500_000)])).astype(np.int64)
+    cuts = np.concatenate([cuts[:1000], cuts[999:1000], cuts[1000:]])      # one empty document
+    out2 = np.empty(2 * (cuts.size - 1), dtype=np.int64)
+    got2 = rx.search_batch_host(host.data_ptr(), host.numel(), out2, doc_offsets=cuts)
+    want2 = rx.search_batch(mr.Text(arr), doc_offsets=cuts)
+    assert np.array_equal(got2, want2)
+    for k in rng.integers(0, cuts.size - 1, 2000):
+        r = orx.search(arr[cuts[k]:cuts[k + 1]])
+        assert tuple(got2[k]) == (r if r else (-1, -1))
