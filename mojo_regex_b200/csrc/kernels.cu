@@ -276,6 +276,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
   uint16_t *q = sh.q_pos[warp];
   const int warp_rel0 = warp * kWarpBytes;
 
+  // block-uniform: required-byte findall whose attempts can run on the staged tile alone (see the attempt loop)
+  const bool lean_rb = prm.out_kind == OUT_SPANS && prm.mode == MRX_MODE_REQUIRED_BYTE && (sh.prog.flags & DF_DENSE_FWD) &&
+                       !(sh.prog.flags & (DF_SHORTCUT | DF_START_ANCHOR | DF_END_ANCHOR | DF_START_ACCEPTING));
   int list_n = 0;                    // warp-uniform: matches found by this warp so far
   unsigned long long out_idx = 0;    // pass 1: global index of this warp's next match
 
@@ -336,9 +339,32 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
         int64_t doc_lo = 0;
         int64_t cur_doc = 0;
         if (j < total) {
-          const int64_t pos = tile_start + q[j];
+          const int rel = q[j];
+          const int64_t pos = tile_start + rel;
           bool ok = true;
-          if (FILT != FILT_ALL && pos < prm.n && !cand[sh.text[q[j]]]) ok = false;  // SWAR filter is a superset
+          if (FILT != FILT_ALL && pos < prm.n && !cand[sh.text[rel]]) ok = false;  // SWAR filter is a superset
+          if (ok && lean_rb && pos < prm.n) {
+            // required-byte attempt entirely inside the staged window, 32-bit indices, shared memory only:
+            // back-scan over the matcher class (matcher.mojo:883-888), then the dense forward walk from
+            // there (dfa.mojo:1979-2026); a match must end past the needle (matcher.mojo:891)
+            const uint8_t *tx = sh.text, *lk = sh.prog.lookup, *fwd = sh.prog.trans;
+            int st = rel;
+            while (st > 0 && lk[tx[st - 1]]) --st;
+            if (st > 0 || tile_start == 0) {  // else the run may continue left of the tile: generic path
+              uint32_t sx = (uint32_t)sh.prog.fwd_start;
+              int x = st, last = -1;
+              while (x < stage_bytes) {
+                sx = *reinterpret_cast<const uint16_t *>(fwd + sx + 2u * tx[x]);
+                if (sx == 0) break;
+                ++x;
+                if (sx & 4u) last = x;
+              }
+              if (sx == 0 || tile_start + stage_bytes >= prm.n) {  // ended inside the window, or at the text's end
+                ok = false;                                          // (handled here)
+                if (last > rel) { hit = true; h.key = pos; h.s = tile_start + st; h.e = tile_start + last; }
+              }
+            }
+          }
           if (ok && prm.out_kind == OUT_BATCH) {
             cur_doc = doc_of(prm, pos);
             doc_lo = prm.doc_offsets ? prm.doc_offsets[cur_doc] : cur_doc * prm.doc_stride;
