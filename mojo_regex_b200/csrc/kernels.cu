@@ -1531,10 +1531,10 @@ __global__ void __launch_bounds__(kThreads) k_seg_lengths(const int64_t *spans, 
 
 // Output-stationary assembly, one CTA per kAsmTile (8 KiB) of output.
 //
-// The segments that touch the tile (tile_seg gives the window) are read once, in blocks of consecutive
-// segments per thread; those with output bytes are compacted into records {output offset, search position,
-// gap length} in shared memory, and a bitmap over the tile's kAsmTile output positions gets a bit where each of
-// them starts.  Then every lane produces 4 consecutive output bytes per step (a warp writes 128 contiguous
+// The segments that touch the tile (tile_seg gives the window) are read once, round-robin (coalesced), into
+// records {output offset, search position, gap length} in shared memory; a bitmap over the tile's kAsmTile
+// output positions gets a bit where each segment WITH output bytes starts, prefix popcounts of the bitmap
+// words are taken, and nzk[rank] maps the r-th set bit back to its segment.  Then every lane produces 4 consecutive output bytes per step (a warp writes 128 contiguous
 // bytes, STG.32): the record of an output byte is rank(bitmap, position) -- one popcount for the first byte
 // of the word, the next bit for each following byte -- so there is no search and no per-lane walk, and the
 // lanes of a warp read consecutive text bytes.  Gap bytes come from the text, replacement bytes from the
