@@ -210,6 +210,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
                                 timeout=datetime.timedelta(seconds=180))
     dev = torch.device("cuda", local_rank)
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl (library communicator)" if mrd.init_native_exchange(dev) else "nccl (torch.distributed)"
     cfg = corpora.CONFIGS[args.config]
     size = args.size or default_size(args.config)
     rx = mr.compile_regex(cfg["pattern"])
@@ -310,7 +313,7 @@ def run_gpu(args):
                        "bytes_per_gpu": int(n_bytes), "units_per_step": int(total_units),
                        "l2": "input (%.0f MiB per GPU) is larger than the 126 MB L2; no flush needed" % (n_bytes / 2**20)
                        if n_bytes > 256 << 20 else "input re-read every step; smaller than 2x L2",
-                       "sharding": "byte ranges + halo, count all-gather over NCCL" if world > 1 else "single GPU"},
+                       "sharding": ("byte ranges + halo, count all-gather: " + exchange) if world > 1 else "single GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None,
                          "traffic": args.traffic if args.traffic is not None else load_traffic(args.config, n_bytes, res.kernel),

@@ -208,6 +208,19 @@ int mrx_split_host(const mrx_regex *re, const uint8_t *host, size_t n, int64_t m
 int mrx_search_batch_host(const mrx_regex *re, const uint8_t *host, size_t n, const int64_t *doc_offsets,
                           size_t n_docs, int64_t doc_stride, int64_t *out_start_end);
 
+/* ---- multi-GPU count exchange (one process per GPU) ---------------------------------------------------
+ * The only collective on the path: an all-gather of a small int64 record per rank (match count, output
+ * bytes), from which each rank derives the global offset of its slice of the result.  NCCL is looked up at
+ * run time (libnccl.so.2), not linked.  Rank 0 creates the id, the caller distributes its 128 bytes (any
+ * transport), every rank calls mrx_comm_init.  mrx_comm_allgather is asynchronous on the library's exchange
+ * stream: `*table_dev` (world x width int64, device memory owned by the library, overwritten by the next
+ * exchange) is valid after mrx_comm_join(stream) for work ordered on `stream`. */
+int mrx_comm_unique_id(uint8_t out[128]);
+int mrx_comm_init(const uint8_t id[128], int rank, int world);
+int mrx_comm_allgather(const int64_t *values, int width /* 1..4 */, void **table_dev);
+int mrx_comm_join(void *stream /* cudaStream_t; NULL = mrx_stream() */);
+int mrx_comm_shutdown(void);
+
 void mrx_spans_free(mrx_spans *s);
 void mrx_bytes_free(mrx_bytes *b);
 void mrx_pieces_free(mrx_pieces *p);

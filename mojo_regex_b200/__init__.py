@@ -84,7 +84,8 @@ EXPORTS = [
     "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
     "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
-    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_search_batch_host", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
+    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_search_batch_host", "mrx_comm_unique_id", "mrx_comm_init", "mrx_comm_allgather", "mrx_comm_join",
+    "mrx_comm_shutdown", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
 ]
 
 
@@ -128,6 +129,10 @@ def _load() -> ctypes.CDLL:
     lib.mrx_sub_host.argtypes = [vp, c.c_char_p, sz, i64, vp, sz, P(_Bytes)]
     lib.mrx_split_host.argtypes = [vp, vp, sz, i64, P(_Pieces)]
     lib.mrx_search_batch_host.argtypes = [vp, vp, sz, vp, sz, i64, vp]
+    lib.mrx_comm_unique_id.argtypes = [vp]
+    lib.mrx_comm_init.argtypes = [vp, c.c_int, c.c_int]
+    lib.mrx_comm_allgather.argtypes = [P(i64), c.c_int, P(vp)]
+    lib.mrx_comm_join.argtypes = [vp]
     lib.mrx_spans_free.argtypes = [P(_Spans)]
     lib.mrx_spans_free.restype = None
     lib.mrx_bytes_free.argtypes = [P(_Bytes)]
@@ -188,6 +193,32 @@ def last_kernel_ms() -> float:
 
 def synchronize() -> None:
     _check(lib.mrx_synchronize())
+
+
+def comm_unique_id() -> bytes:
+    """Rank 0: a fresh NCCL id (128 bytes) for comm_init on every rank."""
+    buf = ctypes.create_string_buffer(128)
+    _check(lib.mrx_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+    return buf.raw
+
+
+def comm_init(uid: bytes, rank: int, world: int) -> None:
+    """Join the library's own NCCL communicator (count exchange inside the library, no Python per step)."""
+    _ensure_init()
+    buf = ctypes.create_string_buffer(uid, 128)
+    _check(lib.mrx_comm_init(ctypes.cast(buf, ctypes.c_void_p), rank, world))
+
+
+def comm_allgather(values) -> int:
+    """Queue one all-gather of a record of 1..4 int64; returns the device address of the (world, width) table."""
+    arr = (ctypes.c_int64 * len(values))(*[int(v) for v in values])
+    out = ctypes.c_void_p()
+    _check(lib.mrx_comm_allgather(arr, len(values), ctypes.byref(out)))
+    return int(out.value or 0)
+
+
+def comm_join(stream_handle_: int = 0) -> None:
+    _check(lib.mrx_comm_join(stream_handle_ or None))
 
 
 def _as_bytes(x) -> bytes:

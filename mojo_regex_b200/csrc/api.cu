@@ -1,5 +1,7 @@
 // C ABI of libmojoregex_cuda.so (see include/mojoregex_cuda.h).  Host orchestration only:
 // every byte of text is touched by the kernels in kernels.cu, never by host code.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -1464,6 +1466,126 @@ struct GrowHost {
 };
 
 }  // namespace
+
+// ---- count exchange over NCCL, inside the library ---------------------------------------------------
+// The only collective on the path: every rank contributes a small int64 record (match count,
+// output bytes) and gets the table of all ranks, from which it derives the global offset of its slice.
+// libnccl is not linked: it is looked up in the process (torch has it loaded) or on the default search
+// path, so single-GPU users never need it.  The record goes through a ring of pinned slots and the
+// all-gather runs on its own stream: a call costs a few microseconds of host time and never waits.
+namespace {
+
+struct NcclUid { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+  void *h = nullptr;
+  int (*GetUniqueId)(NcclUid *) = nullptr;
+  int (*CommInitRank)(NcclComm *, int, NcclUid, int) = nullptr;
+  int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+  int (*CommDestroy)(NcclComm) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+};
+constexpr int kXRing = 64, kXWidth = 4, kNcclInt64 = 4;
+struct Exchange {
+  NcclApi api;
+  NcclComm comm = nullptr;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev = nullptr;
+  int64_t *h_ring = nullptr;  // pinned, kXRing x kXWidth
+  int64_t *d_ring = nullptr;  // device mirror of the slots
+  int64_t *d_table = nullptr; // world x width of the last exchange
+  uint64_t count = 0;
+} gx;
+
+int nccl_load() {
+  if (gx.api.h) return MRX_OK;
+  void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW);
+  if (!h) return fail(MRX_E_UNSUPPORTED, std::string("libnccl.so.2 not found: ") + dlerror());
+  NcclApi a;
+  a.h = h;
+  a.GetUniqueId = (int (*)(NcclUid *))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(NcclComm *, int, NcclUid, int))dlsym(h, "ncclCommInitRank");
+  a.AllGather = (int (*)(const void *, void *, size_t, int, NcclComm, cudaStream_t))dlsym(h, "ncclAllGather");
+  a.CommDestroy = (int (*)(NcclComm))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllGather || !a.CommDestroy) return fail(MRX_E_UNSUPPORTED, "libnccl.so.2 lacks an entry point");
+  gx.api = a;
+  return MRX_OK;
+}
+int nccl_fail(const char *what, int code) {
+  return fail(MRX_E_CUDA, std::string(what) + ": " + (gx.api.GetErrorString ? gx.api.GetErrorString(code) : "nccl error"));
+}
+
+}  // namespace
+
+extern "C" int mrx_comm_unique_id(uint8_t out[128]) {
+  int rc = nccl_load();
+  if (rc) return rc;
+  NcclUid id;
+  const int e = gx.api.GetUniqueId(&id);
+  if (e) return nccl_fail("ncclGetUniqueId", e);
+  std::memcpy(out, id.internal, 128);
+  return MRX_OK;
+}
+
+extern "C" int mrx_comm_init(const uint8_t id_bytes[128], int rank, int world) {
+  int rc = require_device();
+  if (rc) return rc;
+  if ((rc = nccl_load())) return rc;
+  if (gx.comm) return MRX_OK;
+  if (world < 1 || rank < 0 || rank >= world) return fail(MRX_E_INVALID, "bad rank / world");
+  NcclUid id;
+  std::memcpy(id.internal, id_bytes, 128);
+  const int e = gx.api.CommInitRank(&gx.comm, world, id, rank);
+  if (e) { gx.comm = nullptr; return nccl_fail("ncclCommInitRank", e); }
+  gx.rank = rank;
+  gx.world = world;
+  CUDA_TRY(cudaStreamCreateWithFlags(&gx.stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&gx.ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaHostAlloc((void **)&gx.h_ring, sizeof(int64_t) * kXRing * kXWidth, cudaHostAllocDefault));
+  CUDA_TRY(cudaMalloc((void **)&gx.d_ring, sizeof(int64_t) * kXRing * kXWidth));
+  CUDA_TRY(cudaMalloc((void **)&gx.d_table, sizeof(int64_t) * (size_t)world * kXWidth));
+  CUDA_TRY(cudaMemset(gx.d_table, 0, sizeof(int64_t) * (size_t)world * kXWidth));
+  return MRX_OK;
+}
+
+extern "C" int mrx_comm_allgather(const int64_t *values, int width, void **table_dev) {
+  if (!gx.comm) return fail(MRX_E_NO_DEVICE, "mrx_comm_init has not been called");
+  if (!values || width < 1 || width > kXWidth) return fail(MRX_E_INVALID, "bad record");
+  if (gx.count && gx.count % kXRing == 0) CUDA_TRY(cudaStreamSynchronize(gx.stream));  // the ring wraps: slots are free again
+  const size_t slot = (size_t)(gx.count++ % kXRing) * kXWidth;
+  for (int i = 0; i < width; ++i) gx.h_ring[slot + i] = values[i];
+  CUDA_TRY(cudaMemcpyAsync(gx.d_ring + slot, gx.h_ring + slot, sizeof(int64_t) * width, cudaMemcpyHostToDevice, gx.stream));
+  const int e = gx.api.AllGather(gx.d_ring + slot, gx.d_table, (size_t)width, kNcclInt64, gx.comm, gx.stream);
+  if (e) return nccl_fail("ncclAllGather", e);
+  if (table_dev) *table_dev = gx.d_table;
+  return MRX_OK;
+}
+
+// Make `stream` (a cudaStream_t; NULL = the library stream) wait for every exchange issued so far.
+extern "C" int mrx_comm_join(void *stream) {
+  if (!gx.comm) return MRX_OK;
+  CUDA_TRY(cudaEventRecord(gx.ev, gx.stream));
+  CUDA_TRY(cudaStreamWaitEvent(stream ? (cudaStream_t)stream : g.stream, gx.ev, 0));
+  return MRX_OK;
+}
+
+extern "C" int mrx_comm_shutdown(void) {
+  if (!gx.comm) return MRX_OK;
+  cudaStreamSynchronize(gx.stream);
+  gx.api.CommDestroy(gx.comm);
+  cudaFreeHost(gx.h_ring);
+  cudaFree(gx.d_ring);
+  cudaFree(gx.d_table);
+  cudaEventDestroy(gx.ev);
+  cudaStreamDestroy(gx.stream);
+  NcclApi keep = gx.api;
+  gx = Exchange();
+  gx.api = keep;
+  return MRX_OK;
+}
 
 extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host, size_t n, const int64_t *doc_offsets,
                                      size_t n_docs, int64_t doc_stride, int64_t *out_start_end) {

@@ -190,6 +190,100 @@ class DeviceGather:
             stream.wait_stream(self.stream)
 
 
+class NativeGather:
+    """The same exchange through the library's own NCCL communicator (mrx_comm_*): a few microseconds of
+    host time per step in C, no Python thread, no torch dispatcher.  Used when `init_native_exchange`
+    succeeded on every rank; `DeviceGather` (torch.distributed) is the fallback."""
+
+    def __init__(self, width: int, device):
+        import torch.distributed as dist
+
+        self.width = width
+        self.device = device
+        self.world = dist.get_world_size()
+        self.rank = dist.get_rank()
+        self.table_ptr = 0
+
+    def gather(self, values: List[int]) -> None:
+        import mojo_regex_b200 as mr
+
+        assert len(values) == self.width
+        self.table_ptr = mr.comm_allgather(values)
+
+    def table(self) -> torch.Tensor:
+        """(world, width) view of the library's table, ordered after the exchanges on the current stream."""
+        import mojo_regex_b200 as mr
+
+        mr.comm_join(torch.cuda.current_stream().cuda_stream)
+
+        class _V:
+            pass
+
+        v = _V()
+        v.__cuda_array_interface__ = {"shape": (self.world, self.width), "typestr": "<i8", "data": (self.table_ptr, False),
+                                      "version": 3, "strides": None}
+        return torch.as_tensor(v, device=self.device)
+
+    def base_offset(self, column: int = 0) -> torch.Tensor:
+        col = self.table()[:, column]
+        return torch.cumsum(col, 0)[self.rank] - col[self.rank]
+
+    def drain(self) -> None:
+        pass
+
+    def join(self, stream) -> None:
+        import mojo_regex_b200 as mr
+
+        mr.comm_join(stream.cuda_stream)
+
+
+_NATIVE = False
+
+
+def init_native_exchange(device) -> bool:
+    """Set up the library's NCCL communicator next to torch.distributed's (rank 0 creates the id, it is
+    broadcast through torch.distributed).  All ranks agree on the outcome; False = keep DeviceGather."""
+    global _NATIVE
+    import torch.distributed as dist
+
+    import mojo_regex_b200 as mr
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return False
+    # probe first (not collective): ncclCommInitRank below blocks until EVERY rank has called it, so nobody
+    # may enter it unless every rank can
+    try:
+        probe_id = mr.comm_unique_id()
+        probe = 1
+    except Exception:
+        probe_id, probe = b"", 0
+    pf = torch.tensor([probe], dtype=torch.int32, device=device)
+    dist.all_reduce(pf, op=dist.ReduceOp.MIN)
+    if not int(pf.item()):
+        return False
+    ok = 1
+    try:
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            uid.copy_(torch.tensor(list(probe_id), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        if ok:
+            try:
+                if int(uid.sum().item()) == 0:
+                    ok = 0
+                else:
+                    mr.comm_init(bytes(uid.cpu().tolist()), rank, world)
+            except Exception:
+                ok = 0
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    _NATIVE = bool(flag.item())
+    return _NATIVE
+
+
 def global_offsets(counts: List[int]) -> List[int]:
     """Exclusive prefix sum: where each rank's slice of the global result starts."""
     out, acc = [], 0
@@ -280,7 +374,7 @@ def join_exchanges(stream) -> None:
 def _gather_for(width: int, device) -> DeviceGather:
     key = (width, str(device))
     if key not in _GATHERS:
-        _GATHERS[key] = DeviceGather(width, device)
+        _GATHERS[key] = NativeGather(width, device) if _NATIVE else DeviceGather(width, device)
     return _GATHERS[key]
 
 
