@@ -151,6 +151,16 @@ void release_owner(void *o) {
   delete w;
 }
 
+// MRX_DEBUG_SYNC=1: synchronise after the named launch and report which one failed (debugging aid)
+int debug_sync(const char *what) {
+  static const bool on = getenv("MRX_DEBUG_SYNC") != nullptr;
+  if (!on) return MRX_OK;
+  cudaError_t e = cudaStreamSynchronize(g.stream);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(MRX_E_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return MRX_OK;
+}
+
 int require_device() {
   if (!g.inited) return fail(MRX_E_NO_DEVICE, "mrx_init() has not been called (no CUDA device selected); there is no CPU fallback");
   return MRX_OK;
@@ -1239,6 +1249,11 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   if ((rc = ensure_uploaded(re))) return bail(rc);
   DevSpans ms;
   if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  // the assembly works in buffer coordinates: a shard's global offset (mrx_text_set_window) applies to the
+  // spans findall reports, never to the match list sub / split are built from
+  mrx_text local = *t;
+  local.global_offset = 0;
+  t = &local;
   rc = match_list(re, t, p.search, re->d_search, ms);
   g.prof_outer = false;
   if (rc) return bail(rc);
@@ -1313,6 +1328,9 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   if ((rc = ensure_uploaded(re))) return rc;
   DevSpans ms;
   if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  mrx_text local = *t;  // buffer coordinates for the assembly (see mrx_sub)
+  local.global_offset = 0;
+  t = &local;
   rc = match_list(re, t, re->prog.findall, re->d_findall, ms);
   g.prof_outer = false;
   if (rc) return rc;
@@ -1334,9 +1352,11 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   CUDA_TRY(cudaMemsetAsync(d_desc.p, 0, sizeof(unsigned long long) * seg_tiles, g.stream));
   CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
   CUDA_TRY(cudaMemsetAsync(d_bad.p, 0, 16, g.stream));
+  if ((rc = debug_sync("split: match list"))) return bail(rc);
   launch_seg_lengths(ms.spans, M, n, SEG_SPLIT, 0, d_desc.as<unsigned long long>(), g.ticket, (int64_t *)d_offs,
                      d_bad.as<int>(), d_tseg.as<int64_t>(), g.stream);
   ++g.launches;
+  if ((rc = debug_sync("split: k_seg_lengths"))) return bail(rc);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 8, (int64_t *)d_offs + (M + 1), 8, cudaMemcpyDeviceToHost, g.stream));
   CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 9, d_bad.p, 4, cudaMemcpyDeviceToHost, g.stream));
@@ -1354,6 +1374,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
     ap.tile_seg = d_tseg.as<int64_t>(); ap.n_tiles = (total + kAsmTile - 1) / kAsmTile; ap.mode = SEG_SPLIT;
     ap.repl_len = 0; ap.tpl_src = nullptr; ap.total = total; ap.out = (uint8_t *)d_bytes;
     launch_assemble(ap, g.stream);
+    if ((rc = debug_sync("split: k_assemble"))) return bail(rc);
     g.launches += total > 0 ? 1 : 0;
     if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
   }

@@ -597,3 +597,24 @@ def test_search_batch_host_pipelined():
     for k in rng.integers(0, cuts.size - 1, 2000):
         r = orx.search(arr[cuts[k]:cuts[k + 1]])
         assert tuple(got2[k]) == (r if r else (-1, -1))
+
+
+def test_sub_split_ignore_a_shards_global_offset():
+    """A shard's global offset rebases the spans findall reports; sub and split assemble in buffer
+    coordinates and must not see it (a multi-GPU C4/C5 rank > 0 used to feed rebased spans to the assembly)."""
+    t4 = corpora.make("c4", 3 << 20).numpy()
+    t5 = corpora.make("c5", 3 << 20).numpy()
+    c4 = corpora.CONFIGS["c4"]
+    for text, kind in ((t4, "sub"), (t5, "split")):
+        t = mr.Text(text)
+        t.set_window(0, text.size, 7 * text.size)          # whole buffer is the core, far-away global offset
+        if kind == "sub":
+            want = oracle.compile(c4["pattern"]).sub(c4["repl"].encode(), text)
+            assert mr.compile_regex(c4["pattern"]).sub(c4["repl"], t) == want
+        else:
+            wd, wo = oracle.compile(r"\s*,\s*").split_raw(text)
+            gd, go = mr.compile_regex(r"\s*,\s*").split_raw(t)
+            assert gd == wd and np.array_equal(go, wo)
+        # findall on the same text does report global coordinates
+        rx = mr.compile_regex(r"\d+" if kind == "sub" else r",")
+        assert int(rx.match_all(t).spans[0, 0]) >= 7 * text.size
