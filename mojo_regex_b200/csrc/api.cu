@@ -675,10 +675,13 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   mrx_text tview;
   tview.d = dt; tview.n = (size_t)n; tview.owned = false; tview.core_begin = (size_t)core_begin; tview.core_end = (size_t)core_end;
   tview.global_offset = global_offset;
-  const int64_t n_chunks = (n + kPipeChunk - 1) / kPipeChunk;
+  // chunk = 1/16 of the text, between 4 and 32 MiB: enough stages for the three streams to overlap on
+  // small texts, few enough launches and host synchronisations on large ones
+  const int64_t chunk = std::min<int64_t>(kPipeChunk, std::max<int64_t>(4ll << 20, ((n / 16) + 0xfffff) & ~0xfffffll));
+  const int64_t n_chunks = (n + chunk - 1) / chunk;
   CUDA_TRY(cudaMemsetAsync(dt + n, 0, 512, g.s_in));
   for (int64_t c = 0; c < n_chunks; ++c) {
-    const int64_t b = c * kPipeChunk, len = std::min(kPipeChunk, n - b);
+    const int64_t b = c * chunk, len = std::min(chunk, n - b);
     CUDA_TRY(cudaMemcpyAsync(dt + b, host + b, (size_t)len, cudaMemcpyHostToDevice, g.s_in));
     CUDA_TRY(cudaEventRecord(pipe_event((size_t)c), g.s_in));
   }
@@ -704,7 +707,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   int64_t t0 = 0, copied = 0, total = 0;
   bool overflow = false;
   for (int64_t c = 0; c < n_chunks && !overflow; ++c) {
-    const int64_t vis = std::min(n, (c + 1) * kPipeChunk);
+    const int64_t vis = std::min(n, (c + 1) * chunk);
     const int64_t t1 = (c == n_chunks - 1) ? tiles
                                            : std::min(tiles, std::max<int64_t>(t0, (vis - kLookAhead - origin) / kTile));
     if (t1 <= t0) continue;
@@ -1017,7 +1020,7 @@ int mrx_findall_host_shard(const mrx_regex *re_c, const uint8_t *host, size_t n,
   mrx_regex *re = const_cast<mrx_regex *>(re_c);
   std::memset(out, 0, sizeof *out);
   if ((rc = ensure_uploaded(re))) return rc;
-  if (plan_pipelines(re->prog.findall) && (int64_t)n >= 2 * kPipeChunk)
+  if (plan_pipelines(re->prog.findall) && (int64_t)n >= (16ll << 20))
     return findall_host_pipelined(re, host, (int64_t)n, (int64_t)core_begin, (int64_t)core_end, global_offset, out);
   mrx_text *t = nullptr;
   if ((rc = mrx_text_upload(host, n, &t))) return rc;
