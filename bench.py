@@ -290,12 +290,13 @@ def run_gpu(args):
 
     # ---- reduce over ranks ----------------------------------------------------------------------
     t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(n_bytes), float(units), float(launches)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_bytes), float(units), float(launches), float(shard.buffer.numel()), float(d2h)],
+                       dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max, k_ms = [float(x) for x in t.tolist()]
-    total_bytes, total_units, total_launches = [float(x) for x in tot.tolist()]
+    total_bytes, total_units, total_launches, total_h2d, total_d2h = [float(x) for x in tot.tolist()]
 
     # ---- CPU baseline on rank 0 (bounded sample, single thread: the reference is single-threaded)
     cpu = None
@@ -321,7 +322,7 @@ def run_gpu(args):
                          "kernel_ms": k_ms, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": total_bytes * e2e_steps / (e2e_ms_max / 1e3) / 1e9, "unit": "GB/s",
-                    "h2d_bytes_per_step": int(shard.buffer.numel()), "d2h_bytes_per_step": int(d2h)},
+                    "h2d_bytes_per_step": int(total_h2d), "d2h_bytes_per_step": int(total_d2h)},  # summed over ranks
             "gpu_launches": int(total_launches),
             "clocks": clk,
         }
