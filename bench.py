@@ -9,10 +9,14 @@ With N>1 (torchrun, one rank per GPU) every rank scans its own 1 GiB shard (+ ha
 N GiB corpus and the ranks all-gather their match counts over NCCL (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = input GB/s with the corpus already resident in HBM
-(device time, CUDA events on the library stream, max over ranks); `e2e` = the same metric
-through the public API with host buffers (pinned), H2D and D2H copies inside the timed region.
-`--impl reference` times the CPU restatement of the reference's own path (oracle/) on the
-host cores instead.
+(device time, CUDA events on the library stream, max over ranks); `roofline` = algorithmic bytes of a
+step over the dominant kernel's event time (for sub / split: the whole kernel sequence), against the
+measured HBM peak, with the DRAM traffic of the committed ncu capture; `e2e` = the same metric through
+the host-buffer calls of the C ABI (mrx_findall_host, mrx_search_batch_host, mrx_sub_host, mrx_split_host)
+from pinned host memory, every H2D and D2H byte inside the timed region; `cpu_baseline` = the oracle port
+of the reference's path on one host thread.  `--impl reference` times that port on all host threads
+instead (the reference itself is Mojo and cannot be built here).  With N > 1 the count all-gather runs on
+the library's own NCCL communicator (mrx_comm_*), off the scan stream.
 """
 import argparse
 import json

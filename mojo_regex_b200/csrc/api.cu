@@ -367,7 +367,6 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
       dp.dense = job.dense; dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
       dp.n_tiles = (int)tiles; dp.spans = (int64_t *)spans; dp.cap = cap; dp.rebase = job.rebase;
       dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = g.scalars;
-      dp.debug_no_lookback = getenv("MRX_DEBUG_NOLOOKBACK") != nullptr;
       launch_dense(dp, (int)tiles, g.stream);
     } else {
       launch_scan(p, (int)tiles, g.stream);

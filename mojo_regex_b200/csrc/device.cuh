@@ -18,7 +18,6 @@ constexpr int kTile = kThreads * kChunk;       // 36864 bytes of text per CTA
 constexpr int kHalo = 256;                     // look-ahead bytes staged after the tile
 constexpr int kMaxTrans = 8192;                // n_states * n_classes budget in shared memory
 constexpr int kMaxLiteral = 256;
-constexpr int kSlots = 8;                      // buffered matches per thread before the recompute path
 
 enum DevFlags : int32_t {
   DF_END_ANCHOR = 1 << 0,
@@ -150,32 +149,6 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
 __device__ __forceinline__ void lookback_publish(unsigned long long *desc, int tile, unsigned long long aggregate) {
   st_volatile_u64(desc + tile, (tile == 0 ? kFlagPre : kFlagAgg) | aggregate);
 }
-// all 32 lanes of one warp; aggregate(tile) must already be published
-__device__ __forceinline__ unsigned long long lookback_resolve(unsigned long long *desc, int tile,
-                                                               unsigned long long aggregate) {
-  const int lane = threadIdx.x & 31;
-  if (tile == 0) return 0;
-  unsigned long long excl = 0;
-  int idx = tile - 1;
-  while (true) {
-    const int my = idx - lane;
-    unsigned long long d = kFlagPre;
-    if (my >= 0) {
-      do { d = ld_volatile_u64(desc + my); } while ((d >> 62) == 0);
-    }
-    const unsigned pre_mask = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-    const int first_pre = pre_mask ? (__ffs(pre_mask) - 1) : 32;
-    unsigned long long v = (lane <= first_pre) ? (d & kValMask) : 0;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    excl += v;
-    if (pre_mask) break;
-    idx -= 32;
-  }
-  if (lane == 0) st_volatile_u64(desc + tile, kFlagPre | (excl + aggregate));
-  return excl;
-}
-
 // Block-wide resolve (all kThreads threads): looks at 256 predecessors per round, so a whole wave of
 // concurrently running tiles is crossed in two or three rounds.  Needs every predecessor's AGGREGATE to
 // be published (true one tile behind); never waits for a predecessor's prefix.  `ws`: 2 * kThreads/32 + 2

@@ -1292,14 +1292,6 @@ __global__ void k_batch_trivial(const ScanParams prm, int wildcard, int64_t *out
   st_span(out + 2 * d, s_rel, e_rel);
 }
 
-// first class run at or after `start` (dfa.mojo:2222-2239): OUT_FIRST found the first in-class byte
-__global__ void k_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  int64_t q = pos;
-  while (q < n && prog->lookup[text[q]]) ++q;
-  out[0] = pos; out[1] = q; out[2] = q > pos ? 1 : 0;
-}
-
 __global__ void k_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
                                  int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out) {
   const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1621,7 +1613,7 @@ __device__ __forceinline__ void assemble_tile_slow(const AsmParams &p, int64_t t
 __global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   AsmShared &sh = *reinterpret_cast<AsmShared *>(smem_raw);
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x;
   const int64_t tile = blockIdx.x;
   const int64_t lo_seg = __ldg(p.tile_seg + tile);
   const int64_t hi_seg = (tile + 1 < p.n_tiles) ? __ldg(p.tile_seg + tile + 1) : p.M;
@@ -1823,9 +1815,6 @@ void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaS
 }
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st) {
   k_attempt_one<<<1, 32, 0, st>>>(p, pos, out);
-}
-void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out, cudaStream_t st) {
-  k_run_extent<<<1, 32, 0, st>>>(text, n, prog, pos, out);
 }
 void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
                            int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st) {

@@ -9,8 +9,6 @@
 
 namespace mrx {
 
-constexpr int64_t kBackSlack = 1 << 20;  // buffered match starts may precede the tile by this much
-
 enum OutKind : int32_t {
   OUT_SPANS = 0,  // ordered (start,end) list through look-back compaction
   OUT_FIRST = 1,  // global minimum key (search)
@@ -91,7 +89,6 @@ struct DenseParams {
   unsigned int *ticket;
   unsigned long long *total;
   unsigned long long *best;  // OUT_FIRST: min over (start << 8 | len)
-  int32_t debug_no_lookback;  // measurement only (MRX_DEBUG_NOLOOKBACK=1): results are NOT ordered
 };
 
 // Per-document search (k_lines): one thread per document.
@@ -151,7 +148,6 @@ void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st);
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st);
 void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaStream_t st);
-void launch_run_extent(const uint8_t *text, int64_t n, const DevProg *prog, int64_t pos, int64_t *out, cudaStream_t st);
 void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,
                            int64_t doc_stride, int64_t n, int empty_at_end, int64_t *out, cudaStream_t st);
 void launch_fill_u64(unsigned long long *p, int64_t n, unsigned long long v, cudaStream_t st);
