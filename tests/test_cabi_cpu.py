@@ -177,3 +177,51 @@ def test_matching_without_a_device_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(mr.RegexCudaError):
         mr.findall(r"\d+", b"abc123")
+
+
+def _random_patterns(n: int, seed: int):
+    """Small grammar around the shapes compile_dfa_pattern knows (dfa.mojo:2385-2496): classes, literals,
+    quantifiers, groups, alternations, anchors -- plus noise that should be rejected the same way by both
+    front ends."""
+    import random
+
+    rng = random.Random(seed)
+    atoms = [r"\d", r"\w", r"\s", "a", "b", "ab", "abc", "x", "-", r"\.", ",", "@", ".", "[a-z]", "[0-9]", "[A-Z]", "[a-c]",
+             "[^0-9]", "[a-zA-Z0-9._%+-]", "[;,]", "[89]", "hello", "foo"]
+    quants = ["", "", "", "+", "*", "?", "{2}", "{3}", "{2,}", "{1,3}", "{0,2}"]
+
+    def piece():
+        a = rng.choice(atoms)
+        q = rng.choice(quants)
+        if len(a) > 1 and a[0] not in "\\[" and q and rng.random() < 0.7:
+            a = "(" + a + ")"
+        return a + q
+
+    out = []
+    for _ in range(n):
+        k = rng.choice([1, 1, 2, 2, 3, 4, 5])
+        kind = rng.random()
+        if kind < 0.15:
+            p = "|".join(rng.choice(["a", "b", "ab", "abc", "hello", "world", "foo", "na", "nb", "cat", "dog"])
+                         for _ in range(rng.randint(2, 4)))
+            if rng.random() < 0.6:
+                p = "(" + p + ")"
+            if rng.random() < 0.3:
+                p += rng.choice(["+", "*", "?"])
+        elif kind < 0.3:
+            p = "".join("(" + piece() + ")" for _ in range(k))
+        else:
+            p = "".join(piece() for _ in range(k))
+        if rng.random() < 0.1:
+            p = "^" + p
+        if rng.random() < 0.1:
+            p = p + "$"
+        out.append(p)
+    return sorted(set(out))
+
+
+@pytest.mark.parametrize("pattern", _random_patterns(420, 20261018), ids=lambda p: p or "<empty>")
+def test_random_patterns_front_ends_agree(pattern):
+    """Differential test of the two independent restatements of the reference's front end (C++ in the
+    product, Python in the oracle): same verdict (tables / unsupported / parse error) on random patterns."""
+    test_product_front_end_matches_oracle_tables(pattern)

@@ -618,3 +618,38 @@ def test_sub_split_ignore_a_shards_global_offset():
         # findall on the same text does report global coordinates
         rx = mr.compile_regex(r"\d+" if kind == "sub" else r",")
         assert int(rx.match_all(t).spans[0, 0]) >= 7 * text.size
+
+
+def _supported_random_patterns():
+    from test_cabi_cpu import _random_patterns
+
+    out = []
+    for p in _random_patterns(420, 20261018):
+        try:
+            oracle.frontend.compile_regex(p.encode())
+            out.append(p)
+        except (oracle.Unsupported, oracle.RegexError):
+            pass
+    return out
+
+
+@pytest.mark.parametrize("pattern", _supported_random_patterns(), ids=lambda p: p or "<empty>")
+def test_random_patterns_all_ops_against_oracle(pattern):
+    """Every DFA-routed pattern of the random grammar (all nine plan modes): all ops on a short text and on
+    one that crosses a scan tile, alphabet = the pattern's own characters plus a few that match nothing."""
+    import zlib
+
+    rng = random.Random(zlib.crc32(pattern.encode()))
+    chars = sorted(set(c for c in pattern if c.isalnum() or c in "-.,@;_%+ ")) or ["a"]
+    if "\\d" in pattern or "[0-9]" in pattern or "[89]" in pattern:
+        chars += list("0189")
+    if "\\w" in pattern or "[a-z]" in pattern or "[a-c]" in pattern or "[a-zA-Z0-9._%+-]" in pattern:
+        chars += list("abcz")
+    if "[A-Z]" in pattern:
+        chars += list("AZ")
+    if "\\s" in pattern:
+        chars += [" ", "\t"]
+    alphabet = "".join(chars) + " #\n"
+    for n in (700, TILE + 3000):
+        text = bytes(ord(rng.choice(alphabet)) for _ in range(n))
+        _compare_all_ops(pattern, text)
