@@ -1256,6 +1256,19 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   mrx_text local = *t;
   local.global_offset = 0;
   t = &local;
+  if (p.flag(BF_WILDCARD_ANY)) {
+    // `.*`: the replace loop (matcher.mojo:1824-1847) calls match_next(text, pos) until it fails: (0, n), then
+    // the empty match (n, n) at the end of the text (matcher.mojo:762-766) -- two replacements, not the one
+    // span match_all reports
+    void *sp = nullptr;
+    if ((rc = dev_alloc(32, &sp))) return bail(rc);
+    const int64_t h[4] = {0, n, n, n};
+    CUDA_TRY(cudaMemcpyAsync(sp, h, 32, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    ms.spans = (int64_t *)sp;
+    ms.n = 2;
+    rc = MRX_OK;
+  } else
   rc = match_list(re, t, p.search, re->d_search, ms);
   g.prof_outer = false;
   if (rc) return bail(rc);

@@ -88,6 +88,7 @@ def _compare_all_ops(pattern, text, repl=None):
 
 
 FUZZ = [
+    (r".*", "ab\n"),
     (r"\d+", "0123456789ab xyz"),
     (r"[a-c]*", "abcx "),
     (r"\d{2,4}", "0123456789ab "),
@@ -639,6 +640,9 @@ def test_random_patterns_all_ops_against_oracle(pattern):
     one that crosses a scan tile, alphabet = the pattern's own characters plus a few that match nothing."""
     import zlib
 
+    info = mr.compile_regex(pattern).info()
+    if info.findall_mode == -1 or info.search_mode == -1:
+        pytest.skip("documented refusal: the reference's result depends on the host SIMD width (DESIGN.md section 2)")
     rng = random.Random(zlib.crc32(pattern.encode()))
     chars = sorted(set(c for c in pattern if c.isalnum() or c in "-.,@;_%+ ")) or ["a"]
     if "\\d" in pattern or "[0-9]" in pattern or "[89]" in pattern:
