@@ -208,6 +208,74 @@ split(f"{TS}:66-70", ",", "a,b,c", ["a,b,c"], maxsplit=-1)
 split(f"{TS}:73-77", "[;,]", "a;b,c;d", ["a", "b", "c", "d"])
 split(f"{RD}:47-49 (docs only, not an executed test)", r"\s*,\s*", "a, b ,c,  d", ["a", "b", "c", "d"])
 
+# ---- tests/test_dfa.mojo: the DFAEngine driven directly ------------------------------
+# compile_pattern(lit, start_anchor, end_anchor) is written here as the equivalent regex
+# source ("^" / "$" around the literal), which dfa.mojo:3060-3200 compiles the same way.
+TF = "tests/test_dfa.mojo"
+mfirst(f"{TF}:14-22", "hello", "hello world", [0, 5])
+mfirst(f"{TF}:25-27", "hello", "say hello there", None)
+mfirst(f"{TF}:30-31", "hello", "goodbye world", None)
+mfirst(f"{TF}:56-62", "[a-z]+", "hello123", [0, 5])
+mfirst(f"{TF}:64-66", "[a-z]+", "123hello", None)
+findall(f"{TF}:72-83", "a", "banana", spans=[[1, 2], [3, 4], [5, 6]])
+mfirst(f"{TF}:116-121", "hello", "hello world", [0, 5])
+mfirst(f"{TF}:127-132", "a", "a", [0, 1])
+mfirst(f"{TF}:135-137", "a", "banana", None)
+mfirst(f"{TF}:143-147", "Hello", "Hello World", [0, 5])
+mfirst(f"{TF}:150-151", "Hello", "hello world", None)
+mfirst(f"{TF}:153-154", "Hello", "HELLO WORLD", None)
+mfirst(f"{TF}:176-181", "abc", "abc", [0, 3])
+mfirst(f"{TF}:184-185", "abc", "ab", None)
+mfirst(f"{TF}:188-189", "abc", "axbc", None)
+mfirst(f"{TF}:195-203", "^hello", "hello world", [0, 5])
+mfirst(f"{TF}:206-207", "^hello", "say hello", None)
+mfirst(f"{TF}:217-222", "world$", "hello world", None)
+mfirst(f"{TF}:225-226", "world$", "world peace", None)
+mfirst(f"{TF}:232-240", "^hello$", "hello", [0, 5])
+mfirst(f"{TF}:243-244", "^hello$", "hello world", None)
+mfirst(f"{TF}:246-247", "^hello$", "say hello", None)
+mfirst(f"{TF}:253-260", "^", "hello", [0, 0])
+mfirst(f"{TF}:267-272", "$", "hello", None)
+findall(f"{TF}:279-284", "^a", "aaa", spans=[[0, 1]])
+findall(f"{TF}:288-293", "a$", "aaa", spans=[[2, 3]])
+findall(f"{TF}:297-300", "^a$", "a", count=1)
+findall(f"{TF}:302-303", "^a$", "aaa", spans=[])
+mfirst(f"{TF}:309-314", "^hello", "hello world", [0, 5])
+mfirst(f"{TF}:316-321", "world$", "hello world", None)
+mfirst(f"{TF}:323-328", "^hello$", "hello", [0, 5])
+mfirst(f"{TF}:333-339", r"[+]*\d+[-]*\d+[-]*\d+[-]*\d+", "+1-541-236-5432", [0, 15])
+mfirst(f"{TF}:366-372", "[a-z]+[0-9]+", "hello123", [0, 8])
+mfirst(f"{TF}:375-381", "[A-Z][a-z]+[0-9]+", "Hello123", [0, 8])
+mfirst(f"{TF}:384-385", "[A-Z][a-z]+[0-9]+", "hello123", None)
+mfirst(f"{TF}:388-389", "[A-Z][a-z]+[0-9]+", "Hello", None)
+mfirst(f"{TF}:414-416", "[a-z]*[0-9]+", "abc123", [0, 6])
+mfirst(f"{TF}:419-420", "[a-z]*[0-9]+", "abc", None)
+
+# ---- tests/test_predefined_classes.mojo: per-byte membership loops --------------------
+for _i in range(10):
+    mfirst(f"{TP}:12-17", r"\d", str(_i), [0, 1])
+    mfirst(f"{TP}:119-124", r"\w", str(_i), [0, 1])
+for _c in "abcdefghijklmnopqrstuvwxyz":
+    mfirst(f"{TP}:98-104", r"\w", _c, [0, 1])
+    mfirst(f"{TP}:107-113", r"\w", _c.upper(), [0, 1])
+mfirst(f"{TP}:127-130", r"\w", "_", [0, 1])
+for _c in "@#$%^&*()-+=[]{}|\\:;\"'<>,.?/~`":
+    mfirst(f"{TP}:135-140", r"\w", _c, None)
+for _c in " \t\n":
+    mfirst(f"{TP}:145-152", r"\w", _c, None)
+mfirst(f"{TP}:23-27", r"\d", "0", [0, 1])
+mfirst(f"{TP}:26-27", r"\d", "9", [0, 1])
+mfirst(f"{TP}:30-31", r"\d", "a", None)
+mfirst(f"{TP}:33-34", r"\d", " ", None)
+mfirst(f"{TP}:36-37", r"\d", "@", None)
+mfirst(f"{TP}:158-161", r"\w+", "hello123", [0, 8])
+mfirst(f"{TP}:164-167", r"\w*", "hello_world", [0, 11])
+mfirst(f"{TP}:170-173", r"\w?", "a", [0, 1])
+mfirst(f"{TP}:178-179", r"\w", "", None)
+mfirst(f"{TP}:181-184", r"\w*", "", [0, 0])
+mfirst(f"{TP}:186-189", r"\w?", "", [0, 0])
+mfirst(f"{TP}:191-192", r"\w+", "", None)
+
 # ---- assertions the reference answers through its NFA engines (out of scope) --------
 NFA_ROUTED = [
     dict(src=f"{TM}:729", pattern="^[a-z]+$"),
