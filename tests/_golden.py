@@ -33,7 +33,9 @@ def check_vector(impl, v):
             assert spans[-1] == v["last"], (v, spans)
     elif op in ("search", "match_first"):
         r = rx.search(text) if op == "search" else rx.match_first(text)
-        if "starts" in v:
+        if "found" in v:  # CompiledRegex.test / is_match: only whether a match exists is asserted
+            assert (r is not None) == v["found"], (v, r)
+        elif "starts" in v:
             assert r is not None and r[0] == v["starts"], (v, r)
         elif v["span"] is None:
             assert r is None, (v, r)

@@ -11,8 +11,8 @@ listed under "nfa_routed" so the tests can check that both the oracle and the pr
 refuse them the same way.
 
 Fields: op in {findall, search, match_first, sub, split}; `src` = reference file:line.
-Expectations: spans=[[s,e],...] (exact), or texts / starts / count where the reference
-test only asserts those; span=[s,e] or null for search/match_first; out for sub;
+Expectations: spans=[[s,e],...] (exact), or texts / starts / count / found where the
+reference test only asserts those; span=[s,e] or null for search/match_first; out for sub;
 pieces for split.
 """
 import json
@@ -38,6 +38,16 @@ def mfirst(src, p, t, span):
 
 def search(src, p, t, span=None, **kw):
     V.append(dict(op="search", src=src, pattern=p, text=t, span=span, **kw))
+
+
+def test(src, p, t, found):
+    """CompiledRegex.test (matcher.mojo:1091-1101): match_next(text, 0) is not None."""
+    V.append(dict(op="search", src=src, pattern=p, text=t, found=found))
+
+
+def is_match(src, p, t, found):
+    """CompiledRegex.is_match (matcher.mojo:1104): a match exists AT position 0."""
+    V.append(dict(op="match_first", src=src, pattern=p, text=t, found=found))
 
 
 def sub(src, p, r, t, out, count=0):
@@ -276,6 +286,149 @@ mfirst(f"{TP}:181-184", r"\w*", "", [0, 0])
 mfirst(f"{TP}:186-189", r"\w?", "", [0, 0])
 mfirst(f"{TP}:191-192", r"\w+", "", None)
 
+# ---- tests/test_matcher.mojo: remaining DFA-routed assertions ---------------------------
+mfirst(f"{TM}:18-30", "hello", "hello world", [0, 5])
+findall(f"{TM}:45-52", "a", "banana", starts=[1, 3, 5])
+test(f"{TM}:155-156", "hello", "hello world", True)
+for _p in ("hello", "world", "test"):
+    mfirst(f"{TM}:170-179", _p, _p + " text", [0, len(_p)])
+test(f"{TM}:202", "^hello", "hello world", True)
+test(f"{TM}:203", "^hello", "say hello", False)
+test(f"{TM}:206", "world$", "hello world", True)
+test(f"{TM}:207", "world$", "world peace", False)
+test(f"{TM}:210", "^hello$", "hello", True)
+test(f"{TM}:211", "^hello$", "hello world", False)
+test(f"{TM}:212", "^hello$", "say hello", False)
+test(f"{TM}:219", "Hello", "Hello World", True)
+test(f"{TM}:220", "Hello", "hello world", False)
+test(f"{TM}:221", "Hello", "HELLO WORLD", False)
+mfirst(f"{TM}:274-279", "(a)*", "aa", [0, 2])
+mfirst(f"{TM}:338-340", "nb$", "nb ", None)
+mfirst(f"{TM}:402-406", "^$", "", [0, 0])
+mfirst(f"{TM}:408-412", "$", "", [0, 0])
+mfirst(f"{TM}:414-418", "^", "", [0, 0])
+mfirst(f"{TM}:480-484", "[a-z]+", "hello", [0, 5])
+mfirst(f"{TM}:951-956", "[^0-9]", "hello", [0, 1])
+mfirst(f"{TM}:959-960", "[^0-9]", "5", None)
+mfirst(f"{TM}:963-966", "[^a-z]", "A", [0, 1])
+mfirst(f"{TM}:1014-1017", "[^abc]", " ", [0, 1])
+mfirst(f"{TM}:1020-1023", "[^abc]", "\n", [0, 1])
+mfirst(f"{TM}:1026-1029", "[^abc]", "\t", [0, 1])
+for _t in ("8001234567", "8005551234", "8009998877", "9001234567", "9005551234", "9009998877"):
+    test(f"{TM}:1068-1075", "[89]00[0-9]+", _t, True)
+for _t in ("7001234567", "8101234567", "5551234567"):
+    test(f"{TM}:1078-1080", "[89]00[0-9]+", _t, False)
+P8 = "8(?:00|33|44|55|66|77|88)[2-9][0-9]+"
+for _t in ("80021234567", "80091234567", "80051234567", "83321234567", "84421234567", "85521234567",
+           "86621234567", "87721234567", "88821234567"):
+    test(f"{TM}:1099-1109", P8, _t, True)
+for _t in ("80001234567", "80011234567", "81121234567", "90021234567", "70021234567"):
+    test(f"{TM}:1112-1120", P8, _t, False)
+for _t in ("8001234567", "9001234567", "Call 8001234567", "8001234567 please", " 8001234567 "):
+    test(f"{TM}:1153-1159", "[89]00[0-9]{6}", _t, True)
+test(f"{TM}:1191", "[89]00[0-9]+", "8001234567", True)
+test(f"{TM}:1192", "[89]00[0-9]+", "555-123-4567", False)
+test(f"{TM}:1195", "[0-9]+-[0-9]+-[0-9]+", "555-123-4567", True)
+test(f"{TM}:1201", "[0-9]+", "5551234567", True)
+test(f"{TM}:1202", "[0-9]+", "8001234567", True)
+test(f"{TM}:1203-1205", "[0-9]+", "555-123-4567", True)
+is_match(f"{TM}:1428", "[a-z]+", "abcdef", True)
+is_match(f"{TM}:1429", "[a-z]+", "z", True)
+is_match(f"{TM}:1430", "[a-z]+", "123", False)
+is_match(f"{TM}:1431", "[a-z]+", "ABC", False)
+is_match(f"{TM}:1435", "[0-9]+", "123abc", True)
+is_match(f"{TM}:1436", "[0-9]+", "0", True)
+is_match(f"{TM}:1437", "[0-9]+", "abc", False)
+is_match(f"{TM}:1441", r"\d+", "5hello", True)
+is_match(f"{TM}:1442", r"\d+", "hello", False)
+is_match(f"{TM}:1445", r"\w+", "hello", True)
+is_match(f"{TM}:1446", r"\w+", "_underscore", True)
+is_match(f"{TM}:1447", r"\w+", " space", False)
+is_match(f"{TM}:1454", "[a-z]*", "abc", True)
+is_match(f"{TM}:1455", "[a-z]*", "123", True)
+is_match(f"{TM}:1456", "[a-z]*", "", True)
+is_match(f"{TM}:1462", "^abc", "abcdef", True)
+is_match(f"{TM}:1463", "^abc", "xabc", False)
+is_match(f"{TM}:1471", "hello", "hello world", True)
+is_match(f"{TM}:1472", "hello", "world", False)
+is_match(f"{TM}:1478", "[a-z]+", "", False)
+is_match(f"{TM}:1481", "[a-z]*", "", True)
+for _p, _cls in (("[a-z]+", "abcdefghijklmnopqrstuvwxyz"), ("[0-9]+", "0123456789"), (r"\d+", "0123456789"),
+                 (r"\w+", "abcdefghijklmnopqrstuvwxyz0123456789_"),
+                 ("[a-zA-Z0-9]+", "abcdefghijklmnopqrstuvwxyz0123456789")):
+    for _t in ("hello", "12345", "abc123", "@#$%", ""):
+        # the reference asserts is_match == bool(match_first); both are "first byte in class" here
+        is_match(f"{TM}:1486-1508", _p, _t, bool(_t) and _t[0].lower() in _cls)
+
+# ---- tests/test_predefined_classes.mojo: remaining DFA-routed assertions ------------------
+for _t in ("0", "9"):
+    is_match(f"{TP}:288-292", r"\d", _t, True)
+for _t in ("a", "Z", "_"):
+    is_match(f"{TP}:294-301", r"\w", _t, True)
+mfirst(f"{TP}:307-311", r"\d+", "123456789012345678901234567890", [0, 30])
+mfirst(f"{TP}:314-320", r"\w+", "abcdefghijklmnopqrstuvwxyzABCDEFGHIJKLMNOPQRSTUVWXYZ0123456789_", [0, 63])
+is_match(f"{TP}:430-431", r"\d", "5", True)
+is_match(f"{TP}:433-434", r"\w", "a", True)
+mfirst(f"{TP}:437-440", r"\d*", "abc", [0, 0])
+mfirst(f"{TP}:442-445", r"\w*", "@#$", [0, 0])
+mfirst(f"{TP}:451-454", r"\w+", "variable123", [0, 11])
+mfirst(f"{TP}:457-460", r"\d+", "123abc", [0, 3])
+mfirst(f"{TP}:463-466", r"\w+", "hello_123@world", [0, 9])
+mfirst(f"{TP}:475-476", r"\d", "/", None)
+mfirst(f"{TP}:478-479", r"\d", ":", None)
+mfirst(f"{TP}:482-486", r"\d", "0", [0, 1])
+mfirst(f"{TP}:485-486", r"\d", "9", [0, 1])
+for _t in ("`", "{", "@", "["):
+    mfirst(f"{TP}:492-503", r"\w", _t, None)
+for _t in ("a", "z"):
+    mfirst(f"{TP}:506-510", r"\w", _t, [0, 1])
+
+# ---- tests/test_comptime_regex.mojo: the comptime API drives the same DFAEngine ---------
+search(f"{TC}:7-10", "hello", "say hello world", [4, 9])
+search(f"{TC}:11", "hello", "no match here", None)
+test(f"{TC}:15", "^abc$", "abc", True)
+test(f"{TC}:16", "^abc$", "xabc", False)
+test(f"{TC}:17", "^abc$", "abcx", False)
+search(f"{TC}:26-29", "a+b", "xxaaabby", [4, 6])  # engine quirk the reference's test pins
+search(f"{TC}:30", "a+b", "xxyy", None)
+search(f"{TC}:42", "(x|y)", "abc", None)
+search(f"{TC}:54", "[0-9]+", "no digits", None)
+search(f"{TC}:58-61", "[^abc]+", "abxyc", [2, 4])
+test(f"{TC}:63", r"\w+", "...abc...", True)
+search(f"{TC}:65-68", "[0-9]{3}", "id 4567", [3, 6])
+search(f"{TC}:70-73", "[a-z]+[0-9]+", "QQab12ZZ", [2, 6])
+is_match(f"{TC}:90", "hello", "hello world", True)
+is_match(f"{TC}:91", "hello", "say hello", False)
+is_match(f"{TC}:96", r"\d+", "42 is the answer", True)
+is_match(f"{TC}:97", r"\d+", "answer is 42", False)
+findall(f"{TC}:101-104", "ab", "ab abab ab", count=4, starts=[0, 3, 5, 8])
+search(f"{TC}:117-120", "hello", "prefix hello suffix", starts=7)
+
+# ---- tests/test_simd.mojo: the search helpers, driven through the regex that calls them --
+# (simd_search is the literal path of dfa.mojo:1927-1951; CharacterClassSIMD.find_* is the
+#  single-class scan of dfa.mojo:2277-2372.  The helper assertions are restated as the regex
+#  call whose result they determine.)
+search(f"{TD}:48 (find_first_match)", "[aeiou]", "hello world", starts=1)
+search(f"{TD}:49 (find_first_match)", "[aeiou]", "programming", starts=2)
+search(f"{TD}:52 (find_first_match)", "[aeiou]", "xyz", None)
+findall(f"{TD}:62-68 (find_all_matches)", "[l]", "hello world", starts=[2, 3, 9])
+findall(f"{TD}:74 (count_matches)", "[a]", "banana", count=3)
+findall(f"{TD}:75 (count_matches)", "[a]", "hello", count=0)
+findall(f"{TD}:76 (count_matches)", "[a]", "aardvark", count=3)
+search(f"{TD}:160 (simd_search)", "hello", "hello world", starts=0)
+search(f"{TD}:161 (simd_search)", "hello", "say hello there", starts=4)
+search(f"{TD}:162 (simd_search)", "hello", "goodbye", None)
+findall(f"{TD}:172-192 (simd_search loop)", "ll", "hello world, all well", starts=[2, 14, 19])
+search(f"{TD}:213 (simd_search)", "a", "banana", starts=1)
+search(f"{TD}:214 (simd_search)", "a", "hello", None)
+findall(f"{TD}:217-232 (simd_search loop)", "a", "banana", starts=[1, 3, 5])
+search(f"{TD}:283 (find_first_match)", "[abc]", "", None)
+findall(f"{TD}:284-285 (find_all_matches)", "[abc]", "", count=0)
+search(f"{TD}:288 (find_first_match)", "[abc]", "a", starts=0)
+search(f"{TD}:289 (find_first_match)", "[abc]", "x", None)
+search(f"{TD}:303-308 (find_first_nibble_match)", "[89]", "Call 8001234567", starts=5)
+search(f"{TD}:311-316 (find_first_nibble_match)", r"\(", "hello (world)", starts=6)
+
 # ---- assertions the reference answers through its NFA engines (out of scope) --------
 NFA_ROUTED = [
     dict(src=f"{TM}:729", pattern="^[a-z]+$"),
@@ -283,6 +436,28 @@ NFA_ROUTED = [
     dict(src=f"{TS}:14-19", pattern=r"\s+"),
     dict(src=f"{TP}:360", pattern=r"(\w\d)+"),
     dict(src=f"{TM}:1696-1703", pattern="(hello)"),
+    dict(src=f"{TM}:262", pattern="^a|b$"),
+    dict(src=f"{TM}:283", pattern="^(a)+"),
+    dict(src=f"{TM}:307", pattern=r"\s"),
+    dict(src=f"{TM}:325", pattern="^na|nb$"),
+    dict(src=f"{TM}:344", pattern="^x(a)?ac$"),
+    dict(src=f"{TM}:369", pattern="https?://"),
+    dict(src=f"{TM}:384", pattern="^aaaa.*a$"),
+    dict(src=f"{TM}:393", pattern="^x(a|b)?bc$"),
+    dict(src=f"{TM}:445", pattern=r"^\s$"),
+    dict(src=f"{TM}:228", pattern="hello.world"),
+    dict(src=f"{TM}:1689-1693", pattern=r"(\d+)"),
+    dict(src=f"{TM}:1783-1787", pattern=r"(?:hello) (\w+)"),
+    dict(src=f"{TP}:222", pattern=r"\d|\w"),
+    dict(src=f"{TP}:253", pattern=r"^\d+$"),
+    dict(src=f"{TP}:261", pattern=r"^\w+$"),
+    dict(src=f"{TP}:326", pattern=r"\d*abc"),
+    dict(src=f"{TP}:332", pattern=r"\w*@"),
+    dict(src=f"{TC}:79", pattern="(a|b)x"),
+    dict(src=f"{TC}:85", pattern="h[ae]llo"),
+    dict(src=f"{TM}:1808", pattern="3[02]|40"),
+    dict(src=f"{TM}:1811", pattern="3[02]|40|[68]9"),
+    dict(src=f"{TM}:1816", pattern="24|[346]|7[2-57-9]|9[2-9]"),
 ]
 
 if __name__ == "__main__":
