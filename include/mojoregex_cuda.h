@@ -88,6 +88,8 @@ typedef struct {
   int32_t fixed_sub_total_width, fixed_sub_num_groups, fixed_sub_concat;
   int32_t findall_dense, search_dense; /* 1 = served by the dense literal-set automaton (k_dense)       */
   int32_t search_rev_states;           /* > 0: batch search runs the reverse-automaton kernel (k_lines)  */
+  int32_t search_skip_byte;            /* >= 0: a byte every match contains, read off the automaton; the    */
+                                       /* batch kernel does not walk documents without it (-1 = none)       */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */

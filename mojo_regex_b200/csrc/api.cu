@@ -935,6 +935,7 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
   o->fixed_sub_concat = p.fixed_concat;
   o->findall_dense = p.findall.dense.valid; o->search_dense = p.search.dense.valid;
   o->search_rev_states = p.search.rev.valid ? p.search.rev.n_rev : 0;
+  o->search_skip_byte = p.search.rev.valid ? p.search.rev.req_byte : -1;
   return MRX_OK;
 }
 
@@ -1141,7 +1142,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     lp.text = t->d; lp.n = n; lp.tables = re->d_rev_search;
     lp.rev_bytes = (int32_t)(pl.rev.rev.size() * 2); lp.fwd_bytes = (int32_t)(pl.rev.fwd.size() * 2);
     lp.fwd_start = pl.rev.fwd_start; lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
-    lp.n_docs = (int64_t)n_docs; lp.out = outp;
+    lp.n_docs = (int64_t)n_docs; lp.out = outp; lp.req_byte = pl.rev.req_byte;
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
     launch_lines(lp, g.stream);
     if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }

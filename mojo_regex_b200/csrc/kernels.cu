@@ -898,6 +898,133 @@ __global__ void __launch_bounds__(kThreads) k_lines(const LinesParams prm) {
   }
 }
 
+// Batch search with a required byte (RevTable::req_byte, e.g. '@' for the e-mail pattern): a document that
+// does not hold that byte cannot match, so only the others are walked.  One CTA per SM, kReqWarps
+// independent warps.  A warp loads 32 consecutive documents with coalesced 16-byte loads and tests every
+// 16-byte piece for the byte while it is still in registers (SWAR zero-byte test on piece ^ byte x 4); the
+// OR over a document's pieces says whether it is a candidate.  Documents that are not get (-1, -1) at once and
+// never touch shared memory; the pieces of candidates go to the next free rows of a 64-row ring (same bank-
+// skewed row pitch as k_lines) together with the document index.  As soon as 32 rows are pending, every
+// lane walks one of them exactly as k_lines does (reverse automaton for the leftmost start, forward table for
+// the longest accept), so the walk always runs with full warps however sparse the candidates are.  The ring
+// holds < 32 pending rows before a batch and receives <= 32 new ones: 64 rows never overflow.
+constexpr int kReqWarps = 16;  // 512 threads x 128 registers: two batches of pieces live in registers
+constexpr int kReqThreads = 32 * kReqWarps;
+constexpr int kReqRing = 64;
+constexpr int kReqMaxVecs = 8;  // documents of up to 128 bytes: a lane holds one 16-byte piece per vector slot
+
+__device__ __forceinline__ void lines_walk_row(const uint8_t *rev, const uint8_t *fwd, uint32_t fwd_start,
+                                               const uint8_t *mine, int nv, int stride, int64_t *out) {
+  uint32_t r = 0, best_pk = 0;
+  int best_word = -1;  // index of the 4-byte word that holds the leftmost flagged byte
+#pragma unroll 2
+  for (int k = nv - 1; k >= 0; --k) {
+    const uint4 w4 = *reinterpret_cast<const uint4 *>(mine + 16 * k);
+    const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+    for (int wi = 3; wi >= 0; --wi) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        const uint32_t b = __byte_perm(ws[wi], 0, 0x4440 + j);
+        uint32_t addr;
+        asm("mad.lo.u32 %0, %1, 2, %2;" : "=r"(addr) : "r"(b), "r"(r));
+        r = *reinterpret_cast<const uint16_t *>(rev + addr);
+        pk = __byte_perm(pk, r, j == 0 ? 0x3214 : j == 1 ? 0x3240 : j == 2 ? 0x3410 : 0x4210);
+      }
+      if (pk & 0x04040404u) { best_pk = pk; best_word = 4 * k + wi; }
+    }
+  }
+  const int best = best_word >= 0 ? 4 * best_word + ((__ffs(best_pk & 0x04040404u) - 1) >> 3) : -1;
+  lines_emit(fwd, fwd_start, [&](int q) { return (uint32_t)mine[q]; }, stride, best, out);
+}
+
+template <int NV>  // NV = 16-byte pieces per document when known at compile time (8: 128-byte lines), 0 = runtime
+__global__ void __launch_bounds__(kReqThreads, 1) k_lines_req(const LinesParams prm) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  LinesShared &sh = *reinterpret_cast<LinesShared *>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  {
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(prm.tables);
+    uint4 *d4 = reinterpret_cast<uint4 *>(sh.tables);
+    for (int i = tid; i < (prm.rev_bytes + prm.fwd_bytes) / 16; i += kReqThreads) d4[i] = s4[i];
+  }
+  __syncthreads();
+  const uint8_t *rev = sh.tables, *fwd = sh.tables + prm.rev_bytes;
+  const int pitch = prm.line_pitch, stride = (int)prm.doc_stride, nv = NV ? NV : (stride >> 4);
+  const int nv_shift = (nv & (nv - 1)) == 0 ? 31 - __clz(nv) : -1;  // power of two: shifts instead of divisions
+  const size_t per_warp = (size_t)kReqRing * pitch + (size_t)kReqRing * sizeof(int64_t);
+  uint8_t *rows = sh.tables + prm.rev_bytes + prm.fwd_bytes + (size_t)warp * per_warp;
+  int64_t *ids = reinterpret_cast<int64_t *>(rows + (size_t)kReqRing * pitch);
+  const uint32_t rq = (uint32_t)prm.req_byte * 0x01010101u;
+  const uint32_t below = (1u << lane) - 1u;
+  uint32_t head = 0, tail = 0;  // ring counters of this warp (warp-uniform); row = counter & 63
+  const int64_t n_groups = (prm.n_docs + 31) / 32;
+  const int64_t gstep = (int64_t)gridDim.x * kReqWarps;
+  // the pieces of batch g: piece c = 32 j + lane of the batch's contiguous byte range, j < nv
+  auto load_batch = [&](int64_t g, uint4 (&dst)[kReqMaxVecs]) {
+    const int64_t d0 = g * 32;
+    const int chunks = (int)min((int64_t)32, prm.n_docs - d0) * nv;
+    const uint4 *src = reinterpret_cast<const uint4 *>(prm.text + d0 * stride);
+#pragma unroll
+    for (int j = 0; j < kReqMaxVecs; ++j) {
+      const int c = 32 * j + lane;
+      if (j < nv && c < chunks) dst[j] = __ldg(src + c);
+    }
+  };
+  int64_t grp = (int64_t)blockIdx.x * kReqWarps + warp;
+  uint4 v[kReqMaxVecs];
+  if (grp < n_groups) load_batch(grp, v);
+  for (; grp < n_groups; grp += gstep) {
+    // the next batch's loads are in flight while this one is filtered, parked and (now and then) walked
+    uint4 nx[kReqMaxVecs];
+    if (grp + gstep < n_groups) load_batch(grp + gstep, nx);
+    const int64_t d0 = grp * 32;
+    const int in_grp = (int)min((int64_t)32, prm.n_docs - d0);
+    const int chunks = in_grp * nv;
+    uint32_t fl = 0;  // bit d: one of my pieces of document d0 + d holds the byte
+#pragma unroll
+    for (int j = 0; j < kReqMaxVecs; ++j) {
+      const int c = 32 * j + lane;
+      if (j < nv && c < chunks) {
+        const uint32_t x0 = v[j].x ^ rq, x1 = v[j].y ^ rq, x2 = v[j].z ^ rq, x3 = v[j].w ^ rq;
+        const uint32_t z = ((x0 - 0x01010101u) & ~x0) | ((x1 - 0x01010101u) & ~x1) | ((x2 - 0x01010101u) & ~x2) |
+                           ((x3 - 0x01010101u) & ~x3);
+        const int d = nv_shift >= 0 ? (c >> nv_shift) : (c / nv);
+        if (z & 0x80808080u) fl |= 1u << d;
+      }
+    }
+    const uint32_t m = __reduce_or_sync(0xffffffffu, fl);  // candidate documents of this batch
+    if (lane < in_grp && !((m >> lane) & 1u)) st_span(prm.out + 2 * (d0 + lane), -1, -1);
+#pragma unroll
+    for (int j = 0; j < kReqMaxVecs; ++j) {
+      const int c = 32 * j + lane;
+      if (j < nv && c < chunks) {
+        const int d = nv_shift >= 0 ? (c >> nv_shift) : (c / nv);
+        if ((m >> d) & 1u) {
+          const uint32_t slot = (tail + (uint32_t)__popc(m & ((1u << d) - 1u))) & (kReqRing - 1);
+          *reinterpret_cast<uint4 *>(rows + (size_t)slot * pitch + 16 * (c - d * nv)) = v[j];
+        }
+      }
+    }
+    if ((m >> lane) & 1u) ids[(tail + (uint32_t)__popc(m & below)) & (kReqRing - 1)] = d0 + lane;
+    tail += (uint32_t)__popc(m);
+    __syncwarp();
+    if (tail - head >= 32u) {
+      const uint32_t slot = (head + (uint32_t)lane) & (kReqRing - 1);
+      lines_walk_row(rev, fwd, (uint32_t)prm.fwd_start, rows + (size_t)slot * pitch, nv, stride, prm.out + 2 * ids[slot]);
+      head += 32u;
+      __syncwarp();  // the walked rows may be overwritten by the next batch
+    }
+#pragma unroll
+    for (int j = 0; j < kReqMaxVecs; ++j) v[j] = nx[j];
+  }
+  if ((uint32_t)lane < tail - head) {
+    const uint32_t slot = (head + (uint32_t)lane) & (kReqRing - 1);
+    lines_walk_row(rev, fwd, (uint32_t)prm.fwd_start, rows + (size_t)slot * pitch, nv, stride, prm.out + 2 * ids[slot]);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // class runs
 constexpr int kRunTok = 12;  // matches a thread buffers before it has to walk its chunk a second time
@@ -1749,15 +1876,36 @@ void launch_lines(LinesParams p, cudaStream_t st) {
                       tables + kThreads * pitch <= 56 * 1024;
   p.staged = staged ? 1 : 0;
   p.line_pitch = pitch;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  {  // candidates-only walk when the automaton has a (rare) required byte; MRX_LINES_FILTER=0 turns it off
+    const char *env = getenv("MRX_LINES_FILTER");
+    const size_t req_smem = sizeof(LinesShared) + (size_t)tables +
+                            (size_t)kReqWarps * ((size_t)kReqRing * pitch + kReqRing * sizeof(int64_t));
+    if (staged && p.req_byte >= 0 && p.doc_stride <= 16 * kReqMaxVecs && req_smem <= 220 * 1024 &&
+        !(env && env[0] == '0')) {
+      static size_t req_attr = 0;
+      if (req_smem > req_attr) {
+        cudaFuncSetAttribute(k_lines_req<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)req_smem);
+        cudaFuncSetAttribute(k_lines_req<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)req_smem);
+        req_attr = req_smem;
+      }
+      const int64_t n_groups = (p.n_docs + 31) / 32;
+      const int64_t want = (n_groups + kReqWarps - 1) / kReqWarps;
+      const unsigned grid = (unsigned)(want < sms ? want : sms);
+      if (p.doc_stride == 128) k_lines_req<8><<<grid, kReqThreads, req_smem, st>>>(p);
+      else k_lines_req<0><<<grid, kReqThreads, req_smem, st>>>(p);
+      return;
+    }
+  }
   const int smem = (int)sizeof(LinesShared) + tables + (staged ? kThreads * pitch : 0);
   static int attr_smem = 0;
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
   }
-  int per_sm = 0, dev = 0, sms = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int per_sm = 0;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_lines, kThreads, smem);
   const int64_t n_batches = (p.n_docs + kThreads - 1) / kThreads;
   const int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);

@@ -104,6 +104,7 @@ struct LinesParams {
   int64_t *out;                // (start, end) relative to the document, (-1, -1) = no match
   int32_t staged;              // 1: fixed-size, 16-byte aligned documents staged through shared memory by TMA
   int32_t line_pitch;          // shared-memory bytes per staged document (odd multiple of 16)
+  int32_t req_byte;            // RevTable::req_byte: documents without this byte cannot match (-1: none)
 };
 
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };

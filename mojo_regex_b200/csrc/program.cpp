@@ -428,6 +428,53 @@ void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
 
 }  // namespace
 
+// How common a byte is in ordinary text (higher = more common); only used to choose among required bytes.
+static int byte_commonness(int b) {
+  if (b >= 'a' && b <= 'z') return 6;
+  if (b == ' ') return 7;
+  if (b == '\n') return 5;
+  if (b >= '0' && b <= '9') return 4;
+  if (b >= 'A' && b <= 'Z') return 3;
+  if (b == '.' || b == ',' || b == '-' || b == '_' || b == '/' || b == ':' || b == '\'' || b == '"' || b == '\t') return 2;
+  if (b >= 0x21 && b < 0x7f) return 1;
+  return 0;
+}
+
+// A byte c is required when no accepting state can be reached from the start state without consuming c.
+// Decided on the automaton the kernels walk (which carries the reference's overwrite quirks), never on the
+// pattern text.  Returns the rarest such byte, or -1 when there is none or only common ones (lower-case
+// letters, blanks: nearly every document holds them, a filter would not pay).
+static int required_byte(const Program &p) {
+  const int n = p.n_states;
+  if (n <= 0 || p.start_accepting()) return -1;
+  int best = -1, best_rank = 1 << 30;
+  std::vector<int> stack;
+  std::vector<char> seen((size_t)n);
+  for (int c = 0; c < 256; ++c) {
+    std::fill(seen.begin(), seen.end(), 0);
+    stack.assign(1, p.start_state);
+    seen[(size_t)p.start_state] = 1;
+    bool reach = false;
+    while (!stack.empty() && !reach) {
+      const int q = stack.back();
+      stack.pop_back();
+      for (int b = 0; b < 256 && !reach; ++b) {
+        if (b == c) continue;
+        const int nx = p.next(q, b);
+        if (nx == kDead || seen[(size_t)nx]) continue;
+        if (p.accepting[nx]) reach = true;
+        seen[(size_t)nx] = 1;
+        stack.push_back(nx);
+      }
+    }
+    if (reach) continue;
+    const int rank = byte_commonness(c) * 256 + c;
+    if (rank < best_rank) { best_rank = rank; best = c; }
+  }
+  if (best >= 0 && byte_commonness(best) > 5) return -1;
+  return best;
+}
+
 bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
   rt = RevTable();
   if (pl.unsupported || pl.shortcut || p.n_states <= 0 || p.n_states > 32 || p.start_accepting()) return false;
@@ -473,6 +520,7 @@ bool build_reverse(const Program &p, const Plan &pl, RevTable &rt) {
   for (int i = 0; i < rt.n_rev; ++i)
     for (int b = 0; b < 256; ++b) rt.rev[(size_t)rev_off(i) / 2 + b] = (uint16_t)rev_off(next[(size_t)i * 256 + b]);
   build_forward_table(p, rt.fwd, rt.fwd_start);
+  rt.req_byte = required_byte(p);
   rt.valid = true;
   return true;
 }

@@ -75,6 +75,9 @@ struct RevTable {
   int32_t n_rev = 0;
   std::vector<uint16_t> rev, fwd;  // whole tables (bytes / 2 entries each)
   uint16_t fwd_start = 0;
+  // a byte every accepted string contains (derived from the forward table, not from the pattern), chosen
+  // for rarity, or -1: documents without it cannot match and skip the walk (k_lines_req)
+  int32_t req_byte = -1;
 };
 
 struct Plan {

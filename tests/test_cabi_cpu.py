@@ -225,3 +225,18 @@ def test_random_patterns_front_ends_agree(pattern):
     """Differential test of the two independent restatements of the reference's front end (C++ in the
     product, Python in the oracle): same verdict (tables / unsupported / parse error) on random patterns."""
     test_product_front_end_matches_oracle_tables(pattern)
+
+
+def test_search_skip_byte_is_read_off_the_automaton():
+    """RevTable::req_byte (program.cpp: required_byte): the rarest byte every accepted string contains, or -1
+    when there is none / only common ones.  Used by the batch kernel to skip documents."""
+    cases = {
+        r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-zA-Z]{2,}": ord("@"),
+        r"[A-Z]{2}-[0-9]{3}": ord("-"),
+        r"[89]00[0-9]+": ord("0"),
+        r"[a-z]+[0-9]+": -1,
+        r"(hello|world|foo)": -1,   # 'o' is required but lower-case letters are too common to filter on
+        r"a+b": -1,
+    }
+    for pattern, want in cases.items():
+        assert mr.compile_regex(pattern).info().search_skip_byte == want, pattern

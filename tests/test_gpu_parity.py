@@ -375,6 +375,45 @@ def test_search_batch_lines_kernel_against_oracle(pattern, alphabet):
         del os.environ["MRX_NO_LINES"]
 
 
+SKIP_BYTE_PATTERNS = [
+    (corpora.CONFIGS["c3"]["pattern"], "@", "ab.-_%+Z9 \n"),
+    (r"[A-Z]{2}-[0-9]{3}", "-", "AZ019 "),
+    (r"[89]00[0-9]+", "0", "891a "),
+]
+
+
+@pytest.mark.parametrize("stride", [16, 48, 64, 128])
+@pytest.mark.parametrize("pattern,skip,alphabet", SKIP_BYTE_PATTERNS, ids=[p for p, _, _ in SKIP_BYTE_PATTERNS])
+def test_search_batch_skip_byte_kernel(pattern, skip, alphabet, stride):
+    """k_lines_req: documents without the automaton's required byte are answered without a walk, the others
+    are compacted into full warps.  Sparse and dense candidate mixes, document counts that are not multiples of
+    32, enough documents for the 64-row ring to wrap many times; checked against the oracle document by document
+    and against the unfiltered kernel."""
+    import os
+
+    rx = mr.compile_regex(pattern)
+    assert rx.info().search_skip_byte == ord(skip)
+    orx = oracle.compile(pattern)
+    rng = np.random.default_rng(stride * 131 + len(pattern))
+    for n_docs, p_cand in ((1, 1.0), (31, 0.5), (33, 0.0), (5003, 0.35), (2049, 0.97), (4000, 0.02)):
+        without = np.frombuffer(alphabet.encode(), dtype=np.uint8)
+        with_ = np.frombuffer((alphabet + skip * 2).encode(), dtype=np.uint8)
+        docs = without[rng.integers(0, without.size, (n_docs, stride))]
+        cand = rng.random(n_docs) < p_cand
+        docs[cand] = with_[rng.integers(0, with_.size, (int(cand.sum()), stride))]
+        text = np.ascontiguousarray(docs.reshape(-1))
+        got = rx.search_batch(text, doc_stride=stride)
+        step = 1 if n_docs <= 2049 else 3
+        for i in range(0, n_docs, step):
+            r = orx.search(text[stride * i:stride * (i + 1)])
+            assert tuple(got[i]) == (r if r else (-1, -1)), (pattern, stride, n_docs, i, bytes(docs[i]))
+        os.environ["MRX_LINES_FILTER"] = "0"
+        try:
+            assert np.array_equal(rx.search_batch(text, doc_stride=stride), got)
+        finally:
+            del os.environ["MRX_LINES_FILTER"]
+
+
 # ---- assembly kernels (k_seg_lengths / k_assemble) on shapes that stress the tile logic ---------------------
 def _rand_text(alphabet: bytes, n: int, seed: int) -> np.ndarray:
     rng = np.random.default_rng(seed)
