@@ -13,6 +13,7 @@ gathered records is plain Python so that the world_size-2 gloo tests exercise it
 
 from __future__ import annotations
 
+import os
 import time
 from dataclasses import dataclass
 from typing import List, Optional, Tuple
@@ -425,7 +426,10 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
         out = getattr(shard, "_batch_out", None)
         if out is None:
             out = shard._batch_out = torch.empty((shard.n_docs, 2), dtype=torch.int64, device=dev)
-            shard._batch_kernel = "k_lines" if rx.info().search_rev_states > 0 else "k_scan"
+            info = rx.info()
+            shard._batch_kernel = ("k_scan" if info.search_rev_states <= 0 else
+                                   "k_lines_req" if info.search_skip_byte >= 0 and os.environ.get("MRX_LINES_FILTER", "1")[:1] != "0"
+                                   else "k_lines")
         rx.search_batch_device(shard.text, out.data_ptr(), shard.n_docs, doc_stride=128, sync=False)
         if multi:
             _gather_for(1, dev).gather([shard.n_docs])
