@@ -181,6 +181,20 @@ Filter make_filter(const Plan &pl) {
   return f;
 }
 
+// a table that lives as long as its regex: plain cudaMalloc (not the pool), freed again if the copy fails
+int upload_blob(const void *src, size_t n, void **out) {
+  void *d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, n));
+  cudaError_t e = cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, g.stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g.stream);
+  if (e != cudaSuccess) {
+    cudaFree(d);
+    return fail(MRX_E_CUDA, std::string("table upload: ") + cudaGetErrorString(e));
+  }
+  *out = d;
+  return MRX_OK;
+}
+
 int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
   // attempts walk a dense forward table (one lookup per byte) when it fits the table budget, else the
   // class-compressed one (byte -> class, (state, class) -> state, state -> accepting)
@@ -212,9 +226,7 @@ int upload_devprog(const Program &p, const Plan &pl, DevProg **out) {
   if (dense_fwd) std::memcpy(h->trans, fwd.data(), fwd.size() * 2);
   else if (!p.trans.empty()) std::memcpy(h->trans, p.trans.data(), p.trans.size());
   void *d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, sizeof(DevProg)));
-  CUDA_TRY(cudaMemcpyAsync(d, h, sizeof(DevProg), cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (int rc = upload_blob(h, sizeof(DevProg), &d)) return rc;
   *out = static_cast<DevProg *>(d);
   return MRX_OK;
 }
@@ -236,9 +248,7 @@ int upload_dense(const DenseTable &dt, uint8_t **out) {
   std::memcpy(h->len_lut, dt.len_lut.data(), 32);
   std::memcpy(raw.data() + sizeof(DenseHdr), dt.next.data(), dt.next.size() * 2);
   void *d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, raw.size()));
-  CUDA_TRY(cudaMemcpyAsync(d, raw.data(), raw.size(), cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  if (int rc = upload_blob(raw.data(), raw.size(), &d)) return rc;
   *out = static_cast<uint8_t *>(d);
   return MRX_OK;
 }
@@ -252,9 +262,7 @@ int ensure_uploaded(mrx_regex *re) {
     std::vector<uint16_t> tb(rt.rev);
     tb.insert(tb.end(), rt.fwd.begin(), rt.fwd.end());
     void *d = nullptr;
-    CUDA_TRY(cudaMalloc(&d, tb.size() * 2));
-    CUDA_TRY(cudaMemcpyAsync(d, tb.data(), tb.size() * 2, cudaMemcpyHostToDevice, g.stream));
-    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    if (int rc = upload_blob(tb.data(), tb.size() * 2, &d)) return rc;
     re->d_rev_search = static_cast<uint8_t *>(d);
   }
   if (!re->d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->d_findall); if (rc) return rc; }
