@@ -429,6 +429,20 @@ search(f"{TD}:289 (find_first_match)", "[abc]", "x", None)
 search(f"{TD}:303-308 (find_first_nibble_match)", "[89]", "Call 8001234567", starts=5)
 search(f"{TD}:311-316 (find_first_nibble_match)", r"\(", "hello (world)", starts=6)
 
+# ---- tests/test_literal_optimization.mojo: the literal searchers' contract, through the regex API --------
+# (twoway_search / MultiLiteralSearcher are prefilter helpers, not the DFA scan itself; the assertions fix
+#  WHERE the literals occur in these texts, which is what findall over the same literals must return.)
+TLO = "tests/test_literal_optimization.mojo"
+_FOX = "The quick brown fox jumps over the lazy dog. The fox is quick."
+findall(f"{TLO}:125-129 (twoway_search)", "fox", _FOX, starts=[16, 49])
+findall(f"{TLO}:135-136 (twoway_search)", "cat", _FOX, spans=[])
+search(f"{TLO}:142-143 (twoway_search)", "quick brown", _FOX, starts=4)
+findall(f"{TLO}:149-153 (twoway_search)", "quick", _FOX, starts=[4, 56])
+findall(f"{TLO}:168-182 (MultiLiteralSearcher)", "(apple|banana|cherry)", "apple banana cherry apple pie banana split",
+        starts=[0, 6, 13, 20, 30])
+search(f"{TLO}:207-210", "hello", "abcdefghello", starts=7)
+findall(f"{TLO}:215-217", "[0-9]+", "Price: 100, Cost: 200, Total: 300", count=3)
+
 # ---- assertions the reference answers through its NFA engines (out of scope) --------
 NFA_ROUTED = [
     dict(src=f"{TM}:729", pattern="^[a-z]+$"),
@@ -455,6 +469,8 @@ NFA_ROUTED = [
     dict(src=f"{TP}:332", pattern=r"\w*@"),
     dict(src=f"{TC}:79", pattern="(a|b)x"),
     dict(src=f"{TC}:85", pattern="h[ae]llo"),
+    dict(src=f"{TLO}:192", pattern="hello.*!"),
+    dict(src=f"{TLO}:203", pattern="[a-z]+@example.(com|org)"),
     dict(src=f"{TM}:1808", pattern="3[02]|40"),
     dict(src=f"{TM}:1811", pattern="3[02]|40|[68]9"),
     dict(src=f"{TM}:1816", pattern="24|[346]|7[2-57-9]|9[2-9]"),
