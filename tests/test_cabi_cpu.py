@@ -240,3 +240,37 @@ def test_search_skip_byte_is_read_off_the_automaton():
     }
     for pattern, want in cases.items():
         assert mr.compile_regex(pattern).info().search_skip_byte == want, pattern
+
+
+def test_skip_byte_is_required_according_to_the_oracle():
+    """Whatever byte the planner derives as `search_skip_byte`, the restated reference must find nothing in
+    documents that lack it -- and the filter must not be claimed for a byte some match can do without.
+    Random DFA-routed patterns; documents drawn from the bytes the pattern mentions plus filler."""
+    import random
+
+    rng = random.Random(77)
+    checked = 0
+    for pattern in _random_patterns(420, 20261018):
+        try:
+            info = mr.compile_regex(pattern).info()
+            orx = oracle.compile(pattern)
+        except (mr.RegexError, mr.UnsupportedPattern, mr.UndefinedBehaviour, oracle.Unsupported, oracle.RegexError):
+            continue
+        c = info.search_skip_byte
+        if c < 0:
+            continue
+        assert info.search_rev_states > 0
+        alphabet = bytes(sorted(set(b"abcxhelowrdfn0189AZ.,;@-_%+ \t\n") - {c}))
+        for _ in range(60):
+            doc = bytes(rng.choice(alphabet) for _ in range(rng.randint(0, 48)))
+            assert orx.search(doc) is None, (pattern, chr(c), doc)
+        # and with the byte available the pattern is satisfiable at all (the filter is not vacuous)
+        hit = False
+        full = alphabet + bytes([c]) * 6
+        for _ in range(4000):
+            doc = bytes(rng.choice(full) for _ in range(rng.randint(1, 24)))
+            if orx.search(doc) is not None:
+                hit = True
+                break
+        checked += 1 if hit else 0
+    assert checked >= 6
