@@ -1,5 +1,5 @@
 // Core of the next finder for patterns of the shape X* c Y* (C5: `\s*,\s*`) -- NOT part of the library yet: no
-// product source includes this header.  It exists so that the arithmetic can be checked on the CPU
+// product source includes this header (only the experimental next/k_sep.cu does).  It exists so that the arithmetic can be checked on the CPU
 // (tests/test_sep_core_cpu.py compiles it with g++ and holds it against the oracle) before it is wrapped in a
 // kernel.  DESIGN.md section 8, item 1; the closed form it implements is in tests/test_finder_model_cpu.py.
 //
@@ -69,13 +69,39 @@ MRX_HD WordBits classify4(uint32_t w, const Classes &k) {
 
 struct Window { uint32_t c[kWords], l[kWords], bad[kWords]; };
 
-// 32 bits of a bit array starting at window position p (0 <= p, p + 32 <= 32 * kWords)
-MRX_HD uint32_t take32(const uint32_t *w, int p) {
-  const int k = p >> 5, s = p & 31;
-  const uint32_t lo = w[k];
-  const uint32_t hi = k + 1 < kWords ? w[k + 1] : 0u;
-  return s ? (lo >> s) | (hi << (32 - s)) : lo;
+// membership bits of 16 bytes given as four little-endian words (bit i = byte i); `live` = how many of the 16
+// bytes exist in the text (bits of the others are cleared)
+MRX_HD void bits16(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, int live, const Classes &k, uint32_t &c,
+                   uint32_t &l, uint32_t &b) {
+  const uint32_t ws[4] = {w0, w1, w2, w3};
+  c = l = b = 0;
+  for (int i = 0; i < 4; ++i) {
+    const WordBits r = classify4(ws[i], k);
+    c |= r.c << (4 * i);
+    l |= r.l << (4 * i);
+    b |= r.bad << (4 * i);
+  }
+  if (live < 16) {
+    const uint32_t m = live <= 0 ? 0u : ((1u << live) - 1u);
+    c &= m; l &= m; b &= m;
+  }
 }
+
+// Bit streams of one tile (one uint16 per 16 text bytes, per set): halfwords [0, 2) = the 32 bytes before the
+// tile, [2, 2 + 9 T) = the tile (T threads x 9 vectors), then 3 halfwords for the 48 bytes after it.
+constexpr int kStreamPre = 2, kStreamPost = 3;
+MRX_HD int stream_chunk(int tid, int vec) { return kStreamPre + 9 * tid + vec; }
+MRX_HD int stream_post(int n_threads, int vec) { return kStreamPre + 9 * n_threads + vec; }
+// the 224 window bits of thread tid: 14 halfwords starting 2 halfwords (32 bits) before its chunk
+MRX_HD void window_from_streams(const uint16_t *bc, const uint16_t *bl, const uint16_t *bb, int tid, Window &w) {
+  for (int k = 0; k < kWords; ++k) {
+    const int h = 9 * tid + 2 * k;
+    w.c[k] = (uint32_t)bc[h] | ((uint32_t)bc[h + 1] << 16);
+    w.l[k] = (uint32_t)bl[h] | ((uint32_t)bl[h + 1] << 16);
+    w.bad[k] = (uint32_t)bb[h] | ((uint32_t)bb[h + 1] << 16);
+  }
+}
+
 MRX_HD int clz32(uint32_t x) {
 #if defined(__CUDA_ARCH__)
   return __clz((int)x);
@@ -91,21 +117,27 @@ MRX_HD int ctz32(uint32_t x) {
 #endif
 }
 
-// The separator that owns the comma at window position p (kPre <= p < kPre + kChunk).
-// Returns 1 and (start, end) as window positions, 0 when the reference reports nothing for this comma;
-// sets *overflow when a run is too long for the window.
-MRX_HD int separator_at(const Window &w, int p, int *start, int *end, int *overflow) {
-  const uint32_t below = take32(w.l, p - 32);                 // bit 31 = position p - 1
-  const int back = clz32(~below);                             // leading ones
-  const uint32_t above = take32(w.l, p + 1) & ~take32(w.bad, p + 1);  // Y = X = L \ bad; bit 0 = position p + 1
-  const int fwd = ctz32(~above);                              // trailing ones
-  if (back == 32 || fwd == 32) *overflow = 1;
-  if (back > 0) {
-    const uint32_t badbelow = take32(w.bad, p - 32);
-    if (badbelow >> (32 - back)) return 0;                    // the attempt dies inside the back-scanned run
+// The separator that owns the comma at bit j of window word k (window position p = 32 k + j), given the words
+// k - 1, k, k + 1 of the L and bad streams -- the caller indexes them statically, so a kernel keeps the
+// window in registers.  Returns 1 and the run lengths (start = p - back, end = p + 1 + fwd), 0 when the
+// reference reports nothing for this comma; sets *overflow when a run fills its 32-bit window (longer than
+// the window can tell).
+MRX_HD int separator_at(uint32_t l_prev, uint32_t l_cur, uint32_t l_next, uint32_t b_prev, uint32_t b_cur,
+                        uint32_t b_next, int j, int *back, int *fwd, int *overflow) {
+  // the 32 L-bits below p: bit 31 = position p - 1
+  const uint32_t below = (uint32_t)(((((uint64_t)l_cur) << 32) | l_prev) >> j);
+  const int nb = clz32(~below);  // leading ones
+  // the 32 Y-bits above p (Y = X = L minus bad): bit 0 = position p + 1
+  const uint64_t y2 = ((((uint64_t)(l_next & ~b_next)) << 32) | (l_cur & ~b_cur));
+  const uint32_t above = (uint32_t)(y2 >> (j + 1));
+  const int nf = ctz32(~above);  // trailing ones
+  if (nb == 32 || nf == 32) *overflow = 1;
+  *back = nb;
+  *fwd = nf;
+  if (nb > 0) {
+    const uint32_t badbelow = (uint32_t)(((((uint64_t)b_cur) << 32) | b_prev) >> j);
+    if (badbelow >> (32 - nb)) return 0;  // the attempt dies inside the back-scanned run
   }
-  *start = p - back;
-  *end = p + 1 + fwd;
   return 1;
 }
 

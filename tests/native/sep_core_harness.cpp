@@ -1,14 +1,31 @@
-// CPU harness for mojo_regex_b200/csrc/next/sep_core.hpp: walks a text the way the kernel's threads will
-// (144-byte chunks, 224-bit windows built from SWAR membership flags) and lists the separators.
+// CPU harness for mojo_regex_b200/csrc/next/sep_core.hpp: emulates k_sep tile by tile with the kernel's own
+// index arithmetic (T threads x 144 bytes per tile, three halfword bit streams with 2 + 3 halo halfwords, 224-bit
+// windows read back from the streams) and lists the separators.  `threads` is a parameter so that small texts
+// span several tiles.
 #include <cstdint>
 #include <cstring>
+#include <vector>
 
 #include "../../mojo_regex_b200/csrc/next/sep_core.hpp"
 
 using namespace mrx::sep;
 
-extern "C" int64_t sep_scan(const uint8_t *text, int64_t n, int needle, int range_lo, int range_hi, const int *extra,
-                            int n_extra, const int *bad, int n_bad, int64_t *out, int64_t cap, int *overflow) {
+static void bits_at(const uint8_t *text, int64_t n, int64_t pos, const Classes &k, uint32_t &c, uint32_t &l, uint32_t &b) {
+  // 16 bytes starting at pos (may start before the text or run past its end)
+  uint8_t buf[16] = {0};
+  c = l = b = 0;
+  uint32_t valid = 0;
+  for (int i = 0; i < 16; ++i)
+    if (pos + i >= 0 && pos + i < n) { buf[i] = text[pos + i]; valid |= 1u << i; }
+  uint32_t w[4];
+  std::memcpy(w, buf, 16);
+  bits16(w[0], w[1], w[2], w[3], 16, k, c, l, b);
+  c &= valid; l &= valid; b &= valid;
+}
+
+extern "C" int64_t sep_scan(const uint8_t *text, int64_t n, int threads, int needle, int range_lo, int range_hi,
+                            const int *extra, int n_extra, const int *bad, int n_bad, int64_t *out, int64_t cap,
+                            int *overflow) {
   Classes k{};
   k.needle = (uint32_t)needle * 0x01010101u;
   k.range_lo = (uint32_t)range_lo;
@@ -19,29 +36,41 @@ extern "C" int64_t sep_scan(const uint8_t *text, int64_t n, int needle, int rang
   for (int i = 0; i < n_bad; ++i) k.bad[i] = (uint32_t)bad[i] * 0x01010101u;
   *overflow = 0;
   int64_t m = 0;
-  for (int64_t chunk0 = 0; chunk0 < n; chunk0 += kChunk) {
-    Window w{};
-    for (int word = 0; word < kWords; ++word) {
-      for (int q = 0; q < 8; ++q) {  // 8 groups of 4 bytes per 32-bit word of the window
-        const int64_t pos = chunk0 - kPre + 32 * word + 4 * q;
-        uint8_t four[4] = {0, 0, 0, 0};
-        uint32_t valid = 0;
-        for (int b = 0; b < 4; ++b)
-          if (pos + b >= 0 && pos + b < n) { four[b] = text[pos + b]; valid |= 1u << b; }
-        uint32_t packed;
-        std::memcpy(&packed, four, 4);
-        const WordBits r = classify4(packed, k);
-        w.c[word] |= (r.c & valid) << (4 * q);
-        w.l[word] |= (r.l & valid) << (4 * q);
-        w.bad[word] |= (r.bad & valid) << (4 * q);
+  const int64_t tile_bytes = (int64_t)threads * kChunk;
+  const int hw = kStreamPre + 9 * threads + kStreamPost + 1;
+  std::vector<uint16_t> bc((size_t)hw), bl((size_t)hw), bb((size_t)hw);
+  for (int64_t tile_start = 0; tile_start < n; tile_start += tile_bytes) {
+    uint32_t c, l, b;
+    for (int tid = 0; tid < threads; ++tid)
+      for (int v = 0; v < 9; ++v) {
+        bits_at(text, n, tile_start + (int64_t)tid * kChunk + 16 * v, k, c, l, b);
+        bc[(size_t)stream_chunk(tid, v)] = (uint16_t)c; bl[(size_t)stream_chunk(tid, v)] = (uint16_t)l; bb[(size_t)stream_chunk(tid, v)] = (uint16_t)b;
       }
+    for (int i = 0; i < kStreamPre; ++i) {
+      bits_at(text, n, tile_start - 32 + 16 * i, k, c, l, b);
+      bc[(size_t)i] = (uint16_t)c; bl[(size_t)i] = (uint16_t)l; bb[(size_t)i] = (uint16_t)b;
     }
-    for (int p = kPre; p < kPre + kChunk; ++p) {
-      if (!((w.c[p >> 5] >> (p & 31)) & 1u)) continue;
-      int s, e;
-      if (separator_at(w, p, &s, &e, overflow)) {
-        if (m < cap) { out[2 * m] = chunk0 - kPre + s; out[2 * m + 1] = chunk0 - kPre + e; }
-        ++m;
+    for (int v = 0; v < kStreamPost; ++v) {
+      bits_at(text, n, tile_start + tile_bytes + 16 * v, k, c, l, b);
+      bc[(size_t)stream_post(threads, v)] = (uint16_t)c; bl[(size_t)stream_post(threads, v)] = (uint16_t)l; bb[(size_t)stream_post(threads, v)] = (uint16_t)b;
+    }
+    for (int tid = 0; tid < threads; ++tid) {
+      Window w;
+      window_from_streams(bc.data(), bl.data(), bb.data(), tid, w);
+      const int64_t chunk0 = tile_start + (int64_t)tid * kChunk;
+      for (int kk = 1; kk < kWords - 1; ++kk) {  // chunk = window positions 32 .. 175
+        uint32_t f = w.c[kk];
+        if (kk == 5) f &= 0xffffu;
+        while (f) {
+          const int j = __builtin_ctz(f);
+          f &= f - 1;
+          int back, fwd;
+          if (separator_at(w.l[kk - 1], w.l[kk], w.l[kk + 1], w.bad[kk - 1], w.bad[kk], w.bad[kk + 1], j, &back, &fwd, overflow)) {
+            const int64_t pos = chunk0 - kPre + 32 * kk + j;
+            if (m < cap) { out[2 * m] = pos - back; out[2 * m + 1] = pos + 1 + fwd; }
+            ++m;
+          }
+        }
       }
     }
   }

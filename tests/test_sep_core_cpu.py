@@ -23,13 +23,13 @@ def harness():
                            os.path.join(HERE, "native", "sep_core_harness.cpp")])
     lib = ctypes.CDLL(out)
     lib.sep_scan.restype = ctypes.c_int64
-    lib.sep_scan.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    lib.sep_scan.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                              ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                              ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
     return lib
 
 
-def scan_ws_comma(lib, text: bytes):
+def scan_ws_comma(lib, text: bytes, threads: int = 256):
     """`\\s*,\\s*`: L = {9..13, 32} (simd_ops.mojo:879-883), bad = {11} (the DFA's \\s has no \\v, dfa.mojo:2901-2902)."""
     buf = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, np.uint8)
     cap = len(text) + 1
@@ -37,7 +37,7 @@ def scan_ws_comma(lib, text: bytes):
     extra = (ctypes.c_int * 2)(32, 0)
     bad = (ctypes.c_int * 2)(11, 0)
     ovf = ctypes.c_int(0)
-    m = lib.sep_scan(buf.ctypes.data, len(text), ord(","), 9, 13, extra, 1, bad, 1, out.ctypes.data, cap, ctypes.byref(ovf))
+    m = lib.sep_scan(buf.ctypes.data, len(text), threads, ord(","), 9, 13, extra, 1, bad, 1, out.ctypes.data, cap, ctypes.byref(ovf))
     return out[:m].tolist(), bool(ovf.value)
 
 
@@ -64,11 +64,12 @@ def test_random_texts_all_chunk_alignments(harness):
     for _ in range(1500):
         n = rng.choice([0, 1, 2, 31, 143, 144, 145, 175, 176, 177, 288, 300, 500])
         t = bytes(rng.choice(alphabet) for _ in range(n))
-        got, ovf = scan_ws_comma(harness, t)
-        if ovf:
-            assert longest_blank_run(t) >= 32
-            continue
-        assert got == rx.findall(t).tolist(), t
+        for threads in (1, 2, 256):      # tiles of 144, 288 and 36 864 bytes: the halo halfwords get exercised
+            got, ovf = scan_ws_comma(harness, t, threads)
+            if ovf:
+                assert longest_blank_run(t) >= 32
+                continue
+            assert got == rx.findall(t).tolist(), (threads, t)
 
 
 def test_long_runs_raise_overflow_instead_of_guessing(harness):
