@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../mojo_regex_b200/csrc/next/sep_core.hpp"
+#include "../../mojo_regex_b200/csrc/next/sep_plan.hpp"
 
 using namespace mrx::sep;
 
@@ -23,6 +24,9 @@ static void bits_at(const uint8_t *text, int64_t n, int64_t pos, const Classes &
   c &= valid; l &= valid; b &= valid;
 }
 
+static int64_t scan_with(const Classes &k, const uint8_t *text, int64_t n, int threads, int64_t *out, int64_t cap,
+                         int *overflow);
+
 extern "C" int64_t sep_scan(const uint8_t *text, int64_t n, int threads, int needle, int range_lo, int range_hi,
                             const int *extra, int n_extra, const int *bad, int n_bad, int64_t *out, int64_t cap,
                             int *overflow) {
@@ -34,6 +38,20 @@ extern "C" int64_t sep_scan(const uint8_t *text, int64_t n, int threads, int nee
   for (int i = 0; i < n_extra; ++i) k.extra[i] = (uint32_t)extra[i] * 0x01010101u;
   k.n_bad = n_bad;
   for (int i = 0; i < n_bad; ++i) k.bad[i] = (uint32_t)bad[i] * 0x01010101u;
+  return scan_with(k, text, n, threads, out, cap, overflow);
+}
+
+// planner + scan: -2 when the automaton is not of the X* c Y* shape (or its sets cannot be expressed)
+extern "C" int64_t sep_detect_scan(const int32_t *trans, const uint8_t *accepting, int n_states, int start,
+                                   const uint8_t *lookup, int c, const uint8_t *text, int64_t n, int threads,
+                                   int64_t *out, int64_t cap, int *overflow) {
+  Classes k{};
+  if (!detect(trans, accepting, n_states, start, lookup, c, k)) return -2;
+  return scan_with(k, text, n, threads, out, cap, overflow);
+}
+
+static int64_t scan_with(const Classes &k, const uint8_t *text, int64_t n, int threads, int64_t *out, int64_t cap,
+                         int *overflow) {
   *overflow = 0;
   int64_t m = 0;
   const int64_t tile_bytes = (int64_t)threads * kChunk;

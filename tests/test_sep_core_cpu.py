@@ -26,6 +26,10 @@ def harness():
     lib.sep_scan.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                              ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                              ctypes.c_void_p, ctypes.c_int64, ctypes.POINTER(ctypes.c_int)]
+    lib.sep_detect_scan.restype = ctypes.c_int64
+    lib.sep_detect_scan.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                    ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p, ctypes.c_int64,
+                                    ctypes.POINTER(ctypes.c_int)]
     return lib
 
 
@@ -81,3 +85,55 @@ def test_long_runs_raise_overflow_instead_of_guessing(harness):
                 assert not ovf and got == rx.findall(t).tolist(), (run, t)
             else:
                 assert ovf, (run, t)
+
+
+def detect_and_scan(lib, pattern: str, text: bytes, threads: int = 2):
+    """Planner (sep_plan.hpp) on the oracle's automaton for `pattern`, then the scan.  None = shape not recognised."""
+    rx = oracle.compile(pattern)
+    c = rx.compiled
+    if c.dfa is None or c.dfa.matcher is None or c.required_byte < 0:
+        return None, False, rx
+    trans = np.ascontiguousarray(np.asarray(c.dfa.trans, dtype=np.int32).reshape(-1, 256))
+    acc = np.asarray(c.dfa.accepting, dtype=np.uint8)
+    lookup = np.asarray(c.dfa.matcher.lookup, dtype=np.uint8)
+    buf = np.frombuffer(text, dtype=np.uint8) if text else np.zeros(1, np.uint8)
+    cap = len(text) + 1
+    out = np.zeros((cap, 2), dtype=np.int64)
+    ovf = ctypes.c_int(0)
+    m = lib.sep_detect_scan(trans.ctypes.data, acc.ctypes.data, trans.shape[0], c.dfa.start_state, lookup.ctypes.data,
+                            c.required_byte, buf.ctypes.data, len(text), threads, out.ctypes.data, cap, ctypes.byref(ovf))
+    if m == -2:
+        return None, False, rx
+    return out[:m].tolist(), bool(ovf.value), rx
+
+
+SHAPED = [r"\s*,\s*", r"\s*;\s*", r" *, *", r"\s*,", r",\s*", r"\d*-\d*", r"[ab]*,[ab]*", r"\s*=\s*"]
+NOT_SHAPED = [r"\s*,\s*,", r"[a-z]+@[a-z]+", r"\s+,\s*", r"(hello|world|foo)", r"\d+"]
+
+
+def test_planner_recognises_the_family_and_the_scan_equals_the_oracle(harness):
+    rng = random.Random(33)
+    recognised = 0
+    for pattern in SHAPED:
+        try:
+            got, _, rx = detect_and_scan(harness, pattern, b"")
+        except (oracle.Unsupported, oracle.RegexError):
+            continue
+        if got is None:
+            continue
+        recognised += 1
+        alphabet = b"ab01,;=- \t\n\x0b"
+        for _ in range(300):
+            t = bytes(rng.choice(alphabet) for _ in range(rng.randint(0, 320)))
+            for threads in (1, 2):
+                got, ovf, _ = detect_and_scan(harness, pattern, t, threads)
+                if ovf:
+                    continue
+                assert got == rx.findall(t).tolist(), (pattern, threads, t)
+    assert recognised >= 4
+    for pattern in NOT_SHAPED:
+        try:
+            got, _, _ = detect_and_scan(harness, pattern, b"a, b")
+        except (oracle.Unsupported, oracle.RegexError):
+            continue
+        assert got is None, pattern
