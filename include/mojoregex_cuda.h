@@ -151,7 +151,10 @@ void mrx_regex_free(mrx_regex *re);
 /* ---- texts ---------------------------------------------------------------------------- */
 /* Copy `n` host bytes into HBM (staged through pinned memory, async on the library stream). */
 int mrx_text_upload(const uint8_t *host, size_t n, mrx_text **out);
-/* Wrap `n` bytes already in device memory (not copied, not freed). */
+/* Wrap `n` bytes already in device memory (not copied, not freed).  Stream contract: the library's stream is
+ * created with cudaStreamNonBlocking and is NOT ordered after the stream that produced the buffer; the caller
+ * synchronises its producer stream (or makes mrx_stream() wait on an event of it) before the first matching
+ * call on the wrapped text. */
 int mrx_text_wrap_device(const void *dptr, size_t n, mrx_text **out);
 /* Multi-GPU shards: the buffer is [left halo | core | right halo].  Matching behaves as if
  * the text were exactly the buffer, but only matches whose key (start; the needle hit for

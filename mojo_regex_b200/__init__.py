@@ -9,7 +9,7 @@ matching path -- same names, argument meaning and error behaviour as
     sub(pattern, repl, text, count=0) / split(pattern, text, maxsplit=0)
 
 All matching runs in libmojoregex_cuda.so (hand-written sm_100a kernels); there is no
-CPU fallback.  Importing the package without the built library raises ImportError;
+CPU fallback.  The library is loaded on first use; without the built library that raises ImportError;
 matching without a CUDA device raises RegexCudaError.
 """
 
@@ -142,7 +142,19 @@ def _load() -> ctypes.CDLL:
     return lib
 
 
-lib = _load()
+class _LazyLib:
+    """libmojoregex_cuda.so is loaded on first use, not at import: helpers of this package that never touch
+    the GPU (corpus generators, the shard arithmetic) can be imported without pulling the library in."""
+
+    _lib = None
+
+    def __getattr__(self, name):
+        if _LazyLib._lib is None:
+            _LazyLib._lib = _load()
+        return getattr(_LazyLib._lib, name)
+
+
+lib = _LazyLib()
 _initialised_device: Optional[int] = None
 
 
@@ -254,8 +266,13 @@ class Text:
 
     @classmethod
     def from_tensor(cls, t) -> "Text":
-        """Wrap a contiguous CUDA uint8 torch tensor without copying."""
+        """Wrap a contiguous CUDA uint8 torch tensor without copying.  The library stream is non-blocking and
+        not ordered after torch's streams (see mrx_text_wrap_device): the producer stream of `t` is
+        synchronised here so that the kernels never read an unfinished buffer."""
+        import torch
+
         assert t.is_cuda and t.is_contiguous() and t.element_size() == 1
+        torch.cuda.current_stream(t.device).synchronize()
         return cls(device_ptr=t.data_ptr(), nbytes=t.numel(), keepalive=t)
 
     @classmethod

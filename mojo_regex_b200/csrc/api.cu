@@ -116,6 +116,33 @@ struct DevTmp {
   template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// a pool block that is handed on with take() or goes back to the pool when the scope is left early
+struct PoolBlock {
+  void *p = nullptr;
+  ~PoolBlock() { dev_release(p); }
+  void *take() { void *q = p; p = nullptr; return q; }
+};
+// sub / split bracket their whole kernel sequence: list jobs must not record while the flag is up, and the flag
+// must come down on every exit path
+struct ProfOuter {
+  bool armed = false;
+  void arm() { if (g.profiling) { g.prof_outer = armed = true; cudaEventRecord(g.ev0, g.stream); } }
+  void disarm() { if (armed) { g.prof_outer = false; armed = false; } }
+  ~ProfOuter() { disarm(); }
+};
+// result owner that is released again unless the call commits it (early CUDA_TRY returns included)
+struct OwnerGuard {
+  void *own;
+  void **slot;
+  ~OwnerGuard();
+  void commit() { own = nullptr; }
+};
+// the host-buffer pipelines own device / pinned blocks that async copies on the side streams still use: drain
+// those streams before the blocks can go back to the pool, whatever the exit path
+struct DrainSideStreams {
+  ~DrainSideStreams() { if (g.s_in) cudaStreamSynchronize(g.s_in); if (g.s_out) cudaStreamSynchronize(g.s_out); }
+};
+
 }  // namespace
 
 struct mrx_regex {
@@ -149,6 +176,9 @@ void release_owner(void *o) {
   for (void *p : w->dev) dev_release(p);
   for (void *p : w->host) host_release(p);
   delete w;
+}
+OwnerGuard::~OwnerGuard() {
+  if (own) { release_owner(own); *slot = nullptr; }
 }
 
 // MRX_DEBUG_SYNC=1: synchronise after the named launch and report which one failed (debugging aid)
@@ -345,7 +375,10 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
   const int64_t n = (int64_t)job.t->n;
   const bool at_end = pl.try_at_end && job.re->prog.start_accepting() && job.key_hi >= n;
   const int64_t origin = job.key_lo & ~15ll;
-  const int64_t last_pos = at_end ? n : job.key_hi - 1;
+  int64_t last_pos = at_end ? n : job.key_hi - 1;
+  // the dense kernel records a match in the tile that holds its END byte: a match that starts inside the key
+  // window may end up to max_len - 1 bytes past it (its start is filtered against the window by the kernel)
+  if (job.dense && !want_keys) last_pos = std::min<int64_t>(n - 1, job.key_hi - 1 + std::max(pl.dense.max_len - 1, 0));
   const int64_t tiles = n_tiles_for(origin, last_pos);
   out.n = 0;
   if (tiles <= 0) return MRX_OK;
@@ -355,10 +388,10 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
   int rc = desc.get(sizeof(unsigned long long) * tiles);
   if (rc) return rc;
   for (int attempt = 0; attempt < 3; ++attempt) {
-    void *spans = nullptr, *keys = nullptr;
-    rc = dev_alloc(sizeof(int64_t) * 2 * cap, &spans);
-    if (rc) return rc;
-    if (want_keys) { rc = dev_alloc(sizeof(int64_t) * cap, &keys); if (rc) { dev_release(spans); return rc; } }
+    PoolBlock b_spans, b_keys;
+    if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &b_spans.p))) return rc;
+    if (want_keys && (rc = dev_alloc(sizeof(int64_t) * cap, &b_keys.p))) return rc;
+    void *spans = b_spans.p, *keys = b_keys.p;
     CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
@@ -382,18 +415,15 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
-    rc = read_scalars(0, 1);
-    if (rc) { dev_release(spans); dev_release(keys); return rc; }
+    if ((rc = read_scalars(0, 1))) return rc;
     const int64_t total = (int64_t)g.h_scalars[0];
     note_density(job, total);
     if (total <= cap) {
-      out.spans = (int64_t *)spans;
+      out.spans = (int64_t *)b_spans.take();
       out.n = total;
-      if (keys_out) *keys_out = (int64_t *)keys; else dev_release(keys);
+      if (keys_out) *keys_out = (int64_t *)b_keys.take();
       return MRX_OK;
     }
-    dev_release(spans);
-    dev_release(keys);
     cap = total;
   }
   return fail(MRX_E_CUDA, "match count did not stabilise");
@@ -407,7 +437,7 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
   out.n = 0;
   if (tiles <= 0) return MRX_OK;
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
-  DevTmp desc, trail, allf, carry;
+  DevTmp desc, trail, allf, carry, carry0;
   int rc = desc.get(sizeof(unsigned long long) * tiles);
   if (rc) return rc;
   const long long *d_carry = nullptr;
@@ -415,17 +445,25 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     if ((rc = trail.get(sizeof(long long) * tiles))) return rc;
     if ((rc = allf.get(sizeof(int) * tiles))) return rc;
     if ((rc = carry.get(sizeof(long long) * tiles))) return rc;
-    // the carry of the first tile is the run length ending just before `origin`: cover it by
-    // starting the trailing-run pass one tile earlier when there is text to the left
+    // the carry of the first tile is the length of the class run that ends right before `origin` (a windowed
+    // text: the kernel sees the whole buffer, so a run straddling core_begin keeps its phase)
+    const long long *d_carry0 = nullptr;
+    if (origin > 0) {
+      if ((rc = carry0.get(sizeof(long long)))) return rc;
+      launch_back_run(job.t->d, origin, job.dprog, carry0.as<long long>(), g.stream);
+      ++g.launches;
+      d_carry0 = carry0.as<long long>();
+    }
     launch_tile_trailing(job.t->d, n, origin, (int)tiles, job.dprog, trail.as<long long>(), allf.as<int>(), g.stream);
-    launch_carry_scan((int)tiles, trail.as<long long>(), allf.as<int>(), carry.as<long long>(), g.stream);
+    launch_carry_scan((int)tiles, trail.as<long long>(), allf.as<int>(), carry.as<long long>(), d_carry0, g.stream);
     g.launches += 2;
     d_carry = carry.as<long long>();
   }
   int64_t cap = initial_cap(job);
   for (int attempt = 0; attempt < 3; ++attempt) {
-    void *spans = nullptr;
-    if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &spans))) return rc;
+    PoolBlock b_spans;
+    if ((rc = dev_alloc(sizeof(int64_t) * 2 * cap, &b_spans.p))) return rc;
+    void *spans = b_spans.p;
     CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
@@ -439,11 +477,10 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
-    if ((rc = read_scalars(0, 1))) { dev_release(spans); return rc; }
+    if ((rc = read_scalars(0, 1))) return rc;
     const int64_t total = (int64_t)g.h_scalars[0];
     note_density(job, total);
-    if (total <= cap) { out.spans = (int64_t *)spans; out.n = total; return MRX_OK; }
-    dev_release(spans);
+    if (total <= cap) { out.spans = (int64_t *)b_spans.take(); out.n = total; return MRX_OK; }
     cap = total;
   }
   return fail(MRX_E_CUDA, "match count did not stabilise");
@@ -677,6 +714,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   const Plan &pl = re->prog.findall;
   int rc;
   DevTmp d_text, desc;
+  DrainSideStreams drain;  // declared after the blocks: destroyed (= streams drained) before they are released
   if ((rc = d_text.get((size_t)n + 512))) return rc;
   uint8_t *dt = d_text.as<uint8_t>();
   mrx_text tview;
@@ -695,7 +733,9 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   ListJob job{re, &tview, &pl, re->d_findall, core_begin, core_end, global_offset};
   if (pl.dense.valid) job.dense = re->d_dense_findall;
   const int64_t origin = core_begin & ~15ll;
-  const int64_t tiles = n_tiles_for(origin, core_end - 1);
+  // dense plans record a match in the tile that holds its end: up to max_len - 1 bytes past the key window
+  const int64_t last_pos = pl.dense.valid ? std::min<int64_t>(n - 1, core_end - 1 + std::max(pl.dense.max_len - 1, 0)) : core_end - 1;
+  const int64_t tiles = n_tiles_for(origin, last_pos);
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
   if (tiles <= 0) {
     CUDA_TRY(cudaStreamSynchronize(g.s_in));
@@ -971,8 +1011,14 @@ int mrx_text_upload(const uint8_t *host, size_t n, mrx_text **out) {
   t->owned = true;
   t->core_begin = 0;
   t->core_end = n;
-  if (n) CUDA_TRY(cudaMemcpyAsync(d, host, n, cudaMemcpyHostToDevice, g.stream));
-  CUDA_TRY(cudaMemsetAsync((uint8_t *)d + n, 0, 512, g.stream));
+  cudaError_t e = n ? cudaMemcpyAsync(d, host, n, cudaMemcpyHostToDevice, g.stream) : cudaSuccess;
+  if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t *)d + n, 0, 512, g.stream);
+  if (e != cudaSuccess) {
+    cudaStreamSynchronize(g.stream);
+    dev_release(d);
+    delete t;
+    return fail(MRX_E_CUDA, std::string("text upload: ") + cudaGetErrorString(e));
+  }
   *out = t;
   return MRX_OK;
 }
@@ -1251,15 +1297,18 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   for (int k = 0; k < tpl.n_segs; ++k) repl_len += tpl.len[k];
   OwnedOut *own = new OwnedOut();
   out->_owner = own;
-  auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
+  OwnerGuard og{own, &out->_owner};
+  auto bail = [&](int code) { return code; };  // the guard releases the owner
   if (n == 0) {  // matcher.mojo:1697-1698
     out->n = 0;
     out->bytes = nullptr;
+    og.commit();
     return MRX_OK;
   }
   if ((rc = ensure_uploaded(re))) return bail(rc);
   DevSpans ms;
-  if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  ProfOuter prof;
+  prof.arm();
   // the assembly works in buffer coordinates: a shard's global offset (mrx_text_set_window) applies to the
   // spans findall reports, never to the match list sub / split are built from
   mrx_text local = *t;
@@ -1269,17 +1318,17 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
     // `.*`: the replace loop (matcher.mojo:1824-1847) calls match_next(text, pos) until it fails: (0, n), then
     // the empty match (n, n) at the end of the text (matcher.mojo:762-766) -- two replacements, not the one
     // span match_all reports
-    void *sp = nullptr;
-    if ((rc = dev_alloc(32, &sp))) return bail(rc);
+    PoolBlock sp;
+    if ((rc = dev_alloc(32, &sp.p))) return bail(rc);
     const int64_t h[4] = {0, n, n, n};
-    CUDA_TRY(cudaMemcpyAsync(sp, h, 32, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(sp.p, h, 32, cudaMemcpyHostToDevice, g.stream));
     CUDA_TRY(cudaStreamSynchronize(g.stream));
-    ms.spans = (int64_t *)sp;
+    ms.spans = (int64_t *)sp.take();
     ms.n = 2;
     rc = MRX_OK;
   } else
   rc = match_list(re, t, p.search, re->d_search, ms);
-  g.prof_outer = false;
+  prof.disarm();
   if (rc) return bail(rc);
   int64_t M = ms.n;
   if (count > 0 && M > count) M = count;
@@ -1327,6 +1376,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   if (location == MRX_OUT_DEVICE) {
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     out->bytes = (uint8_t *)d_out;
+    og.commit();
     return MRX_OK;
   }
   void *h = nullptr;
@@ -1337,6 +1387,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   dev_release(d_out);
   own->dev[0] = nullptr;
   out->bytes = (uint8_t *)h;
+  og.commit();
   return MRX_OK;
 }
 
@@ -1351,12 +1402,13 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "split on a windowed text: assemble per shard on whole buffers");
   if ((rc = ensure_uploaded(re))) return rc;
   DevSpans ms;
-  if (g.profiling) { g.prof_outer = true; cudaEventRecord(g.ev0, g.stream); }
+  ProfOuter prof;
+  prof.arm();
   mrx_text local = *t;  // buffer coordinates for the assembly (see mrx_sub)
   local.global_offset = 0;
   t = &local;
   rc = match_list(re, t, re->prog.findall, re->d_findall, ms);
-  g.prof_outer = false;
+  prof.disarm();
   if (rc) return rc;
   struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
   int64_t M = ms.n;
@@ -1364,7 +1416,8 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   else if (maxsplit > 0 && M > maxsplit) M = maxsplit;
   OwnedOut *own = new OwnedOut();
   out->_owner = own;
-  auto bail = [&](int code) { release_owner(own); out->_owner = nullptr; return code; };
+  OwnerGuard og{own, &out->_owner};
+  auto bail = [&](int code) { return code; };  // the guard releases the owner
   DevTmp d_desc, d_bad, d_tseg;
   const int64_t seg_tiles = (M + 1 + kSegTile - 1) / kSegTile;
   void *d_offs = nullptr;
@@ -1408,6 +1461,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     out->bytes = (uint8_t *)d_bytes;
     out->offsets = (int64_t *)d_offs;
+    og.commit();
     return MRX_OK;
   }
   void *hb = nullptr, *ho = nullptr;
@@ -1422,6 +1476,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   dev_release(d_offs); own->dev[1] = nullptr;
   out->bytes = (uint8_t *)hb;
   out->offsets = (int64_t *)ho;
+  og.commit();
   return MRX_OK;
 }
 
@@ -1667,6 +1722,7 @@ extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host,
   }
   const size_t k = first.size() - 1;
   DevTmp d_text, d_out, d_offs;
+  DrainSideStreams drain;
   if ((rc = d_text.get(n + 512))) return rc;
   if ((rc = d_out.get(sizeof(int64_t) * 2 * n_docs))) return rc;
   if (doc_offsets && (rc = d_offs.get(sizeof(int64_t) * (n_docs + k + 1)))) return rc;
@@ -1723,6 +1779,7 @@ extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t r
   }
   if ((rc = ensure_uploaded(re))) return rc;
   ChunkedUpload up;
+  DrainSideStreams drain;  // destroyed before `up`: the side streams are idle when its buffer goes back to the pool
   if ((rc = up.start(host, cuts))) return rc;
   const size_t k = cuts.size() - 1;
   std::vector<mrx_bytes> parts(k);
@@ -1773,6 +1830,7 @@ extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t
   }
   if ((rc = ensure_uploaded(re))) return rc;
   ChunkedUpload up;
+  DrainSideStreams drain;
   if ((rc = up.start(host, cuts))) return rc;
   const size_t k = cuts.size() - 1;
   std::vector<mrx_pieces> parts(k);

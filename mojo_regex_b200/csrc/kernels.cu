@@ -1341,7 +1341,8 @@ __global__ void k_tile_trailing(const uint8_t *text, int64_t n, int64_t tile_ori
 // carry[t] = length of the class run that ends exactly at the start of tile t.  Segmented scan over
 // (all, trail) pairs with  (a1,l1) o (a2,l2) = (a1 & a2, a2 ? l1 + l2 : l2):  one block of 1024 threads,
 // every thread owns a contiguous slice of tiles (serial), slices are combined by a block scan.
-__global__ void __launch_bounds__(1024) k_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry) {
+__global__ void __launch_bounds__(1024) k_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry,
+                                                     const long long *carry0) {
   __shared__ long long s_len[1024];
   __shared__ int s_all[1024];
   const int tid = threadIdx.x;
@@ -1371,11 +1372,34 @@ __global__ void __launch_bounds__(1024) k_carry_scan(int n_tiles, const long lon
     s_all[tid] = a2;
     __syncthreads();
   }
-  long long c = tid > 0 ? s_len[tid - 1] : 0;  // run length entering this thread's slice
+  // run length entering this thread's slice; the run that ends right before the first tile (carry0, a windowed
+  // text) continues into it as long as every tile so far is all in class
+  long long c = tid > 0 ? s_len[tid - 1] : 0;
+  if (carry0 && (tid == 0 || s_all[tid - 1])) c += *carry0;
   for (int t = t0; t < t1; ++t) {
     carry[t] = c;
     c = all[t] ? c + trail[t] : trail[t];
   }
+}
+
+// length of the class run that ends right before `origin` (UNIFORM_RUN on a windowed text: the distance of the
+// first tile's first byte from its run start).  One block walks backwards, kThreads bytes per round.
+__global__ void __launch_bounds__(kThreads) k_back_run(const uint8_t *text, int64_t origin, const DevProg *prog, long long *out) {
+  __shared__ int s_first;
+  long long len = 0;
+  for (int64_t hi = origin; hi > 0; hi -= kThreads) {
+    if (threadIdx.x == 0) s_first = kThreads;
+    __syncthreads();
+    const int64_t q = hi - 1 - threadIdx.x;
+    const bool in = q >= 0 && prog->cand[text[q]];
+    if (!in) atomicMin(&s_first, (int)threadIdx.x);
+    __syncthreads();
+    const int first = s_first;
+    __syncthreads();
+    len += first;
+    if (first < kThreads) break;
+  }
+  if (threadIdx.x == 0) *out = len;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1954,8 +1978,12 @@ void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_
   k_tile_trailing<<<(n_tiles + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
       text, n, origin, n_tiles, prog, trail, all);
 }
-void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st) {
-  k_carry_scan<<<1, 1024, 0, st>>>(n_tiles, trail, all, carry);
+void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, const long long *carry0,
+                       cudaStream_t st) {
+  k_carry_scan<<<1, 1024, 0, st>>>(n_tiles, trail, all, carry, carry0);
+}
+void launch_back_run(const uint8_t *text, int64_t origin, const DevProg *prog, long long *out, cudaStream_t st) {
+  k_back_run<<<1, kThreads, 0, st>>>(text, origin, prog, out);
 }
 void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaStream_t st) {
   if (p.n_docs <= 0) return;

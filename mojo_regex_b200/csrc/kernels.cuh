@@ -146,7 +146,9 @@ void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st);
-void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, cudaStream_t st);
+void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, const long long *carry0,
+                       cudaStream_t st);
+void launch_back_run(const uint8_t *text, int64_t origin, const DevProg *prog, long long *out, cudaStream_t st);
 void launch_attempt_one(const ScanParams &p, int64_t pos, int64_t *out, cudaStream_t st);
 void launch_batch_trivial(const ScanParams &p, int wildcard, int64_t *out, cudaStream_t st);
 void launch_batch_finalize(const unsigned long long *doc_best, int64_t n_docs, const int64_t *doc_offsets,

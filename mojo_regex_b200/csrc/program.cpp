@@ -643,6 +643,13 @@ bool load_program(const uint8_t *blob, size_t n, Program &p, std::string &err) {
   std::memcpy(p.fixed_offsets, h.fixed_offsets, sizeof p.fixed_offsets);
   std::memcpy(p.fixed_widths, h.fixed_widths, sizeof p.fixed_widths);
   if (p.fixed_num_groups < 0 || p.fixed_num_groups > 9) { err = "bad fixed-sub group count"; return false; }
+  if (p.fixed_total_width >= 0) {  // group slices index the match: every one must lie inside it (k_assemble reads them)
+    if (p.fixed_total_width > 255) { err = "fixed-sub match width above 255"; return false; }
+    for (int gi = 0; gi <= p.fixed_num_groups; ++gi) {
+      const int64_t o = p.fixed_offsets[gi], w = p.fixed_widths[gi];
+      if (o < 0 || w < 0 || o + w > p.fixed_total_width) { err = "fixed-sub group slice outside the match"; return false; }
+    }
+  }
   const uint8_t *q = blob + sizeof h;
   std::memcpy(p.byte_class.data(), q, 256); q += 256;
   std::memcpy(p.lookup.data(), q, 256); q += 256;

@@ -340,14 +340,21 @@ def findall_record(spans, shard: Shard) -> List[int]:
     return [n, int(spans[0][0]), int(spans[0][1]), int(spans[-1][0]), int(spans[-1][1]), cb, ce]
 
 
-def finish_findall(spans, records: List[List[int]], rank: int, class_runs: bool):
+def finish_findall(spans, records: List[List[int]], rank: int, class_runs: bool, direct: bool = True):
     """Turn a rank's local span list into its slice of the global result.
+
+    Per-shard key-window results compose into the whole-text result only when no match decision crosses a
+    shard edge: `direct` plans (mrx_info.findall_direct: potential matches provably never overlap) and the
+    stitched CLASS_RUNS case.  Greedy-restart plans are refused here rather than silently mis-sharded.
 
     Returns (spans_for_this_rank, global_index_of_first_span, total_matches).  For class-run patterns
     runs were clipped at the shard edges and are stitched here; for every other mode shards already
     report exactly the matches whose key lies in their core, so only offsets are needed."""
     import numpy as np
 
+    if not (class_runs or direct):
+        raise ValueError("sharded findall needs a direct plan (mrx_info.findall_direct) or CLASS_RUNS: a greedy "
+                         "restart chain cannot be cut at a shard boundary")
     spans = np.asarray(spans, dtype=np.int64).reshape(-1, 2)
     if class_runs:
         counts, new_last, drop_first = stitch_class_runs(records)

@@ -159,6 +159,38 @@ def test_blob_roundtrip_and_dfa_pack():
         mr.CompiledRegex(blob=bytes(bad))
 
 
+@pytest.mark.parametrize("pattern", [rb"(\d{3})(\d{3})(\d{4})", rb"(\d{3})-(\d{4})", rb"\s*,\s*", rb"(hello|world|foo)",
+                                     rb"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-z]{2,}", rb"^abc", rb"hello"])
+def test_serializer_entry_with_all_metadata_equals_the_compiled_blob(pattern):
+    """mrx_dfa_pack fed with everything mojo/cuda_backend.mojo passes (raw rows, flags, required byte, literals,
+    CompiledRegex._fixed_sub_*) gives byte for byte the blob mrx_compile builds -- in particular the fixed-width
+    sub metadata of BASELINE config 4 survives the Mojo route."""
+    from _pack import pack_through_the_serializer_entry
+
+    blob = pack_through_the_serializer_entry(pattern)
+    rx = mr.CompiledRegex(pattern)
+    assert blob == rx.blob()
+    a, b = mr.CompiledRegex(blob=blob).info(), rx.info()
+    for k, _ in mr.Info._fields_:
+        assert getattr(a, k) == getattr(b, k), k
+
+
+def test_blob_with_bad_fixed_width_metadata_is_rejected():
+    import struct
+
+    blob = bytearray(mr.CompiledRegex(rb"(\d{3})(\d{3})(\d{4})").blob())
+    off = 16 + 16 + 12          # magic..flags, n_states..required_byte, fixed_total_width / num_groups / concat
+    for value in (-5, 1 << 20):
+        bad = bytearray(blob)
+        struct.pack_into("<i", bad, off + 4 * 2, value)      # fixed_offsets[2]
+        with pytest.raises(ValueError):
+            mr.CompiledRegex(blob=bytes(bad))
+    bad = bytearray(blob)
+    struct.pack_into("<i", bad, off + 40 + 4 * 3, 9)          # fixed_widths[3]: offset 6 + 9 > 10
+    with pytest.raises(ValueError):
+        mr.CompiledRegex(blob=bytes(bad))
+
+
 def test_parse_errors_and_nfa_patterns_are_reported():
     for p in ["(abc", "abc)", "[abc", "a]", "a{x}"]:
         with pytest.raises(mr.RegexError):

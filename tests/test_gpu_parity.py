@@ -269,7 +269,7 @@ def test_sharded_findall_emulated_ranks(config, size):
     shards = [mrd.make_shard(config, size, r, world, "cuda") for r in range(world)]
     locals_ = [rx.match_all(sh.text).spans for sh in shards]
     records = [mrd.findall_record(locals_[r], shards[r]) for r in range(world)]
-    got = np.concatenate([mrd.finish_findall(locals_[r], records, r, class_runs)[0] for r in range(world)])
+    got = np.concatenate([mrd.finish_findall(locals_[r], records, r, class_runs, bool(rx.info().findall_direct))[0] for r in range(world)])
     whole = torch.cat([mrd._core(config, size, r, "cuda") for r in range(world)]).cpu().numpy()
     want = oracle.compile(pat).findall(whole)
     assert np.array_equal(got, want)
@@ -696,3 +696,96 @@ def test_random_patterns_all_ops_against_oracle(pattern):
     for n in (700, TILE + 3000):
         text = bytes(ord(rng.choice(alphabet)) for _ in range(n))
         _compare_all_ops(pattern, text)
+
+
+# ---- round-2 regressions (advisor findings) ---------------------------------------------------------------
+@pytest.mark.parametrize("pattern,lit", [(r"(hello|world|foo)", b"hello"), (r"hello", b"hello")])
+@pytest.mark.parametrize("edge", [0, 1, 2, 3, 4])
+def test_dense_window_ending_on_a_tile_boundary(pattern, lit, edge):
+    """A match that STARTS inside the key window but ENDS past the last tile the window touches must still be
+    reported (the dense kernel records a match in the tile that holds its end byte): core_end on, or within
+    max_len - 1 of, a tile boundary with a literal straddling it -- device path and pipelined host path."""
+    n = 40 * TILE + 777
+    text = corpora.make("c2", n)
+    lo = 16 * 3                        # origin = lo & ~15 = 48
+    cut = 48 + 9 * TILE                # a tile boundary of this window's tiling
+    hi = cut - edge                    # core_end = boundary - edge: the literal below starts inside, ends outside
+    text[cut - edge - 1:cut - edge - 1 + len(lit)] = torch.tensor(list(lit), dtype=torch.uint8)
+    rx = mr.compile_regex(pattern)
+    want = oracle.compile(pattern).findall(text.numpy())
+    sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)]
+    assert (sel[:, 1] > hi).any()      # the straddling literal belongs to this window
+    t = mr.Text(text.numpy())
+    t.set_window(lo, hi, 0)
+    assert np.array_equal(rx.match_all(t).spans, sel)
+    # host path (pipelined from 16 MiB on: use a larger buffer with the same edge geometry)
+    n2 = (17 << 20) + 333
+    big = corpora.make("c2", n2)
+    cut2 = 48 + 300 * TILE
+    hi2 = cut2 - edge
+    big[hi2 - 1:hi2 - 1 + len(lit)] = torch.tensor(list(lit), dtype=torch.uint8)
+    host = torch.empty(n2, dtype=torch.uint8, pin_memory=True)
+    host.copy_(big)
+    want2 = oracle.compile(pattern).findall(big.numpy())
+    sel2 = want2[(want2[:, 0] >= lo) & (want2[:, 0] < hi2)]
+    assert (sel2[:, 1] > hi2).any()
+    got2 = rx.match_all_host(host.data_ptr(), n2, lo, hi2, 0).spans
+    assert np.array_equal(got2, sel2)
+
+
+@pytest.mark.parametrize("pattern", [r"\d{10}", r"[a-z]{2,4}", r"(\d{3})(\d{3})(\d{4})"])
+@pytest.mark.parametrize("lo", [5, 16, 37, TILE - 3, TILE + 16, 2 * TILE + 7])
+def test_uniform_run_window_keeps_the_phase_of_a_straddling_run(pattern, lo):
+    """UNIFORM_RUN on a windowed text: a class run that straddles core_begin is chunked with the phase it has
+    in the whole buffer (the reference sees the whole text); the window only filters by match start."""
+    n = 4 * TILE + 100
+    text = corpora.make("c4", n).numpy().copy()
+    fill = ord("7") if "d" in pattern else ord("q")
+    # one long run across `lo`, starting 1..40 bytes before it, and one that swallows a whole tile before it
+    text[max(lo - 33, 0):lo + 57] = fill
+    if lo > TILE:
+        text[3:lo - 40] = fill
+        text[lo - 40] = ord(" ")
+    rx = mr.compile_regex(pattern)
+    assert rx.info().findall_mode == 8
+    want = oracle.compile(pattern).findall(text)
+    hi = n - 11
+    sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)]
+    t = mr.Text(text)
+    t.set_window(lo, hi, 123)
+    assert np.array_equal(rx.match_all(t).spans, sel + 123)
+
+
+def test_from_tensor_orders_after_the_producer_stream():
+    """Text.from_tensor on a tensor that torch kernels are still writing: the scan must see the final bytes."""
+    rx = mr.compile_regex(r"(hello|world|foo)")
+    base = corpora.make("c2", 8 << 20).cuda()
+    want = oracle.compile(r"(hello|world|foo)").findall(base.cpu().numpy())
+    for _ in range(5):
+        junk = torch.zeros_like(base)
+        buf = torch.cat([junk[:0], base])          # produced on torch's stream right before the scan
+        t = mr.Text.from_tensor(buf)
+        ds = rx.match_all_device(t)
+        assert ds.n == len(want)
+        ds.close()
+
+
+def test_sub_through_a_packed_automaton_with_fixed_width_metadata():
+    """The Mojo serializer's route (mrx_dfa_pack -> mrx_regex_load) for BASELINE config 4: raw DFAEngine rows
+    plus CompiledRegex._fixed_sub_* (matcher.mojo:1002-1035) -> sub with group references."""
+    pat = rb"(\d{3})(\d{3})(\d{4})"
+    from _pack import pack_through_the_serializer_entry
+
+    blob = pack_through_the_serializer_entry(pat)
+    assert blob == mr.CompiledRegex(pat).blob()
+    rx = mr.CompiledRegex(blob=blob)
+    i = rx.info()
+    assert (i.fixed_sub_total_width, i.fixed_sub_num_groups, i.fixed_sub_concat) == (10, 3, 1)
+    eng = oracle.compile(pat)
+    text = corpora.make("c4", 1 << 18).numpy()
+    assert rx.sub(r"\1-\2-\3", text) == eng.sub(rb"\1-\2-\3", text)
+    assert rx.sub(r"\1-\2-\3", b"6502530000 and 4155551234", 1) == b"650-253-0000 and 4155551234"
+    # without the metadata (what the round-1 stub packed) group references are refused, loudly
+    rx_bare = mr.CompiledRegex(blob=mr.CompiledRegex(rb"\d{10}").blob())   # same automaton shape, no groups
+    with pytest.raises(mr.UnsupportedPattern):
+        rx_bare.sub(r"\1-\2-\3", b"6502530000")
