@@ -149,6 +149,7 @@ struct mrx_regex {
   Program prog;
   DevProg *d_findall = nullptr, *d_search = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
+  sand::Table *d_sand_findall = nullptr;                          // Shift-And table of the findall plan (k_sand)
   uint8_t *d_rev_search = nullptr;                                // RevTable::tbl of the search plan
   bool search_dominated = false;
   // matches per key byte seen by the last list job of each plan (findall, search): sizes the span
@@ -287,6 +288,11 @@ int ensure_uploaded(mrx_regex *re) {
   if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
   if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
   if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
+  if (re->prog.findall.sand_valid && !re->d_sand_findall) {
+    void *d = nullptr;
+    if (int rc = upload_blob(&re->prog.findall.sand, sizeof(sand::Table), &d)) return rc;
+    re->d_sand_findall = static_cast<sand::Table *>(d);
+  }
   if (re->prog.search.rev.valid && !re->d_rev_search) {
     const RevTable &rt = re->prog.search.rev;
     std::vector<uint16_t> tb(rt.rev);
@@ -345,7 +351,11 @@ struct ListJob {
   int64_t key_lo, key_hi;  // buffer coordinates
   int64_t rebase;
   const uint8_t *dense = nullptr;  // DenseHdr + table when the plan has a dense automaton
+  const sand::Table *sand = nullptr;  // ... and its Shift-And form when the set fits (findall plan only)
 };
+
+// MRX_NO_SAND=1: literal sets go through k_dense even when k_sand applies (the tests hold the two equal)
+bool sand_enabled() { return getenv("MRX_NO_SAND") == nullptr; }
 
 // Span-buffer capacity for a list job: a guess of one match per 8 bytes (at most 2^26 spans) the first
 // time, then 1/8 above the density the same plan saw last time.  A scan that overflows its buffer still
@@ -365,9 +375,9 @@ void note_density(const ListJob &job, int64_t total) {
   if (keys > 0) density_slot(job) = (double)total / (double)keys;
 }
 
-int64_t n_tiles_for(int64_t origin, int64_t hi_inclusive) {
+int64_t n_tiles_for(int64_t origin, int64_t hi_inclusive, int64_t tile_bytes = kTile) {
   if (hi_inclusive < origin) return 0;
-  return (hi_inclusive - origin) / kTile + 1;
+  return (hi_inclusive - origin) / tile_bytes + 1;
 }
 
 int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **keys_out) {
@@ -379,7 +389,8 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
   // the dense kernel records a match in the tile that holds its END byte: a match that starts inside the key
   // window may end up to max_len - 1 bytes past it (its start is filtered against the window by the kernel)
   if (job.dense && !want_keys) last_pos = std::min<int64_t>(n - 1, job.key_hi - 1 + std::max(pl.dense.max_len - 1, 0));
-  const int64_t tiles = n_tiles_for(origin, last_pos);
+  const bool use_sand = job.sand && job.dense && !want_keys;
+  const int64_t tiles = n_tiles_for(origin, last_pos, use_sand ? kSandTileBytes : kTile);
   out.n = 0;
   if (tiles <= 0) return MRX_OK;
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
@@ -402,7 +413,14 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
-    if (job.dense && !want_keys) {
+    if (use_sand) {
+      SandParams sp{};
+      sp.text = job.t->d; sp.n = n; sp.tile_origin = origin; sp.key_lo = job.key_lo; sp.key_hi = job.key_hi;
+      sp.table = job.sand; sp.n_tiles = (int)tiles; sp.tile_base = 0; sp.base0 = 0; sp.spans = (int64_t *)spans; sp.cap = cap;
+      sp.rebase = job.rebase; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket; sp.total = g.scalars;
+      if (const char *dbg = getenv("MRX_SAND_DEBUG")) sp.debug = atoi(dbg);
+      launch_sand(sp, pl.sand.k, pl.sand.tail != 0, (int)tiles, g.stream);
+    } else if (job.dense && !want_keys) {
       DenseParams dp{};
       dp.text = job.t->d; dp.n = n; dp.tile_origin = origin; dp.key_lo = job.key_lo; dp.key_hi = job.key_hi;
       dp.dense = job.dense; dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
@@ -527,6 +545,7 @@ int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const Dev
   const int64_t n = (int64_t)t->n;
   ListJob job{re, t, &pl, dprog, (int64_t)t->core_begin, (int64_t)t->core_end, t->global_offset};
   if (pl.dense.valid) job.dense = (&pl == &re->prog.findall) ? re->d_dense_findall : re->d_dense_search;
+  if (&pl == &re->prog.findall && pl.sand_valid && sand_enabled()) job.sand = re->d_sand_findall;
   switch (pl.mode) {
     case MRX_MODE_WILDCARD_ANY: {  // matcher.mojo:809-813
       void *p = nullptr;
@@ -732,10 +751,12 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   }
   ListJob job{re, &tview, &pl, re->d_findall, core_begin, core_end, global_offset};
   if (pl.dense.valid) job.dense = re->d_dense_findall;
+  if (pl.sand_valid && sand_enabled()) job.sand = re->d_sand_findall;
   const int64_t origin = core_begin & ~15ll;
   // dense plans record a match in the tile that holds its end: up to max_len - 1 bytes past the key window
   const int64_t last_pos = pl.dense.valid ? std::min<int64_t>(n - 1, core_end - 1 + std::max(pl.dense.max_len - 1, 0)) : core_end - 1;
-  const int64_t tiles = n_tiles_for(origin, last_pos);
+  const int64_t tile_bytes = job.sand ? kSandTileBytes : kTile;
+  const int64_t tiles = n_tiles_for(origin, last_pos, tile_bytes);
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
   if (tiles <= 0) {
     CUDA_TRY(cudaStreamSynchronize(g.s_in));
@@ -756,12 +777,18 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
   for (int64_t c = 0; c < n_chunks && !overflow; ++c) {
     const int64_t vis = std::min(n, (c + 1) * chunk);
     const int64_t t1 = (c == n_chunks - 1) ? tiles
-                                           : std::min(tiles, std::max<int64_t>(t0, (vis - kLookAhead - origin) / kTile));
+                                           : std::min(tiles, std::max<int64_t>(t0, (vis - kLookAhead - origin) / tile_bytes));
     if (t1 <= t0) continue;
     CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event((size_t)c), 0));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
     if (g.profiling && c == 0) cudaEventRecord(g.ev0, g.stream);
-    if (pl.dense.valid) {
+    if (job.sand) {
+      SandParams sp{};
+      sp.text = dt; sp.n = n; sp.tile_origin = origin; sp.key_lo = core_begin; sp.key_hi = core_end; sp.table = job.sand;
+      sp.n_tiles = (int)t1; sp.tile_base = (int)t0; sp.base0 = (unsigned long long)total; sp.spans = (int64_t *)d_spans;
+      sp.cap = cap; sp.rebase = global_offset; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket; sp.total = g.scalars;
+      launch_sand(sp, pl.sand.k, pl.sand.tail != 0, (int)(t1 - t0), g.stream);
+    } else if (pl.dense.valid) {
       DenseParams dp{};
       dp.text = dt; dp.n = n; dp.tile_origin = origin; dp.key_lo = core_begin; dp.key_hi = core_end; dp.dense = job.dense;
       dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
@@ -993,6 +1020,7 @@ void mrx_regex_free(mrx_regex *re) {
   if (re->d_search) cudaFree(re->d_search);
   if (re->d_dense_findall) cudaFree(re->d_dense_findall);
   if (re->d_dense_search) cudaFree(re->d_dense_search);
+  if (re->d_sand_findall) cudaFree(re->d_sand_findall);
   if (re->d_rev_search) cudaFree(re->d_rev_search);
   delete re;
 }

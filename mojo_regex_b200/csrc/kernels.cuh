@@ -91,6 +91,28 @@ struct DenseParams {
   unsigned long long *best;  // OUT_FIRST: min over (start << 8 | len)
 };
 
+// Shift-And literal-set scan (k_sand, sand.hpp); its tiles are kSandTileBytes long (256 threads x 144 bytes)
+namespace sand { struct Table; }
+constexpr int kSandTileBytes = 36864;
+struct SandParams {
+  const uint8_t *text;
+  int64_t n;
+  int64_t tile_origin;
+  int64_t key_lo, key_hi;      // match starts reported: [key_lo, key_hi)
+  const sand::Table *table;    // in HBM
+  int32_t n_tiles;
+  int32_t tile_base;           // this launch scans tiles [tile_base, n_tiles)
+  unsigned long long base0;    // matches before tile_base (the total of the launches that came before)
+  int64_t *spans;
+  int64_t cap;
+  int64_t rebase;
+  unsigned long long *desc;    // one word per tile, zeroed: (1 << 62) | aggregate once the tile is counted
+  unsigned int *ticket;        // zeroed: tiles are handed out in order, tile = tile_base + ticket
+  unsigned long long *total;
+  int32_t debug;               // measurement only (MRX_SAND_DEBUG): 1 = no matches kept, 2 = no walk (results are
+                               // invalid), 4 = static round-robin tiles instead of tickets
+};
+
 // Per-document search (k_lines): one thread per document.
 struct LinesParams {
   const uint8_t *text;
@@ -144,6 +166,7 @@ void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
 void launch_lines(LinesParams p, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
+void launch_sand(const SandParams &p, int k, bool tail, int grid, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st);
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, const long long *carry0,

@@ -2,6 +2,7 @@
 #include "program.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <queue>
@@ -373,6 +374,7 @@ bool build_dense(const std::vector<std::string> &lits, DenseTable &dt) {
 
 void try_dense(const Program &p, Plan &pl) {
   pl.dense = DenseTable();
+  pl.sand_valid = false;
   if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) return;
   std::vector<std::string> lits;
   if (pl.mode == MRX_MODE_LITERAL || pl.mode == MRX_MODE_EXACT_LITERAL) {
@@ -384,7 +386,15 @@ void try_dense(const Program &p, Plan &pl) {
     return;
   }
   DenseTable dt;
-  if (build_dense(lits, dt) && dt.next.size() * 2 <= 24576) pl.dense = dt;
+  if (build_dense(lits, dt) && dt.next.size() * 2 <= 24576) {
+    pl.dense = dt;
+    // the same set as a bit-parallel Shift-And automaton when it fits 32 state bits (distinct literals only:
+    // build_dense has already refused prefixes and nesting)
+    std::vector<std::string> uniq;
+    for (const std::string &w : lits)
+      if (std::find(uniq.begin(), uniq.end(), w) == uniq.end()) uniq.push_back(w);
+    pl.sand_valid = sand::build(uniq, pl.sand, getenv("MRX_SAND_NO_TAIL") == nullptr);  // (the tests compile both forms)
+  }
 }
 
 void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {

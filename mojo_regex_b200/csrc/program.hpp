@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "frontend.hpp"
+#include "sand.hpp"
 
 namespace mrx {
 
@@ -83,6 +84,8 @@ struct RevTable {
 struct Plan {
   int32_t mode = -1;  // MRX_MODE_*
   DenseTable dense;
+  bool sand_valid = false;  // the literal set of `dense` also fits the Shift-And scan (k_sand): findall uses it
+  sand::Table sand;
   RevTable rev;
   bool direct = false;        // potential matches provably never overlap: emit them as final
   bool unsupported = false;   // plan cannot be executed faithfully

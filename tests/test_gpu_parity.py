@@ -789,3 +789,68 @@ def test_sub_through_a_packed_automaton_with_fixed_width_metadata():
     rx_bare = mr.CompiledRegex(blob=mr.CompiledRegex(rb"\d{10}").blob())   # same automaton shape, no groups
     with pytest.raises(mr.UnsupportedPattern):
         rx_bare.sub(r"\1-\2-\3", b"6502530000")
+
+
+# ---- k_sand (Shift-And literal-set scan) against the oracle and against k_dense ----------------------------------
+SAND_CASES = [
+    (r"(hello|world|foo)", "c2"), (r"hello", "c2"), (r"(foo|he)", "c2"), (r"a", "c2"), (r"(ab|cd|ef|gh)", "c2"),
+    (r"ing ", "c2"), (r"(hell|worl|fo)", "c2"), (r"aa", "c2"),
+]
+
+
+def _fresh_regex(pattern, tail, monkeypatch):
+    """Compiled outside the pattern cache: MRX_SAND_NO_TAIL is read when the plan is made (tail = the form of the
+    Shift-And automaton whose hit bits are read once per text word, sand.hpp)."""
+    if tail:
+        monkeypatch.delenv("MRX_SAND_NO_TAIL", raising=False)
+    else:
+        monkeypatch.setenv("MRX_SAND_NO_TAIL", "1")
+    return mr.CompiledRegex(pattern)
+
+
+@pytest.mark.parametrize("pattern,config", SAND_CASES)
+@pytest.mark.parametrize("tail", [True, False])
+def test_sand_kernel_equals_oracle_and_dense_kernel(pattern, config, tail, monkeypatch):
+    rx = _fresh_regex(pattern, tail, monkeypatch)
+    assert rx.info().findall_dense
+    orx = oracle.compile(pattern)
+    for n in (0, 1, 15, 143, 144, 145, TILE - 1, TILE, TILE + 1, 3 * TILE + 77, 2_000_003):
+        text = corpora.make(config, max(n, 1))[:n].numpy()
+        want = orx.findall(text)
+        got = rx.match_all(mr.Text(text)).spans
+        assert np.array_equal(got, want), (pattern, n, tail)
+        monkeypatch.setenv("MRX_NO_SAND", "1")
+        dense = rx.match_all(mr.Text(text)).spans
+        monkeypatch.delenv("MRX_NO_SAND")
+        assert np.array_equal(dense, want), (pattern, n, "k_dense")
+
+
+@pytest.mark.parametrize("tail", [True, False])
+def test_sand_kernel_windows_unaligned_and_dense_hits(tail, monkeypatch):
+    rx = _fresh_regex(r"(hello|world|foo)", tail, monkeypatch)
+    orx = oracle.compile(r"(hello|world|foo)")
+    text = corpora.make("c2", 5 * TILE + 1234)
+    # literals across every tile boundary of the origin-0 tiling and of the window tilings below, hit-dense stretches
+    # (one hit every 3 bytes: more hits per chunk than any private list held), a literal at the very end
+    for b in (TILE, 2 * TILE, 3 * TILE, 48 + TILE, 16 + 2 * TILE):
+        for d in (-4, -2, -1, 0):
+            text[b + d:b + d + 5] = torch.tensor(list(b"hello"), dtype=torch.uint8)
+    text[1000:4000] = torch.tensor(list(b"foo" * 1000), dtype=torch.uint8)
+    text[-3:] = torch.tensor(list(b"foo"), dtype=torch.uint8)
+    host = text.numpy()
+    want = orx.findall(host)
+    assert np.array_equal(rx.match_all(mr.Text(host)).spans, want)
+    for lo, hi in [(5, len(host)), (16, TILE + 16), (48, 48 + TILE), (TILE - 2, TILE + 3), (1001, 3999), (0, 0), (7, 7)]:
+        t = mr.Text(host)
+        t.set_window(lo, hi, 10**12)
+        sel = want[(want[:, 0] >= lo) & (want[:, 0] < hi)] + 10**12
+        assert np.array_equal(rx.match_all(t).spans, sel), (lo, hi)
+    # unaligned device pointer: staging without TMA
+    dev = text.cuda()
+    for off in (1, 5, 17):
+        got = rx.match_all(mr.Text.from_tensor(dev[off:])).spans
+        assert np.array_equal(got, orx.findall(host[off:])), off
+    # text with bytes >= 0x80 and NUL bytes (a literal containing NUL would see stale buffer bytes past the text)
+    raw = np.frombuffer(bytes(random.Random(3).choices(range(256), k=200_000)), dtype=np.uint8).copy()
+    raw[5000:5005] = np.frombuffer(b"hello", dtype=np.uint8)
+    assert np.array_equal(rx.match_all(mr.Text(raw)).spans, orx.findall(raw))
