@@ -150,6 +150,7 @@ struct mrx_regex {
   DevProg *d_findall = nullptr, *d_search = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
   sand::Table *d_sand_findall = nullptr;                          // Shift-And table of the findall plan (k_sand)
+  sepb::Table *d_sep_findall = nullptr;                           // class table of the fused split (k_split)
   uint8_t *d_rev_search = nullptr;                                // RevTable::tbl of the search plan
   bool search_dominated = false;
   // matches per key byte seen by the last list job of each plan (findall, search): sizes the span
@@ -288,6 +289,11 @@ int ensure_uploaded(mrx_regex *re) {
   if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
   if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
   if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
+  if (re->prog.findall.sep_valid && !re->d_sep_findall) {
+    void *d = nullptr;
+    if (int rc = upload_blob(&re->prog.findall.sep, sizeof(sepb::Table), &d)) return rc;
+    re->d_sep_findall = static_cast<sepb::Table *>(d);
+  }
   if (re->prog.findall.sand_valid && !re->d_sand_findall) {
     void *d = nullptr;
     if (int rc = upload_blob(&re->prog.findall.sand, sizeof(sand::Table), &d)) return rc;
@@ -1021,6 +1027,7 @@ void mrx_regex_free(mrx_regex *re) {
   if (re->d_dense_findall) cudaFree(re->d_dense_findall);
   if (re->d_dense_search) cudaFree(re->d_dense_search);
   if (re->d_sand_findall) cudaFree(re->d_sand_findall);
+  if (re->d_sep_findall) cudaFree(re->d_sep_findall);
   if (re->d_rev_search) cudaFree(re->d_rev_search);
   delete re;
 }
@@ -1419,6 +1426,89 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   return MRX_OK;
 }
 
+// split() for X* c Y* patterns in one pass (k_split): no match list.  *done = false when the text holds a run the
+// kernel's windows cannot measure (the caller then takes the general path).
+static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_pieces *out, bool *done) {
+  *done = false;
+  const Plan &pl = re->prog.findall;
+  const int64_t n = (int64_t)t->n;
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
+  int rc;
+  DevTmp desc;
+  if ((rc = desc.get(sizeof(unsigned long long) * tiles))) return rc;
+  OwnedOut *own = new OwnedOut();
+  out->_owner = own;
+  OwnerGuard og{own, &out->_owner};
+  void *d_bytes = nullptr;
+  if ((rc = dev_alloc((size_t)n + 32, &d_bytes))) return rc;
+  own->dev[0] = d_bytes;
+  const double dens = re->density[0];
+  int64_t cap = dens > 0.0 ? (int64_t)(dens * 1.125 * (double)n) + 4096 : std::min<int64_t>(n / 6 + 1024, 1ll << 27);
+  ProfOuter prof;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    void *d_offs = nullptr;
+    if ((rc = dev_alloc(sizeof(int64_t) * (size_t)(cap + 2), &d_offs))) return rc;
+    own->dev[1] = d_offs;
+    CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+    CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 32, g.stream));
+    CUDA_TRY(cudaMemsetAsync(d_offs, 0, 8, g.stream));
+    SplitParams sp{};
+    sp.text = t->d; sp.n = n; sp.table = re->d_sep_findall; sp.n_tiles = (int)tiles; sp.out = (uint8_t *)d_bytes;
+    sp.offs = (int64_t *)d_offs; sp.offs_cap = cap; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket;
+    sp.totals = g.scalars; sp.flags = reinterpret_cast<int *>(g.scalars + 2);
+    prof.arm();
+    launch_split(sp, g.stream);
+    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    prof.disarm();
+    ++g.launches;
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = read_scalars(0, 3))) return rc;
+    const int64_t total = (int64_t)g.h_scalars[0], M = (int64_t)g.h_scalars[1];
+    const int flags = (int)(g.h_scalars[2] & 0xffffffffu);
+    if (flags & 1) return MRX_OK;  // a long run: general path (*done stays false; the guard releases the buffers)
+    if (flags & 2)
+      return fail(MRX_E_UNDEFINED, "separator spans overlap (text[prev_end:start] with prev_end > start): the reference's "
+                                   "behaviour is undefined here (matcher.mojo:1389)");
+    re->density[0] = (double)M / (double)n;
+    if (M > cap) {  // the offsets array was too small: once more with the exact size
+      dev_release(d_offs);
+      own->dev[1] = nullptr;
+      cap = M;
+      continue;
+    }
+    // offs[M + 1] = total (offs[0] = 0 is already there)
+    g.h_scalars[12] = (unsigned long long)total;
+    CUDA_TRY(cudaMemcpyAsync((int64_t *)d_offs + (M + 1), g.h_scalars + 12, 8, cudaMemcpyHostToDevice, g.stream));
+    out->n = (size_t)(M + 1);
+    out->location = location;
+    *done = true;
+    if (location == MRX_OUT_DEVICE) {
+      CUDA_TRY(cudaStreamSynchronize(g.stream));
+      out->bytes = (uint8_t *)d_bytes;
+      out->offsets = (int64_t *)d_offs;
+      og.commit();
+      return MRX_OK;
+    }
+    void *hb = nullptr, *ho = nullptr;
+    if ((rc = host_alloc((size_t)total + 1, &hb))) return rc;
+    own->host[0] = hb;
+    if ((rc = host_alloc(sizeof(int64_t) * (M + 2), &ho))) return rc;
+    own->host[1] = ho;
+    if (total) CUDA_TRY(cudaMemcpyAsync(hb, d_bytes, (size_t)total, cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaMemcpyAsync(ho, d_offs, sizeof(int64_t) * (M + 2), cudaMemcpyDeviceToHost, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    dev_release(d_bytes); own->dev[0] = nullptr;
+    dev_release(d_offs); own->dev[1] = nullptr;
+    out->bytes = (uint8_t *)hb;
+    out->offsets = (int64_t *)ho;
+    og.commit();
+    return MRX_OK;
+  }
+  return fail(MRX_E_CUDA, "separator count did not stabilise");
+}
+
 int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int location, mrx_pieces *out) {
   int rc = require_device();
   if (rc) return rc;
@@ -1429,6 +1519,15 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   const int64_t n = (int64_t)t->n;
   if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "split on a windowed text: assemble per shard on whole buffers");
   if ((rc = ensure_uploaded(re))) return rc;
+  if (re->prog.findall.sep_valid && maxsplit == 0 && n > 0 && re->d_sep_findall && !getenv("MRX_NO_FUSED_SPLIT")) {
+    // X* c Y* (config 5): finder, compaction and piece offsets in one kernel; texts with runs the kernel's windows
+    // cannot measure fall through to the general path
+    bool done = false;
+    rc = split_fused(re, t, location, out, &done);
+    if (rc || done) return rc;
+    std::memset(out, 0, sizeof *out);
+    out->location = location;
+  }
   DevSpans ms;
   ProfOuter prof;
   prof.arm();

@@ -113,6 +113,22 @@ struct SandParams {
                                // invalid), 4 = static round-robin tiles instead of tickets
 };
 
+// Fused split for patterns of the shape X* c Y* (k_split, sepbits.hpp)
+namespace sepb { struct Table; }
+struct SplitParams {
+  const uint8_t *text;
+  int64_t n;
+  const sepb::Table *table;    // in HBM
+  int32_t n_tiles;             // ceil(n / kTile)
+  uint8_t *out;                // the kept bytes (at most n, + 16 slack)
+  int64_t *offs;               // offs[1 + k] = kept bytes before the k-th separator; offs[0] and the last entry: host
+  int64_t offs_cap;            // separators that can be recorded
+  unsigned long long *desc;    // one word per tile, zeroed: (1 << 62) | separators << 20 | kept bytes
+  unsigned int *ticket;        // zeroed
+  unsigned long long *totals;  // [0] kept bytes, [1] separators of the whole text
+  int *flags;                  // zeroed; bit 0: a run the window cannot measure, bit 1: overlapping separators
+};
+
 // Per-document search (k_lines): one thread per document.
 struct LinesParams {
   const uint8_t *text;
@@ -167,6 +183,7 @@ void launch_lines(LinesParams p, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_sand(const SandParams &p, int k, bool tail, int grid, cudaStream_t st);
+void launch_split(const SplitParams &p, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st);
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, const long long *carry0,

@@ -397,6 +397,63 @@ void try_dense(const Program &p, Plan &pl) {
   }
 }
 
+// Recognise, on the automaton the reference built, the shape
+//   S0 --X--> S1,  S0 --c--> S2;   S1 --X--> S1,  S1 --c--> S2;   S2(acc) --Y--> S3;   S3(acc) --Y--> S3
+// (dfa.mojo:699-807 for `X* c Y*`; S1 may coincide with S0, S3 with S2, X / Y may be empty), with
+// c the required byte of the required-byte findall (matcher.mojo:864-898), the back-scan set L (first-class lookup)
+// containing X and not c, and Y == X -- the preconditions of sepbits.hpp -- and fill the class table of k_split.
+bool detect_separator_shape(const Program &p, sepb::Table &out) {
+  const int c = p.required_byte, n = p.n_states, start = p.start_state;
+  if (n <= 0 || c < 0 || c > 255 || p.accepting[start] || !p.flag(BF_HAS_MATCHER)) return false;
+  if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) return false;
+  auto T = [&](int q, int b) { const int t = p.next(q, b); return t == kDead ? -1 : t; };
+  const int s2 = T(start, c);
+  if (s2 < 0 || !p.accepting[s2] || p.lookup[c]) return false;
+  bool X[256] = {false}, Y[256] = {false};
+  int s1 = -1;
+  for (int b = 0; b < 256; ++b) {
+    if (b == c) continue;
+    const int t = T(start, b);
+    if (t < 0) continue;
+    if (s1 >= 0 && t != s1) return false;
+    s1 = t;
+    X[b] = true;
+  }
+  if (s1 >= 0 && s1 != start) {
+    if (p.accepting[s1]) return false;
+    for (int b = 0; b < 256; ++b) {
+      const int t = T(s1, b);
+      if (b == c) { if (t != s2) return false; }
+      else if (X[b]) { if (t != s1) return false; }
+      else if (t >= 0) return false;
+    }
+  }
+  int s3 = -1;
+  for (int b = 0; b < 256; ++b) {
+    const int t = T(s2, b);
+    if (t < 0) continue;
+    if (b == c) return false;
+    if (s3 >= 0 && t != s3) return false;
+    s3 = t;
+    Y[b] = true;
+  }
+  if (s3 >= 0 && s3 != s2) {
+    if (!p.accepting[s3]) return false;
+    for (int b = 0; b < 256; ++b) {
+      const int t = T(s3, b);
+      if (Y[b]) { if (t != s3) return false; }
+      else if (t >= 0) return false;
+    }
+  }
+  out = sepb::Table();
+  for (int b = 0; b < 256; ++b) {
+    if (X[b] != Y[b]) return false;
+    if (X[b] && !p.lookup[b]) return false;
+    out.T[b] = (b == c ? 1u : 0u) | (p.lookup[b] ? 1u << 8 : 0u) | ((p.lookup[b] && !X[b]) ? 1u << 16 : 0u);
+  }
+  return true;
+}
+
 void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
   pl.shortcut = p.flag(BF_HAS_MATCHER) && p.n_states > 0 && (p.flag(BF_SCAN_ELIGIBLE) || p.start_accepting());
   if (first_class) {
@@ -572,6 +629,7 @@ void make_plans(Program &p) {
     fa.cand[p.required_byte] = 1;
     fa.direct = !fa.shortcut && !p.flag(BF_PURE_LITERAL) && !second_needle_possible(p, p.required_byte);
     choose_filter(fa);
+    fa.sep_valid = fa.direct && detect_separator_shape(p, fa.sep);
   } else if (p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR)) {
     fa.mode = MRX_MODE_ANCHORED;
     fa.direct = true;

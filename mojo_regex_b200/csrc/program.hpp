@@ -9,6 +9,7 @@
 
 #include "frontend.hpp"
 #include "sand.hpp"
+#include "sepbits.hpp"
 
 namespace mrx {
 
@@ -86,6 +87,8 @@ struct Plan {
   DenseTable dense;
   bool sand_valid = false;  // the literal set of `dense` also fits the Shift-And scan (k_sand): findall uses it
   sand::Table sand;
+  bool sep_valid = false;   // required-byte plan whose automaton has the shape X* c Y*: split runs fused (k_split)
+  sepb::Table sep;
   RevTable rev;
   bool direct = false;        // potential matches provably never overlap: emit them as final
   bool unsupported = false;   // plan cannot be executed faithfully

@@ -854,3 +854,110 @@ def test_sand_kernel_windows_unaligned_and_dense_hits(tail, monkeypatch):
     raw = np.frombuffer(bytes(random.Random(3).choices(range(256), k=200_000)), dtype=np.uint8).copy()
     raw[5000:5005] = np.frombuffer(b"hello", dtype=np.uint8)
     assert np.array_equal(rx.match_all(mr.Text(raw)).spans, orx.findall(raw))
+
+
+# ---- k_split (fused split for X* c Y* patterns) against the oracle and against the general path ------------------
+def _split_both_paths(rx, text, monkeypatch):
+    """-> (fused result, general-path result); each is (bytes, offsets list) or the exception class raised."""
+    res = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("MRX_NO_FUSED_SPLIT", raising=False)
+        else:
+            monkeypatch.setenv("MRX_NO_FUSED_SPLIT", "1")
+        try:
+            d, o = rx.split_raw(text)
+            res.append((d, o.tolist()))
+        except mr.UndefinedBehaviour:
+            res.append(mr.UndefinedBehaviour)
+    monkeypatch.delenv("MRX_NO_FUSED_SPLIT", raising=False)
+    return res
+
+
+@pytest.mark.parametrize("pattern,alphabet", [(r"\s*,\s*", b"ab,,, \t\n\r\x0b\x0c\xa0\x8c"), (r"\s*;\s*", b"ab; \t\n\x0b"),
+                                              (r"[ab]*,[ab]*", b"abc,, "), (r"\d*-\d*", b"019-x- "), (r"\s*=\s*", b"k=v \t=")])
+def test_fused_split_random_texts(pattern, alphabet, monkeypatch):
+    rx = mr.compile_regex(pattern)
+    orx = oracle.compile(pattern)
+    rng = random.Random(77)
+    outcomes = set()
+    for _ in range(250):
+        n = rng.choice([1, 2, 31, 95, 96, 143, 144, 145, 300, 1000, TILE - 1, TILE, TILE + 1, 2 * TILE + 55])
+        if rng.random() < 0.6:   # separators with their own blanks only: no shared runs
+            sep = bytes([rx.info().required_byte])
+            pad = bytes(b for b in alphabet if b not in sep and b not in b"abkvxc019" and b < 0x80) or b""
+            toks = []
+            while sum(map(len, toks)) < n:
+                toks.append(bytes(rng.choice(b"abkvxc019") for _ in range(rng.randint(0, 7))) or b"q")
+                toks.append(bytes(rng.choice(pad) for _ in range(rng.randint(0, 2))) + sep +
+                            bytes(rng.choice(pad) for _ in range(rng.randint(0, 2))) if pad else sep)
+            t = b"".join(toks)[:n]
+        else:
+            t = bytes(rng.choice(alphabet) for _ in range(n))
+        try:
+            wd, wo = orx.split_raw(t)
+            want = (wd, wo.tolist())
+        except oracle.Unsupported:
+            want = mr.UndefinedBehaviour
+        fused, general = _split_both_paths(rx, t, monkeypatch)
+        assert fused == want, (pattern, t[:300])
+        assert general == want, (pattern, t[:300])
+        outcomes.add("undefined" if want is mr.UndefinedBehaviour else "ok")
+    assert "ok" in outcomes
+
+
+def _check_split(rx, orx, text):
+    try:
+        wd, wo = orx.split_raw(text)
+    except oracle.Unsupported:
+        with pytest.raises(mr.UndefinedBehaviour):
+            rx.split_raw(text)
+        return None
+    gd, go = rx.split_raw(text)
+    assert gd == wd and np.array_equal(go, wo)
+    return wo
+
+
+def test_fused_split_c5_corpus_tiles_and_long_runs(monkeypatch):
+    rx = mr.compile_regex(r"\s*,\s*")
+    orx = oracle.compile(r"\s*,\s*")
+    text = corpora.make("c5", 6 * TILE + 4321).numpy().copy()
+    wo = _check_split(rx, orx, text)
+    assert wo is not None and len(wo) > 20_000
+    # separators across every tile boundary, at the very start and the very end
+    ok = 0
+    for b in (TILE, 2 * TILE, 3 * TILE):
+        for d in (-2, -1, 0, 1):
+            t2 = text.copy()
+            t2[b + d - 3:b + d + 6] = np.frombuffer(b"wx , yzqq", dtype=np.uint8)
+            ok += _check_split(rx, orx, t2) is not None
+    assert ok >= 6
+    t3 = text.copy()
+    t3[:5] = np.frombuffer(b" , ab", dtype=np.uint8)
+    t3[-5:] = np.frombuffer(b"ab , ", dtype=np.uint8)
+    assert _check_split(rx, orx, t3) is not None
+    # blank runs up to and beyond what the kernel's windows measure: short ones fused, long ones through the
+    # general path -- the result is the reference's either way
+    for run in (15, 16, 31, 32, 46, 47, 48, 64, 200, TILE + 10):
+        t4 = text[: 3 * TILE].copy()
+        pos = TILE - 20
+        t4[pos - 2:pos] = np.frombuffer(b"ab", dtype=np.uint8)
+        t4[pos:pos + run] = 32
+        t4[pos + run] = ord(",")
+        t4[pos + run + 1:pos + 2 * run + 1] = 9
+        t4[pos + 2 * run + 1:pos + 2 * run + 4] = np.frombuffer(b"zzz", dtype=np.uint8)
+        assert _check_split(rx, orx, t4) is not None, run
+    # \v in the run before a comma: the comma is no separator (SURVEY appendix B-2)
+    t5 = np.frombuffer(b"a \x0b ,b , c\x0b,d", dtype=np.uint8)
+    assert rx.split(t5) == orx.split(t5)
+    # device-resident, unaligned pointer
+    dev = torch.from_numpy(text).cuda()
+    pc = rx.split_device(mr.Text.from_tensor(dev[7:]))
+    wd, wo = orx.split_raw(text[7:])
+    assert pc.n == len(wo) - 1
+    assert np.array_equal(pc.offsets_tensor().cpu().numpy(), wo)
+    pc.close()
+    # a second call reuses the remembered separator density for the size of the offsets array; a text with many
+    # more separators than the first one makes the kernel run twice
+    dense = np.frombuffer(b"a,b,c,d," * 40_000, dtype=np.uint8)
+    assert _check_split(rx, orx, dense) is not None
