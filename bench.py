@@ -3,10 +3,12 @@
 
     python bench.py --gpus N --steps K --warmup W [--config c2] [--impl reference]
 
-A "step" is one pass of the hot path over one batch of synthetic input.  At N=1 the workload
+A "step" is one pass of the hot path over one batch of synthetic input.  The headline workload
 is BASELINE.json configs[1]: findall("(hello|world|foo)") over a 1 GiB single-buffer corpus.
 With N>1 (torchrun, one rank per GPU) every rank scans its own 1 GiB shard (+ halo) of an
-N GiB corpus and the ranks all-gather their match counts over NCCL (weak scaling).
+N GiB corpus and the ranks all-gather their match counts over NCCL (weak scaling).  The other
+four BASELINE configs are measured in the same run and reported under "configs" of the same
+JSON line (--configs c2 restricts the run to the headline).
 
 Prints ONE JSON line (rank 0).  `value` = input GB/s with the corpus already resident in HBM
 (device time, CUDA events on the library stream, max over ranks); `roofline` = algorithmic bytes of a
@@ -32,13 +34,28 @@ sys.path.insert(0, ROOT)
 GiB = 1 << 30
 
 
+def kernel_source_hash() -> str:
+    """sha256 (16 hex digits) over the CUDA sources: an ncu capture is only quoted for the code it was taken on."""
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "mojo_regex_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".hpp")):
+            with open(os.path.join(csrc, name), "rb") as f:
+                h.update(name.encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic(config: str, n_bytes: int, kernel: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of the same workload
-    (profiles/r01_traffic.json); None when there is no capture for this config / size / kernel."""
+    """DRAM bytes per launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one
+    `ncu --set full` capture), from profiles/r02_traffic.json -- quoted only when the capture is of the same
+    workload, the same kernel AND the same kernel sources (src_sha); None otherwise (never a stale constant)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f).get(config)
-        if t and int(t["bytes_per_gpu"]) == int(n_bytes) and t["kernel"] == kernel:
+        if (t and int(t["bytes_per_gpu"]) == int(n_bytes) and t["kernel"] == kernel
+                and t.get("src_sha") == kernel_source_hash()):
             return float(t["traffic_bytes"])
     except Exception:
         pass
@@ -227,7 +244,39 @@ def cpu_baseline(config: str, cfg, shard, seconds: float = 10.0) -> dict:
 
 
 # --------------------------------------------------------------------------------------------
-def run_gpu(args):
+def bind_to_gpu_numa_node(local_rank: int) -> str:
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host memory is
+    allocated (first touch then places the staging buffers next to the GPU's PCIe root).  Eight ranks that
+    upload from unbound pinned memory measured 16 GB/s per GPU against 53 GB/s alone (round 1)."""
+    try:
+        import torch
+
+        pci = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = "%04x:%02x:%02x.0" % (torch.cuda.get_device_properties(local_rank).pci_domain_id, pci,
+                                    torch.cuda.get_device_properties(local_rank).pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % dom) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return "numa node unknown"
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return "numa node %d has no allowed cpus" % node
+        os.sched_setaffinity(0, cpus)
+        return "numa node %d (%d cpus)" % (node, len(cpus))
+    except Exception as e:  # no sysfs / no permission: run unbound
+        return "unbound (%s)" % type(e).__name__
+
+
+L2_BYTES = 126 << 20
+
+
+def measure_config(args, config: str, ctx, headline: bool) -> dict:
+    """All numbers of one BASELINE config on this rank's shard; collective over the ranks (every rank calls it)."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -236,33 +285,15 @@ def run_gpu(args):
     from mojo_regex_b200 import corpora
     from mojo_regex_b200 import distributed as mrd
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
-    torch.cuda.set_device(local_rank)
-    mr.init(local_rank)
-    if world > 1:
-        import datetime
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
-                                timeout=datetime.timedelta(seconds=180))
-    dev = torch.device("cuda", local_rank)
-    exchange = "none"
-    if world > 1:
-        exchange = "nccl (library communicator)" if mrd.init_native_exchange(dev) else "nccl (torch.distributed)"
-    cfg = corpora.CONFIGS[args.config]
-    size = args.size or default_size(args.config)
+    world, rank, local_rank, dev, lib_stream = ctx["world"], ctx["rank"], ctx["local_rank"], ctx["dev"], ctx["lib_stream"]
+    cfg = corpora.CONFIGS[config]
+    size = (args.size if headline and args.size else 0) or default_size(config)
     rx = mr.compile_regex(cfg["pattern"])
-    peak, peak_src = load_peaks()
+    steps = args.steps if headline else max(3, min(args.steps, 10))
+    warmup = args.warmup
 
-    # ---- this rank's shard, resident in HBM (weak scaling: `size` units per GPU) ----------------
-    shard = mrd.make_shard(args.config, size, rank, world, dev)
+    shard = mrd.make_shard(config, size, rank, world, dev)
     n_bytes = shard.core_bytes
-    lib_stream = torch.cuda.ExternalStream(mr.stream_handle(), device=dev)
-
-    def step_device():
-        return mrd.run_op_device(rx, cfg, shard)
 
     def sync_all():
         mrd.join_exchanges(lib_stream)  # queued count exchanges are issued before any other collective
@@ -272,51 +303,72 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    clocks = ClockSampler(local_rank)
-    for _ in range(args.warmup):
-        res = step_device()
-        res.close()
+    # inputs that fit the L2 (C1: 64 MiB) are evicted between timed steps by writing a buffer twice its size;
+    # each step is then bracketed by its own pair of events and the flush stays outside
+    flush = None
+    if shard.buffer.numel() < 2 * L2_BYTES:
+        flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
+
+    clocks = ClockSampler(local_rank) if headline else None
+    for _ in range(warmup):
+        mrd.run_op_device(rx, cfg, shard).close()
     mr.set_profiling(True)
     sync_all()
     launches0 = mr.launch_count()
     t_begin = time.time()
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = torch.cuda.Event(enable_timing=True)
-    kernel_ms = []
-    units = 0
-    alg_bytes = 0
-    with torch.cuda.stream(lib_stream):
-        ev0.record(lib_stream)
-        for _ in range(args.steps):
-            res = step_device()
+    kernel_ms, units, alg_bytes, res = [], 0, 0, None
+    if flush is None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(lib_stream):
+            ev0.record(lib_stream)
+            for _ in range(steps):
+                res = mrd.run_op_device(rx, cfg, shard)
+                kernel_ms.append(mr.last_kernel_ms())
+                units, alg_bytes = res.units, res.algorithmic_bytes
+                res.close()
+            mrd.join_exchanges(lib_stream)  # the count all-gathers run on their own stream: include them
+            ev1.record(lib_stream)
+        sync_all()
+        dev_ms = ev0.elapsed_time(ev1)
+    else:
+        pairs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            with torch.cuda.stream(lib_stream):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(lib_stream)
+                res = mrd.run_op_device(rx, cfg, shard)
+                mrd.join_exchanges(lib_stream)
+                e1.record(lib_stream)
             kernel_ms.append(mr.last_kernel_ms())
-            units = res.units
-            alg_bytes = res.algorithmic_bytes
+            units, alg_bytes = res.units, res.algorithmic_bytes
             res.close()
-        mrd.join_exchanges(lib_stream)  # the count all-gathers run on their own stream: include them
-        ev1.record(lib_stream)
-    sync_all()
-    dev_ms = ev0.elapsed_time(ev1)
+            pairs.append((e0, e1))
+        sync_all()
+        dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
     launches = mr.launch_count() - launches0
     t_end = time.time()
     mr.set_profiling(False)
-    if t_end - t_begin < 1.0:
-        # the timed region is shorter than nvidia-smi's sampling period: keep the GPU under the very same
-        # kernels (untimed, and WITHOUT the count all-gather: the number of iterations is time based and
-        # differs between ranks) for ~1.2 s so that the clock record is taken under load, not around it
-        t_begin = time.time()
-        while time.time() - t_begin < 1.2:
-            mrd.run_op_local(rx, cfg, shard).close()
-        torch.cuda.synchronize()
-        mr.synchronize()
-        t_end = time.time()
-    clk = clocks.stop(t_begin, t_end)
+    clk = None
+    if clocks is not None:
+        if t_end - t_begin < 1.0:
+            # the timed region is shorter than nvidia-smi's sampling period: keep the GPU under the very same
+            # kernels (untimed, and WITHOUT the count all-gather: the number of iterations is time based and
+            # differs between ranks) for ~1.2 s so that the clock record is taken under load, not around it
+            t_begin = time.time()
+            while time.time() - t_begin < 1.2:
+                mrd.run_op_local(rx, cfg, shard).close()
+            torch.cuda.synchronize()
+            mr.synchronize()
+            t_end = time.time()
+        clk = clocks.stop(t_begin, t_end)
 
     # ---- end to end through the public API with host buffers ---------------------------------
     host = torch.empty(shard.buffer.numel(), dtype=torch.uint8, pin_memory=True)
     host.copy_(shard.buffer)
     torch.cuda.synchronize()
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(steps, 20 if headline else 5))
     mrd.run_op_host(rx, cfg, shard, host)  # warm the pools
     sync_all()
     t0 = time.perf_counter()
@@ -325,45 +377,101 @@ def run_gpu(args):
         d2h = mrd.run_op_host(rx, cfg, shard, host)
     mr.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the ceiling the host side sets: a plain upload of the same buffer from the same pinned memory, all ranks at once
+    sync_all()
+    scratch = torch.empty_like(shard.buffer)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        scratch.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    up_s = (time.perf_counter() - t0) / 3
+    del scratch
 
     # ---- reduce over ranks ----------------------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(kernel_ms))], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(n_bytes), float(units), float(launches), float(shard.buffer.numel()), float(d2h)],
+    t = torch.tensor([dev_ms, e2e_s * 1e3, float(np.mean(kernel_ms)), up_s * 1e3], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(n_bytes), float(units), float(launches), float(shard.buffer.numel()), float(d2h), float(alg_bytes)],
                        dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    dev_ms_max, e2e_ms_max, k_ms = [float(x) for x in t.tolist()]
-    total_bytes, total_units, total_launches, total_h2d, total_d2h = [float(x) for x in tot.tolist()]
+    dev_ms_max, e2e_ms_max, k_ms, up_ms = [float(x) for x in t.tolist()]
+    total_bytes, total_units, total_launches, total_h2d, total_d2h, total_alg = [float(x) for x in tot.tolist()]
 
     # ---- CPU baseline on rank 0 (bounded sample, single thread: the reference is single-threaded)
     cpu = None
     if rank == 0 and not args.no_cpu:
-        cpu = cpu_baseline(args.config, cfg, shard, seconds=10.0)
+        cpu = cpu_baseline(config, cfg, shard, seconds=10.0 if headline else 3.0)
+    kernel = res.kernel
+    flushed = flush is not None
+    del host, shard, flush
+    torch.cuda.empty_cache()
 
+    peak, peak_src = ctx["peak"]
+    value = total_bytes * steps / (dev_ms_max / 1e3) / 1e9
+    achieved = alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
+    return {
+        "value": value, "unit": "GB/s", "steps": steps, "warmup": warmup, "ms_per_step": dev_ms_max / steps,
+        "config": {"workload": CONFIG_DESCR[config], "config": config,
+                   "bytes_per_gpu": int(n_bytes), "units_per_step": int(total_units),
+                   "l2": ("input (%.0f MiB per GPU) is larger than the 126 MB L2; no flush needed" % (n_bytes / 2**20))
+                   if not flushed else "input fits the L2: a 252 MiB buffer is written between the timed steps, "
+                                         "each step has its own pair of events",
+                   "sharding": ("byte ranges + halo, count all-gather: " + ctx["exchange"]) if world > 1 else "single GPU"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": (achieved / peak) if achieved else None,
+                     "traffic": (args.traffic if (args.traffic is not None and headline) else load_traffic(config, n_bytes, kernel)),
+                     "kernel": kernel, "algorithmic_bytes_per_launch": int(alg_bytes), "kernel_ms": k_ms,
+                     "peak_source": peak_src},
+        "cpu_baseline": cpu,
+        "e2e": {"value": total_bytes * e2e_steps / (e2e_ms_max / 1e3) / 1e9, "unit": "GB/s", "steps": e2e_steps,
+                "h2d_bytes_per_step": int(total_h2d), "d2h_bytes_per_step": int(total_d2h),  # summed over ranks
+                "upload_only_gbs": total_h2d / (up_ms / 1e3) / 1e9},
+        "gpu_launches": int(total_launches),
+        "clocks": clk,
+    }
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local_rank)
+    binding = bind_to_gpu_numa_node(local_rank)
+
+    import mojo_regex_b200 as mr
+    from mojo_regex_b200 import distributed as mrd
+
+    mr.init(local_rank)
+    if world > 1:
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank),
+                                timeout=datetime.timedelta(seconds=300))
+    dev = torch.device("cuda", local_rank)
+    exchange = "none"
+    if world > 1:
+        exchange = "nccl (library communicator)" if mrd.init_native_exchange(dev) else "nccl (torch.distributed)"
+    ctx = {"world": world, "rank": rank, "local_rank": local_rank, "dev": dev, "exchange": exchange, "peak": load_peaks(),
+           "lib_stream": torch.cuda.ExternalStream(mr.stream_handle(), device=dev)}
+    wanted = ["c2", "c1", "c3", "c4", "c5"] if args.configs == "all" else [c for c in args.configs.split(",") if c]
+    headline = args.config
+    if headline not in wanted:
+        wanted.insert(0, headline)
+    results = {}
+    for c in [headline] + [c for c in wanted if c != headline]:
+        results[c] = measure_config(args, c, ctx, headline=(c == headline))
     if rank == 0:
-        value = total_bytes * args.steps / (dev_ms_max / 1e3) / 1e9
-        achieved = alg_bytes / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
-        line = {
-            "metric": "input GB/s scanned", "value": value, "unit": "GB/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-            "config": {"workload": CONFIG_DESCR[args.config], "config": args.config,
-                       "bytes_per_gpu": int(n_bytes), "units_per_step": int(total_units),
-                       "l2": "input (%.0f MiB per GPU) is larger than the 126 MB L2; no flush needed" % (n_bytes / 2**20)
-                       if n_bytes > 256 << 20 else "input re-read every step; smaller than 2x L2",
-                       "sharding": ("byte ranges + halo, count all-gather: " + exchange) if world > 1 else "single GPU"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None,
-                         "traffic": args.traffic if args.traffic is not None else load_traffic(args.config, n_bytes, res.kernel),
-                         "kernel": res.kernel, "algorithmic_bytes_per_launch": int(alg_bytes),
-                         "kernel_ms": k_ms, "peak_source": peak_src},
-            "cpu_baseline": cpu,
-            "e2e": {"value": total_bytes * e2e_steps / (e2e_ms_max / 1e3) / 1e9, "unit": "GB/s",
-                    "h2d_bytes_per_step": int(total_h2d), "d2h_bytes_per_step": int(total_d2h)},  # summed over ranks
-            "gpu_launches": int(total_launches),
-            "clocks": clk,
-        }
+        h = results[headline]
+        line = {"metric": "input GB/s scanned", "value": h["value"], "unit": "GB/s", "n_gpus": world, "steps": h["steps"],
+                "warmup": h["warmup"], "ms_per_step": h["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": h["config"], "roofline": h["roofline"],
+                "cpu_baseline": h["cpu_baseline"], "e2e": h["e2e"], "gpu_launches": h["gpu_launches"], "clocks": h["clocks"],
+                "host_binding": binding,
+                "configs": {c: {k: v for k, v in r.items() if k != "clocks"} for c, r in results.items() if c != headline}}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -375,7 +483,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"], help="the headline config of the line")
+    ap.add_argument("--configs", default="all", help="configs measured in this run: 'all' or a comma list (the headline is "
+                                                     "always included); the others go under \"configs\" of the line")
     ap.add_argument("--size", type=int, default=0, help="bytes per GPU (c3: lines); default = BASELINE size")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--traffic", type=float, default=None,

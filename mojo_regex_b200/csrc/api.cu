@@ -1430,7 +1430,6 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
 // kernel's windows cannot measure (the caller then takes the general path).
 static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_pieces *out, bool *done) {
   *done = false;
-  const Plan &pl = re->prog.findall;
   const int64_t n = (int64_t)t->n;
   const int64_t tiles = (n + kTile - 1) / kTile;
   if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");

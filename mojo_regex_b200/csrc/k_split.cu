@@ -16,11 +16,16 @@
 //      whose carries follow the runs): kept-byte mask, valid-separator mask, overlap and overflow flags;
 //   4. (separators, kept bytes) are scanned across the block as one packed integer and published as the tile's
 //      aggregate; the descriptor loads of the look-back window go out here and are consumed after step 5;
-//   5. the kept bytes are compacted into a staging buffer in shared memory (predicated byte stores at a running
-//      pointer that starts at the thread's rank);
-//   6. with the tile's base known (sliding window over the aggregates, as in k_sand) the staging buffer is copied to
-//      its place in the output with 16-byte stores, and every valid separator writes the number of kept bytes before
-//      it -- the offset of the piece it starts -- to the offsets array.
+//   5. the kept bytes are compacted IN PLACE: every thread takes its 144 text bytes into registers, and after a
+//      barrier writes the kept ones back to the same buffer from its rank on, four bytes per store (PRMT with a
+//      selector looked up by the word's four keep bits packs them; a 64-bit queue carries the remainder);  every
+//      valid separator parks the number of kept bytes before it (tile relative, 16 bits) in a second staging array;
+//   6. with the tile's base known (sliding window over the aggregates, as in k_sand) both staging arrays are written
+//      out with coalesced stores: the bytes 16 at a time, the piece offsets as base + staged value.
+// The class table is replicated 32 times (entry b of lane l at word 32 b + l): every lane reads its own bank, so the
+// lookups are conflict free whatever the text is (the first version shared one 1 KiB table: upper- and lower-case
+// letters and digits collide there, 148 M of its 266 M shared-memory wavefronts per GiB were bank conflicts,
+// profiles/r02_k_split_a_ncu.txt).
 // Tiles are handed out by ticket; persistent CTAs, every CTA resident (a flush waits for other CTAs' aggregates).
 #include "kernels.cuh"
 #include "sepbits.hpp"
@@ -31,11 +36,14 @@ constexpr int kSplitPre = 96;    // staged bytes before the tile: the window's h
 constexpr int kSplitPost = 64;   // ... and after it (48 are used)
 constexpr int kSplitHw = kThreads * kVecs;  // 16-bit pieces of one tile's bit stream
 
+constexpr int kSplitOffCap = 8192;  // separators of one tile whose offsets are staged (more: written directly)
+
 struct SplitShared {
-  alignas(128) uint8_t text[kSplitPre + kTile + kSplitPost];
-  alignas(16) uint8_t stage[kTile + 16];      // the tile's kept bytes, compacted
+  alignas(128) uint8_t text[kSplitPre + kTile + kSplitPost];  // the staged text; then, in place, the tile's kept bytes
+  uint32_t T[256 * 32];                        // class table, one copy per lane: entry b of lane l at [32 b + l]
   uint16_t bits[3][6 + kSplitHw + 4];          // C / L / bad streams: 6 pieces of history, the tile, 3 of look-ahead
-  uint32_t T[256];
+  uint16_t offs[kSplitOffCap];                 // kept bytes of the tile before each of its separators
+  uint32_t sel[16];                            // PRMT selectors that pack the kept bytes of a word (by its 4 keep bits)
   alignas(8) uint64_t bar;
   unsigned long long red_ws[2][kThreads / 32];
   uint32_t scan_ws[kThreads / 32];
@@ -43,11 +51,12 @@ struct SplitShared {
 };
 
 // class bits of 16 text bytes: three 16-bit pieces (bit i <-> byte i)
+// T = this lane's column of the replicated table (byte offset 4 * lane already added)
 __device__ __forceinline__ void split_classify16(const uint32_t *T, const uint4 &v, uint32_t &c, uint32_t &l, uint32_t &b) {
   auto entry = [&](uint32_t w, int k) -> uint32_t {
     const uint32_t x = __byte_perm(w, 0, 0x4440 + k);
     uint32_t off;
-    asm("mad.lo.u32 %0, %1, 4, 0;" : "=r"(off) : "r"(x));
+    asm("mad.lo.u32 %0, %1, 128, 0;" : "=r"(off) : "r"(x));
     return *reinterpret_cast<const uint32_t *>(reinterpret_cast<const uint8_t *>(T) + off);
   };
   auto group = [&](uint32_t w0, uint32_t w1) -> uint32_t {  // 8 bytes, last first: byte i ends in bit i of each class byte
@@ -74,7 +83,15 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
     mbar_init(&sh.bar, 1);
     fence_proxy_async();
   }
-  sh.T[tid] = prm.table->T[tid];  // kThreads == 256
+  for (int i = tid; i < 256 * 32; i += kThreads) sh.T[i] = prm.table->T[i >> 5];
+  if (tid < 16) {  // selector that moves the kept bytes of a word to its low end, in order (the rest: byte 0 of the 2nd operand)
+    uint32_t sel = 0x4444u;
+    int o = 0;
+    for (int i = 0; i < 4; ++i)
+      if ((tid >> i) & 1) { sel = (sel & ~(0xfu << (4 * o))) | ((uint32_t)i << (4 * o)); ++o; }
+    sh.sel[tid] = sel;
+  }
+  const uint32_t *myT = sh.T + lane;
   __syncthreads();
 
   auto issue_load = [&](int t) {  // thread 0 only
@@ -152,7 +169,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
     for (int v = 0; v < kVecs; ++v) {
       const uint4 tv = *reinterpret_cast<const uint4 *>(txt + chunk_rel + 16 * v);
       uint32_t c, l, b;
-      split_classify16(sh.T, tv, c, l, b);
+      split_classify16(myT, tv, c, l, b);
       const int live = cv - 16 * v;
       if (live < 16) {
         const uint32_t m = live <= 0 ? 0u : ((1u << live) - 1u);
@@ -166,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
       const int rel = tid < 6 ? -kSplitPre + 16 * tid : kTile + 16 * (tid - 6);  // first byte, relative to the tile
       const uint4 tv = *reinterpret_cast<const uint4 *>(txt + rel);
       uint32_t c, l, b;
-      split_classify16(sh.T, tv, c, l, b);
+      split_classify16(myT, tv, c, l, b);
       // bytes that exist: [-pre, left)
       uint32_t m = 0xffffu;
       if (rel < -pre) m = (rel + 16 <= -pre) ? 0u : (m & ~((1u << (-pre - rel)) - 1u));
@@ -238,30 +255,70 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
     const uint32_t total_k = total & 0xffffu, total_s = total >> 16;
     if (tid == 0) st_volatile_u64(prm.desc + tile, kFlagAgg | ((unsigned long long)total_s << 20) | total_k);
     window_load(tile);  // consumed after the compaction
-    // ---- 5. kept bytes -> staging buffer, in order, from my rank on
+    // ---- 5a. my text -> registers; the barrier below frees the buffer for the compacted bytes
+    uint4 mine[kVecs];
+#pragma unroll
+    for (int v = 0; v < kVecs; ++v) mine[v] = *reinterpret_cast<const uint4 *>(txt + chunk_rel + 16 * v);
+    // ---- 5b. piece offsets of my separators (tile relative) -> staging array, or straight to HBM later
+    const bool offs_staged = total_s <= (uint32_t)kSplitOffCap;
+    if (offs_staged) {
+      uint32_t below = rank_k, idx = rank_s;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        uint32_t m = own.sep[j];
+        while (m) {
+          const int b = __ffs((int)m) - 1;
+          m &= m - 1;
+          sh.offs[idx++] = (uint16_t)(below + __popc(own.kept[j] & ((1u << b) - 1u)));
+        }
+        below += __popc(own.kept[j]);
+      }
+    }
+    if (tid == 0) sh.next_tile = ticket;
+    __syncthreads();  // #3: every thread holds its text; staged offsets and the next ticket are posted
+    // ---- 5c. kept bytes -> the text buffer, in place, from my rank on.  A 64-bit queue (lo, hi) collects packed
+    //      bytes; full words are stored aligned.  The first word of a thread is shared with its predecessor and the
+    //      last one with its successor: those two are written byte by byte.
+    uint8_t *stage = sh.text;
     {
-      uint8_t *wp = sh.stage + rank_k;
+      uint32_t lo = 0, hi = 0;
+      uint32_t fill = rank_k & 3u;                 // bytes of the current word that are not mine (first word only)
+      uint8_t *wp = stage + (rank_k & ~3u);        // aligned address of the current word
+      bool first = true;
+      const uint32_t skip = fill;
 #pragma unroll
       for (int v = 0; v < kVecs; ++v) {
-        const uint4 tv = *reinterpret_cast<const uint4 *>(txt + chunk_rel + 16 * v);
-        const uint32_t ws[4] = {tv.x, tv.y, tv.z, tv.w};
+        const uint32_t ws[4] = {mine[v].x, mine[v].y, mine[v].z, mine[v].w};
         const uint32_t k16 = own.kept[v >> 1] >> (16 * (v & 1));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          if ((k16 >> i) & 1u) {
-            *wp = (uint8_t)__byte_perm(ws[i >> 2], 0, 0x4440 + (i & 3));
-            ++wp;
+        for (int wi = 0; wi < 4; ++wi) {
+          const uint32_t nib = (k16 >> (4 * wi)) & 15u;
+          const uint32_t packed = __byte_perm(ws[wi], 0, sh.sel[nib]);
+          const uint32_t s8 = fill * 8u;
+          lo |= packed << s8;
+          hi |= __funnelshift_l(packed, 0u, s8);   // packed >> (32 - s8), 0 for s8 == 0
+          fill += __popc(nib);
+          if (fill >= 4u) {
+            if (first) {
+              for (uint32_t q = skip; q < 4u; ++q) wp[q] = (uint8_t)(lo >> (8 * q));
+              first = false;
+            } else {
+              *reinterpret_cast<uint32_t *>(wp) = lo;
+            }
+            wp += 4;
+            lo = hi;
+            hi = 0;
+            fill -= 4u;
           }
         }
       }
+      for (uint32_t q = first ? skip : 0u; q < fill; ++q) wp[q] = (uint8_t)(lo >> (8 * q));  // the last, partial word
     }
-    if (lane == 0) { /* (window sums are reduced below) */ }
+    // ---- the look-back window, loaded before the compaction: by now its tiles have been counted
     unsigned long long sk, ss;
     window_sum(tile, sk, ss);
     if (lane == 0) { sh.red_ws[0][warp] = sk; sh.red_ws[1][warp] = ss; }
-    if (tid == 0) sh.next_tile = ticket;
-    __syncthreads();  // #3: staging buffer complete, text buffer free, window sums and the next ticket posted
-    if (tid == 0) issue_load(sh.next_tile);
+    __syncthreads();  // #4: the compacted tile is complete, the window sums are posted
     unsigned long long bk = base_k, bs = base_s;
 #pragma unroll
     for (int w = 0; w < W; ++w) { bk += sh.red_ws[0][w]; bs += sh.red_ws[1][w]; }
@@ -269,31 +326,16 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
     base_s = bs + total_s;
     covered = tile + 1;
     if (tid == 0 && tile == prm.n_tiles - 1) { prm.totals[0] = base_k; prm.totals[1] = base_s; }
-    // ---- 6a. the tile's kept bytes -> out[bk, bk + total_k): head up to 16-byte alignment, 16-byte body, tail
-    {
-      uint8_t *dst = prm.out + bk;
-      const int nkept = (int)total_k;
-      int head = (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
-      if (head > nkept) head = nkept;
-      if (tid < head) dst[tid] = sh.stage[tid];
-      const int body = (nkept - head) >> 4;
-      const int sh8 = (head & 3) * 8;
-      const uint32_t *sw = reinterpret_cast<const uint32_t *>(sh.stage + (head & ~3));
-      for (int i = tid; i < body; i += kThreads) {
-        const uint32_t a0 = sw[4 * i], a1 = sw[4 * i + 1], a2 = sw[4 * i + 2], a3 = sw[4 * i + 3], a4 = sw[4 * i + 4];
-        uint4 o;
-        o.x = __funnelshift_r(a0, a1, sh8); o.y = __funnelshift_r(a1, a2, sh8);
-        o.z = __funnelshift_r(a2, a3, sh8); o.w = __funnelshift_r(a3, a4, sh8);
-        *reinterpret_cast<uint4 *>(dst + head + 16 * i) = o;
-      }
-      const int done = head + 16 * body;
-      if (tid < nkept - done) dst[done + tid] = sh.stage[done + tid];
-    }
     // ---- 6b. piece offsets: the k-th valid separator starts piece k + 1 at (kept bytes before it)
-    {
-      unsigned long long idx = bs + rank_s;             // separators before my first
-      const unsigned long long at = bk + rank_k;        // kept bytes before my chunk
-      uint32_t below = 0;                               // kept bytes of my chunk before the current word
+    if (offs_staged) {
+      for (uint32_t i = tid; i < total_s; i += kThreads) {
+        const unsigned long long idx = bs + i;
+        if (idx < (unsigned long long)prm.offs_cap) prm.offs[1 + idx] = (int64_t)(bk + sh.offs[i]);
+      }
+    } else {  // (a tile with more than kSplitOffCap separators) every thread writes its own
+      unsigned long long idx = bs + rank_s;
+      const unsigned long long at = bk + rank_k;
+      uint32_t below = 0;
 #pragma unroll
       for (int j = 0; j < 5; ++j) {
         uint32_t m = own.sep[j];
@@ -307,7 +349,28 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
         below += __popc(own.kept[j]);
       }
     }
-    __syncthreads();  // #4: everyone has read sh.next_tile and the staging buffer
+    // ---- 6a. the tile's kept bytes -> out[bk, bk + total_k): head up to 16-byte alignment, 16-byte body, tail
+    {
+      uint8_t *dst = prm.out + bk;
+      const int nkept = (int)total_k;
+      int head = (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15);
+      if (head > nkept) head = nkept;
+      if (tid < head) dst[tid] = stage[tid];
+      const int body = (nkept - head) >> 4;
+      const int sh8 = (head & 3) * 8;
+      const uint32_t *sw = reinterpret_cast<const uint32_t *>(stage + (head & ~3));
+      for (int i = tid; i < body; i += kThreads) {
+        const uint32_t a0 = sw[4 * i], a1 = sw[4 * i + 1], a2 = sw[4 * i + 2], a3 = sw[4 * i + 3], a4 = sw[4 * i + 4];
+        uint4 o;
+        o.x = __funnelshift_r(a0, a1, sh8); o.y = __funnelshift_r(a1, a2, sh8);
+        o.z = __funnelshift_r(a2, a3, sh8); o.w = __funnelshift_r(a3, a4, sh8);
+        *reinterpret_cast<uint4 *>(dst + head + 16 * i) = o;
+      }
+      const int done = head + 16 * body;
+      if (tid < nkept - done) dst[done + tid] = stage[done + tid];
+    }
+    __syncthreads();  // #5: the buffer is free for the next tile; everyone has read sh.next_tile's predecessor
+    if (tid == 0) issue_load(sh.next_tile);
     tile = sh.next_tile;
   }
 }
