@@ -106,6 +106,16 @@ typedef struct {
 int mrx_abi_version(void);
 /* Select CUDA device `device` for this process and create the library stream. */
 int mrx_init(int device);
+/* Multi-device mode ("mrx_init(n_gpus) creates per-GPU streams"): initialise devices 0 .. n_gpus-1 in THIS
+ * process.  The host-buffer entry points (mrx_findall_host, mrx_search_batch_host, mrx_sub_host, mrx_split_host)
+ * then shard a large input over all of them inside one call -- byte ranges with a halo, document ranges, ranges that
+ * end after a byte no match can contain -- run the shards from one worker thread per device and combine counts and
+ * boundary records on the host; the result is bit for bit the single-device one.  Everything else (device-resident
+ * texts, mrx_stream, profiling) addresses device 0.  The reference is single-process and single-threaded
+ * (matcher.mojo:1206-1210): this is how its one caller thread reaches every GPU of the box. */
+int mrx_init_multi(int n_gpus);
+/* Devices in use: n_gpus after mrx_init_multi, 1 after mrx_init, 0 before either. */
+int mrx_device_count(void);
 int mrx_shutdown(void);
 const char *mrx_last_error(void);
 /* cudaStream_t the kernels are launched on (so callers can bracket them with events). */

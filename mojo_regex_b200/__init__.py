@@ -80,7 +80,7 @@ class DfaDesc(ctypes.Structure):
 
 
 EXPORTS = [
-    "mrx_abi_version", "mrx_init", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
+    "mrx_abi_version", "mrx_init", "mrx_init_multi", "mrx_device_count", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
     "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
     "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
@@ -99,6 +99,8 @@ def _load() -> ctypes.CDLL:
     vp, i64, sz = c.c_void_p, c.c_int64, c.c_size_t
     lib.mrx_abi_version.restype = c.c_int
     lib.mrx_init.argtypes = [c.c_int]
+    lib.mrx_init_multi.argtypes = [c.c_int]
+    lib.mrx_device_count.restype = c.c_int
     lib.mrx_last_error.restype = c.c_char_p
     lib.mrx_stream.restype = vp
     lib.mrx_launch_count.restype = c.c_uint64
@@ -178,6 +180,24 @@ def init(device: int = 0) -> None:
     global _initialised_device
     _check(lib.mrx_init(device))
     _initialised_device = device
+
+
+def init_multi(n_gpus: int) -> None:
+    """Multi-device mode: devices 0 .. n_gpus-1 in this one process; the host-buffer calls (match_all_host,
+    search_batch_host, sub_host, split_host) then shard a large input over all of them inside one C-ABI call."""
+    global _initialised_device
+    _check(lib.mrx_init_multi(n_gpus))
+    _initialised_device = 0
+
+
+def device_count() -> int:
+    return int(lib.mrx_device_count())
+
+
+def shutdown() -> None:
+    global _initialised_device
+    _check(lib.mrx_shutdown())
+    _initialised_device = None
 
 
 def _ensure_init() -> None:

@@ -9,6 +9,7 @@
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "frontend.hpp"
@@ -44,7 +45,14 @@ struct Lib {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   bool ev_valid = false;
 };
-Lib g;
+// One Lib per CUDA device.  Single-device mode (mrx_init) uses the slot of the selected device; multi-device mode
+// (mrx_init_multi) initialises slots 0 .. n-1 and the host-buffer entry points shard their input over them, one
+// worker thread per device.  `g` is the calling thread's current device.
+constexpr int kMaxDevices = 16;
+Lib g_devs[kMaxDevices];
+int g_multi = 0;                       // > 1: devices 0 .. g_multi - 1 are initialised
+thread_local Lib *g_cur = &g_devs[0];
+#define g (*g_cur)
 
 #define CUDA_TRY(expr)                                                                          \
   do {                                                                                          \
@@ -145,17 +153,23 @@ struct DrainSideStreams {
 
 }  // namespace
 
-struct mrx_regex {
-  Program prog;
+// the tables of a regex as they sit in one device's HBM, and what that device learned about the texts
+struct RegexOnDevice {
   DevProg *d_findall = nullptr, *d_search = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
   sand::Table *d_sand_findall = nullptr;                          // Shift-And table of the findall plan (k_sand)
   sepb::Table *d_sep_findall = nullptr;                           // class table of the fused split (k_split)
   uint8_t *d_rev_search = nullptr;                                // RevTable::tbl of the search plan
-  bool search_dominated = false;
   // matches per key byte seen by the last list job of each plan (findall, search): sizes the span
   // buffer of the next call so that the scan does not have to be repeated with a larger one
   double density[2] = {0.0, 0.0};
+};
+struct mrx_regex {
+  Program prog;
+  bool search_dominated = false;
+  RegexOnDevice dev[16];  // by device index (kMaxDevices); a worker thread only touches its own device's slot
+  RegexOnDevice &on() { return dev[g_cur->device < 0 ? 0 : g_cur->device]; }
+  const RegexOnDevice &on() const { return dev[g_cur->device < 0 ? 0 : g_cur->device]; }
 };
 
 struct mrx_text {
@@ -171,12 +185,16 @@ namespace {
 struct OwnedOut {  // behind the _owner fields
   void *dev[3] = {nullptr, nullptr, nullptr};
   void *host[3] = {nullptr, nullptr, nullptr};
+  Lib *lib = g_cur;  // the blocks belong to this device's pools
 };
 void release_owner(void *o) {
   if (!o) return;
   OwnedOut *w = static_cast<OwnedOut *>(o);
+  Lib *saved = g_cur;
+  g_cur = w->lib;
   for (void *p : w->dev) dev_release(p);
   for (void *p : w->host) host_release(p);
+  g_cur = saved;
   delete w;
 }
 OwnerGuard::~OwnerGuard() {
@@ -287,28 +305,28 @@ int upload_dense(const DenseTable &dt, uint8_t **out) {
 
 int ensure_uploaded(mrx_regex *re) {
   if (re->prog.flag(BF_WILDCARD_ANY)) return MRX_OK;
-  if (re->prog.findall.dense.valid && !re->d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->d_dense_findall); if (rc) return rc; }
-  if (re->prog.search.dense.valid && !re->d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->d_dense_search); if (rc) return rc; }
-  if (re->prog.findall.sep_valid && !re->d_sep_findall) {
+  if (re->prog.findall.dense.valid && !re->on().d_dense_findall) { int rc = upload_dense(re->prog.findall.dense, &re->on().d_dense_findall); if (rc) return rc; }
+  if (re->prog.search.dense.valid && !re->on().d_dense_search) { int rc = upload_dense(re->prog.search.dense, &re->on().d_dense_search); if (rc) return rc; }
+  if (re->prog.findall.sep_valid && !re->on().d_sep_findall) {
     void *d = nullptr;
     if (int rc = upload_blob(&re->prog.findall.sep, sizeof(sepb::Table), &d)) return rc;
-    re->d_sep_findall = static_cast<sepb::Table *>(d);
+    re->on().d_sep_findall = static_cast<sepb::Table *>(d);
   }
-  if (re->prog.findall.sand_valid && !re->d_sand_findall) {
+  if (re->prog.findall.sand_valid && !re->on().d_sand_findall) {
     void *d = nullptr;
     if (int rc = upload_blob(&re->prog.findall.sand, sizeof(sand::Table), &d)) return rc;
-    re->d_sand_findall = static_cast<sand::Table *>(d);
+    re->on().d_sand_findall = static_cast<sand::Table *>(d);
   }
-  if (re->prog.search.rev.valid && !re->d_rev_search) {
+  if (re->prog.search.rev.valid && !re->on().d_rev_search) {
     const RevTable &rt = re->prog.search.rev;
     std::vector<uint16_t> tb(rt.rev);
     tb.insert(tb.end(), rt.fwd.begin(), rt.fwd.end());
     void *d = nullptr;
     if (int rc = upload_blob(tb.data(), tb.size() * 2, &d)) return rc;
-    re->d_rev_search = static_cast<uint8_t *>(d);
+    re->on().d_rev_search = static_cast<uint8_t *>(d);
   }
-  if (!re->d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->d_findall); if (rc) return rc; }
-  if (!re->d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->d_search); if (rc) return rc; }
+  if (!re->on().d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->on().d_findall); if (rc) return rc; }
+  if (!re->on().d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->on().d_search); if (rc) return rc; }
   return MRX_OK;
 }
 
@@ -368,7 +386,7 @@ bool sand_enabled() { return getenv("MRX_NO_SAND") == nullptr; }
 // reports the exact count, and is repeated once with that.
 double &density_slot(const ListJob &job) {
   mrx_regex *re = const_cast<mrx_regex *>(job.re);
-  return re->density[job.pl == &job.re->prog.findall ? 0 : 1];
+  return re->on().density[job.pl == &job.re->prog.findall ? 0 : 1];
 }
 int64_t initial_cap(const ListJob &job) {
   const int64_t keys = job.key_hi - job.key_lo;
@@ -550,8 +568,8 @@ int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const Dev
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
   const int64_t n = (int64_t)t->n;
   ListJob job{re, t, &pl, dprog, (int64_t)t->core_begin, (int64_t)t->core_end, t->global_offset};
-  if (pl.dense.valid) job.dense = (&pl == &re->prog.findall) ? re->d_dense_findall : re->d_dense_search;
-  if (&pl == &re->prog.findall && pl.sand_valid && sand_enabled()) job.sand = re->d_sand_findall;
+  if (pl.dense.valid) job.dense = (&pl == &re->prog.findall) ? re->on().d_dense_findall : re->on().d_dense_search;
+  if (&pl == &re->prog.findall && pl.sand_valid && sand_enabled()) job.sand = re->on().d_sand_findall;
   switch (pl.mode) {
     case MRX_MODE_WILDCARD_ANY: {  // matcher.mojo:809-813
       void *p = nullptr;
@@ -604,13 +622,13 @@ int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t o
     return 0;
   }
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
-  if (pl.dense.valid && re->d_dense_search) {
+  if (pl.dense.valid && re->on().d_dense_search) {
     if (pl.mode == MRX_MODE_EXACT_LITERAL && start >= n) return 0;  // matcher.mojo:773-774
     if (start >= n) return 0;
     const int64_t origin = start & ~15ll;
     const int64_t tiles = n_tiles_for(origin, n - 1);
     DenseParams dp{};
-    dp.text = t->d; dp.n = n; dp.key_lo = start; dp.key_hi = n; dp.dense = re->d_dense_search;
+    dp.text = t->d; dp.n = n; dp.key_lo = start; dp.key_hi = n; dp.dense = re->on().d_dense_search;
     dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_FIRST; dp.best = g.scalars + 1;
     launch_fill_u64(g.scalars + 1, 1, ~0ull, g.stream);
     ++g.launches;
@@ -634,7 +652,7 @@ int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t o
     return 1;
   }
   ScanParams p{};
-  p.text = t->d; p.n = n; p.prog = re->d_search; p.filt = make_filter(pl); p.mode = pl.mode;
+  p.text = t->d; p.n = n; p.prog = re->on().d_search; p.filt = make_filter(pl); p.mode = pl.mode;
   p.search_start = start; p.rebase = 0;
   if (pl.mode == MRX_MODE_ANCHORED) {  // dfa.mojo:1888-1892
     if (start != 0) return 0;
@@ -717,6 +735,7 @@ int finish_spans(DevSpans &ds, int location, mrx_spans *out) {
 // chunk is still arriving.  PCIe is full duplex, so the call costs about one upload of the text.
 // Plans served this way read at most kLookAhead bytes past the tile they scan (dense literal sets: none,
 // class runs: one byte); every other plan uploads first and scans after.
+constexpr size_t kMultiMinBytes = 32u << 20;  // multi-device mode shards a host buffer once every device gets this much
 constexpr int64_t kPipeChunk = 32ll << 20;
 constexpr int64_t kLookAhead = 16;
 
@@ -755,9 +774,9 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
     CUDA_TRY(cudaMemcpyAsync(dt + b, host + b, (size_t)len, cudaMemcpyHostToDevice, g.s_in));
     CUDA_TRY(cudaEventRecord(pipe_event((size_t)c), g.s_in));
   }
-  ListJob job{re, &tview, &pl, re->d_findall, core_begin, core_end, global_offset};
-  if (pl.dense.valid) job.dense = re->d_dense_findall;
-  if (pl.sand_valid && sand_enabled()) job.sand = re->d_sand_findall;
+  ListJob job{re, &tview, &pl, re->on().d_findall, core_begin, core_end, global_offset};
+  if (pl.dense.valid) job.dense = re->on().d_dense_findall;
+  if (pl.sand_valid && sand_enabled()) job.sand = re->on().d_sand_findall;
   const int64_t origin = core_begin & ~15ll;
   // dense plans record a match in the tile that holds its end: up to max_len - 1 bytes past the key window
   const int64_t last_pos = pl.dense.valid ? std::min<int64_t>(n - 1, core_end - 1 + std::max(pl.dense.max_len - 1, 0)) : core_end - 1;
@@ -803,7 +822,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
       launch_dense(dp, (int)(t1 - t0), g.stream);
     } else {
       RunsParams p{};
-      p.text = dt; p.n = n; p.tile_origin = origin; p.key_lo = core_begin; p.key_hi = core_end; p.prog = re->d_findall; p.filt = make_filter(pl);
+      p.text = dt; p.n = n; p.tile_origin = origin; p.key_lo = core_begin; p.key_hi = core_end; p.prog = re->on().d_findall; p.filt = make_filter(pl);
       p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max; p.n_tiles = (int)t1; p.tile_base = (int)t0;
       p.tile_carry = nullptr; p.spans = (int64_t *)d_spans; p.cap = cap; p.rebase = global_offset;
       p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
@@ -829,7 +848,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
     CUDA_TRY(cudaStreamSynchronize(g.s_out));
     CUDA_TRY(cudaStreamSynchronize(g.s_in));
     DevSpans ds;
-    if ((rc = match_list(re, &tview, pl, re->d_findall, ds))) return rc;
+    if ((rc = match_list(re, &tview, pl, re->on().d_findall, ds))) return rc;
     return finish_spans(ds, MRX_OUT_HOST, out);
   }
   note_density(job, total);
@@ -853,13 +872,9 @@ extern "C" {
 int mrx_abi_version(void) { return MRX_ABI_VERSION; }
 const char *mrx_last_error(void) { return g_err.c_str(); }
 
-int mrx_init(int device) {
-  if (g.inited && g.device == device) return MRX_OK;
-  if (g.inited) mrx_shutdown();
-  int count = 0;
-  cudaError_t e = cudaGetDeviceCount(&count);
-  if (e != cudaSuccess || count == 0) return fail(MRX_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
-  if (device < 0 || device >= count) return fail(MRX_E_INVALID, "device index out of range");
+static int init_slot(int device) {  // makes `device` current for this thread and sets its Lib up
+  g_cur = &g_devs[device];
+  if (g.inited) return MRX_OK;
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&g.s_in, cudaStreamNonBlocking));
@@ -874,24 +889,61 @@ int mrx_init(int device) {
   g.launches = 0;
   return MRX_OK;
 }
+static void shutdown_slot(int device) {
+  Lib *saved = g_cur;
+  g_cur = &g_devs[device];
+  if (g.inited) {
+    cudaSetDevice(device);
+    cudaStreamSynchronize(g.stream);
+    for (auto &kv : g.dev_free) cudaFree(kv.second);
+    for (auto &kv : g.host_free) cudaFreeHost(kv.second);
+    g.dev_free.clear();
+    g.host_free.clear();
+    cudaFree(g.ticket);
+    cudaFree(g.scalars);
+    cudaFreeHost(g.h_scalars);
+    cudaEventDestroy(g.ev0);
+    cudaEventDestroy(g.ev1);
+    for (cudaEvent_t e : g.ev_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(g.s_in);
+    cudaStreamDestroy(g.s_out);
+    cudaStreamDestroy(g.stream);
+    g = Lib();
+  }
+  g_cur = saved;
+}
+
+int mrx_init(int device) {
+  if (g_multi <= 1 && g.inited && g.device == device) return MRX_OK;
+  mrx_shutdown();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(MRX_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (device < 0 || device >= count || device >= kMaxDevices) return fail(MRX_E_INVALID, "device index out of range");
+  g_multi = 0;
+  return init_slot(device);
+}
+
+int mrx_init_multi(int n_gpus) {
+  mrx_shutdown();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) return fail(MRX_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(e));
+  if (n_gpus < 1 || n_gpus > count || n_gpus > kMaxDevices) return fail(MRX_E_INVALID, "more devices requested than this process can see");
+  for (int d = n_gpus - 1; d >= 0; --d) {  // device 0 last: it stays the calling thread's current device
+    int rc = init_slot(d);
+    if (rc) { mrx_shutdown(); return rc; }
+  }
+  g_multi = n_gpus;
+  return MRX_OK;
+}
+
+int mrx_device_count(void) { return g_multi > 1 ? g_multi : (g.inited ? 1 : 0); }
 
 int mrx_shutdown(void) {
-  if (!g.inited) return MRX_OK;
-  cudaStreamSynchronize(g.stream);
-  for (auto &kv : g.dev_free) cudaFree(kv.second);
-  for (auto &kv : g.host_free) cudaFreeHost(kv.second);
-  g.dev_free.clear();
-  g.host_free.clear();
-  cudaFree(g.ticket);
-  cudaFree(g.scalars);
-  cudaFreeHost(g.h_scalars);
-  cudaEventDestroy(g.ev0);
-  cudaEventDestroy(g.ev1);
-  for (cudaEvent_t e : g.ev_pool) cudaEventDestroy(e);
-  cudaStreamDestroy(g.s_in);
-  cudaStreamDestroy(g.s_out);
-  cudaStreamDestroy(g.stream);
-  g = Lib();
+  for (int d = 0; d < kMaxDevices; ++d) shutdown_slot(d);
+  g_multi = 0;
+  g_cur = &g_devs[0];
   return MRX_OK;
 }
 
@@ -1022,13 +1074,15 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
 
 void mrx_regex_free(mrx_regex *re) {
   if (!re) return;
-  if (re->d_findall) cudaFree(re->d_findall);
-  if (re->d_search) cudaFree(re->d_search);
-  if (re->d_dense_findall) cudaFree(re->d_dense_findall);
-  if (re->d_dense_search) cudaFree(re->d_dense_search);
-  if (re->d_sand_findall) cudaFree(re->d_sand_findall);
-  if (re->d_sep_findall) cudaFree(re->d_sep_findall);
-  if (re->d_rev_search) cudaFree(re->d_rev_search);
+  for (RegexOnDevice &o : re->dev) {  // (UVA: a device pointer can be freed from any current device)
+    if (o.d_findall) cudaFree(o.d_findall);
+    if (o.d_search) cudaFree(o.d_search);
+    if (o.d_dense_findall) cudaFree(o.d_dense_findall);
+    if (o.d_dense_search) cudaFree(o.d_dense_search);
+    if (o.d_sand_findall) cudaFree(o.d_sand_findall);
+    if (o.d_sep_findall) cudaFree(o.d_sep_findall);
+    if (o.d_rev_search) cudaFree(o.d_rev_search);
+  }
   delete re;
 }
 
@@ -1097,12 +1151,12 @@ int mrx_findall(const mrx_regex *re_c, const mrx_text *t, int location, mrx_span
   std::memset(out, 0, sizeof *out);
   if ((rc = ensure_uploaded(re))) return rc;
   DevSpans ds;
-  if ((rc = match_list(re, t, re->prog.findall, re->d_findall, ds))) return rc;
+  if ((rc = match_list(re, t, re->prog.findall, re->on().d_findall, ds))) return rc;
   return finish_spans(ds, location, out);
 }
 
-int mrx_findall_host_shard(const mrx_regex *re_c, const uint8_t *host, size_t n, size_t core_begin, size_t core_end,
-                           int64_t global_offset, mrx_spans *out) {
+static int findall_host_shard_single(const mrx_regex *re_c, const uint8_t *host, size_t n, size_t core_begin, size_t core_end,
+                                     int64_t global_offset, mrx_spans *out) {
   int rc = require_device();
   if (rc) return rc;
   if (!re_c || !out || (!host && n) || core_begin > core_end || core_end > n) return fail(MRX_E_INVALID, "bad argument");
@@ -1119,8 +1173,18 @@ int mrx_findall_host_shard(const mrx_regex *re_c, const uint8_t *host, size_t n,
   return rc;
 }
 
+int mrx_findall_host_shard(const mrx_regex *re_c, const uint8_t *host, size_t n, size_t core_begin, size_t core_end,
+                           int64_t global_offset, mrx_spans *out) {
+  return findall_host_shard_single(re_c, host, n, core_begin, core_end, global_offset, out);
+}
+
+static int findall_host_multi(const mrx_regex *re_c, const uint8_t *host, size_t n, mrx_spans *out);
+static bool findall_shardable(const mrx_regex *re);
+
 int mrx_findall_host(const mrx_regex *re_c, const uint8_t *host, size_t n, mrx_spans *out) {
-  return mrx_findall_host_shard(re_c, host, n, 0, n, 0, out);
+  if (g_multi > 1 && re_c && n >= (size_t)g_multi * kMultiMinBytes && findall_shardable(re_c))
+    return findall_host_multi(re_c, host, n, out);
+  return findall_host_shard_single(re_c, host, n, 0, n, 0, out);
 }
 
 int mrx_search(const mrx_regex *re_c, const mrx_text *t, int64_t start, int64_t out[2]) {
@@ -1153,14 +1217,14 @@ int mrx_match_first(const mrx_regex *re_c, const mrx_text *t, int64_t start, int
   DevTmp tmpprog;
   if (p.flag(BF_PURE_LITERAL)) {
     sp.mode = MRX_MODE_LITERAL;
-    sp.prog = (p.findall.mode == MRX_MODE_LITERAL) ? re->d_findall : re->d_search;
+    sp.prog = (p.findall.mode == MRX_MODE_LITERAL) ? re->on().d_findall : re->on().d_search;
     if (p.findall.mode != MRX_MODE_LITERAL && p.search.mode != MRX_MODE_LITERAL)
       return fail(MRX_E_UNSUPPORTED, "match_first on a literal routed through the exact-literal path");
   } else {
     sp.mode = MRX_MODE_EVERY_POS;
     // any uploaded program of this regex carries the same automaton and shortcut flag semantics,
     // except that the shortcut depends only on the engine -> take the findall program
-    sp.prog = re->d_findall;
+    sp.prog = re->on().d_findall;
     (void)one;
   }
   launch_attempt_one(sp, start, (int64_t *)(g.scalars + 2), g.stream);
@@ -1209,7 +1273,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
       outp = d_out.as<int64_t>();
     }
     ScanParams p{};
-    p.text = t->d; p.n = n; p.prog = re->d_search; p.mode = MRX_MODE_EVERY_POS;
+    p.text = t->d; p.n = n; p.prog = re->on().d_search; p.mode = MRX_MODE_EVERY_POS;
     p.doc_offsets = offs_dev; p.doc_stride = doc_stride; p.n_docs = (int64_t)n_docs;
     launch_batch_trivial(p, pl.mode == MRX_MODE_WILDCARD_ANY ? 1 : 0, outp, g.stream);
     ++g.launches;
@@ -1220,7 +1284,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     }
     return MRX_OK;
   }
-  if (re->d_rev_search && re->d_search && !getenv("MRX_NO_LINES")) {
+  if (re->on().d_rev_search && re->on().d_search && !getenv("MRX_NO_LINES")) {
     // reverse-automaton kernel: one thread per document, results written in place
     int64_t *outp = out_start_end;
     if (location == MRX_OUT_HOST) {
@@ -1228,7 +1292,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
       outp = d_out.as<int64_t>();
     }
     LinesParams lp{};
-    lp.text = t->d; lp.n = n; lp.tables = re->d_rev_search;
+    lp.text = t->d; lp.n = n; lp.tables = re->on().d_rev_search;
     lp.rev_bytes = (int32_t)(pl.rev.rev.size() * 2); lp.fwd_bytes = (int32_t)(pl.rev.fwd.size() * 2);
     lp.fwd_start = pl.rev.fwd_start; lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
     lp.n_docs = (int64_t)n_docs; lp.out = outp; lp.req_byte = pl.rev.req_byte;
@@ -1248,7 +1312,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   launch_fill_u64(d_best.as<unsigned long long>(), (int64_t)n_docs, ~0ull, g.stream);
   ++g.launches;
   ScanParams p{};
-  p.text = t->d; p.n = n; p.prog = re->d_search; p.filt = make_filter(pl); p.mode = pl.mode;
+  p.text = t->d; p.n = n; p.prog = re->on().d_search; p.filt = make_filter(pl); p.mode = pl.mode;
   p.tile_origin = 0; p.key_lo = 0; p.key_hi = n; p.search_start = -1;
   p.out_kind = OUT_BATCH; p.doc_offsets = offs_dev; p.doc_stride = doc_stride; p.n_docs = (int64_t)n_docs;
   p.doc_best = d_best.as<unsigned long long>();
@@ -1362,7 +1426,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
     ms.n = 2;
     rc = MRX_OK;
   } else
-  rc = match_list(re, t, p.search, re->d_search, ms);
+  rc = match_list(re, t, p.search, re->on().d_search, ms);
   prof.disarm();
   if (rc) return bail(rc);
   int64_t M = ms.n;
@@ -1442,7 +1506,7 @@ static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_piece
   void *d_bytes = nullptr;
   if ((rc = dev_alloc((size_t)n + 32, &d_bytes))) return rc;
   own->dev[0] = d_bytes;
-  const double dens = re->density[0];
+  const double dens = re->on().density[0];
   int64_t cap = dens > 0.0 ? (int64_t)(dens * 1.125 * (double)n) + 4096 : std::min<int64_t>(n / 6 + 1024, 1ll << 27);
   ProfOuter prof;
   for (int attempt = 0; attempt < 3; ++attempt) {
@@ -1454,7 +1518,7 @@ static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_piece
     CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 32, g.stream));
     CUDA_TRY(cudaMemsetAsync(d_offs, 0, 8, g.stream));
     SplitParams sp{};
-    sp.text = t->d; sp.n = n; sp.table = re->d_sep_findall; sp.n_tiles = (int)tiles; sp.out = (uint8_t *)d_bytes;
+    sp.text = t->d; sp.n = n; sp.table = re->on().d_sep_findall; sp.n_tiles = (int)tiles; sp.out = (uint8_t *)d_bytes;
     sp.offs = (int64_t *)d_offs; sp.offs_cap = cap; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket;
     sp.totals = g.scalars; sp.flags = reinterpret_cast<int *>(g.scalars + 2);
     prof.arm();
@@ -1470,7 +1534,7 @@ static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_piece
     if (flags & 2)
       return fail(MRX_E_UNDEFINED, "separator spans overlap (text[prev_end:start] with prev_end > start): the reference's "
                                    "behaviour is undefined here (matcher.mojo:1389)");
-    re->density[0] = (double)M / (double)n;
+    re->on().density[0] = (double)M / (double)n;
     if (M > cap) {  // the offsets array was too small: once more with the exact size
       dev_release(d_offs);
       own->dev[1] = nullptr;
@@ -1518,7 +1582,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   const int64_t n = (int64_t)t->n;
   if (t->core_begin != 0 || t->core_end != t->n) return fail(MRX_E_INVALID, "split on a windowed text: assemble per shard on whole buffers");
   if ((rc = ensure_uploaded(re))) return rc;
-  if (re->prog.findall.sep_valid && maxsplit == 0 && n > 0 && re->d_sep_findall && !getenv("MRX_NO_FUSED_SPLIT")) {
+  if (re->prog.findall.sep_valid && maxsplit == 0 && n > 0 && re->on().d_sep_findall && !getenv("MRX_NO_FUSED_SPLIT")) {
     // X* c Y* (config 5): finder, compaction and piece offsets in one kernel; texts with runs the kernel's windows
     // cannot measure fall through to the general path
     bool done = false;
@@ -1533,7 +1597,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
   mrx_text local = *t;  // buffer coordinates for the assembly (see mrx_sub)
   local.global_offset = 0;
   t = &local;
-  rc = match_list(re, t, re->prog.findall, re->d_findall, ms);
+  rc = match_list(re, t, re->prog.findall, re->on().d_findall, ms);
   prof.disarm();
   if (rc) return rc;
   struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
@@ -1813,8 +1877,8 @@ extern "C" int mrx_comm_shutdown(void) {
   return MRX_OK;
 }
 
-extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host, size_t n, const int64_t *doc_offsets,
-                                     size_t n_docs, int64_t doc_stride, int64_t *out_start_end) {
+static int search_batch_host_single(const mrx_regex *re_c, const uint8_t *host, size_t n, const int64_t *doc_offsets,
+                                    size_t n_docs, int64_t doc_stride, int64_t *out_start_end) {
   int rc = require_device();
   if (rc) return rc;
   if (!re_c || !out_start_end || (!host && n) || (!doc_offsets && doc_stride <= 0)) return fail(MRX_E_INVALID, "bad argument");
@@ -1886,8 +1950,8 @@ extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host,
   return MRX_OK;
 }
 
-extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
-                            size_t n, mrx_bytes *out) {
+static int sub_host_single(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
+                           size_t n, mrx_bytes *out) {
   int rc = require_device();
   if (rc) return rc;
   if (!re_c || !out || (!host && n) || (!repl && repl_n)) return fail(MRX_E_INVALID, "null argument");
@@ -1938,7 +2002,7 @@ extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t r
   return MRX_OK;
 }
 
-extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out) {
+static int split_host_single(const mrx_regex *re_c, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out) {
   int rc = require_device();
   if (rc) return rc;
   if (!re_c || !out || (!host && n)) return fail(MRX_E_INVALID, "null argument");
@@ -2007,6 +2071,247 @@ extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t
   out->_owner = own;
   out->bytes = (uint8_t *)bytes.p;
   out->offsets = (int64_t *)offs.p;
+  out->n = nsep + 1;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
+
+// ---- multi-device mode: one C-ABI call, all the GPUs of the box ---------------------------------------------------
+// mrx_init_multi(n) initialises devices 0 .. n-1 in this process.  The host-buffer entry points then cut their input
+// into n contiguous shards -- byte ranges with a halo (findall), document ranges (batch search), ranges that end
+// after a byte no match can contain (sub, split) -- and run the single-device implementation on each from its own
+// worker thread (own device, own streams, own pools; the threads share nothing but the read-only regex).  No data
+// crosses between GPUs: what has to be combined is counts and a few boundary records, and the calling thread is
+// their one consumer, so they are combined on the host (the NCCL count exchange, mrx_comm_*, is for the
+// one-process-per-GPU layout where no single caller sees all the counts).
+namespace {
+
+template <class F>
+int run_on_devices(int n, F &&f) {  // f(d) runs with device d current in its own thread; first error wins
+  std::vector<int> rcs((size_t)n, MRX_OK);
+  std::vector<std::string> errs((size_t)n);
+  std::vector<std::thread> threads;
+  for (int d = 0; d < n; ++d)
+    threads.emplace_back([&, d]() {
+      g_cur = &g_devs[d];
+      cudaError_t e = cudaSetDevice(d);
+      rcs[(size_t)d] = e == cudaSuccess ? f(d) : fail(MRX_E_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+      errs[(size_t)d] = g_err;
+    });
+  for (std::thread &t : threads) t.join();
+  for (int d = 0; d < n; ++d)
+    if (rcs[(size_t)d] != MRX_OK) return fail(rcs[(size_t)d], "device " + std::to_string(d) + ": " + errs[(size_t)d]);
+  return MRX_OK;
+}
+
+constexpr int64_t kMultiHalo = 1 << 16;
+
+}  // namespace
+
+// byte ranges compose into the whole-text result when no match decision crosses a shard edge: literal sets
+// (every occurrence is a match, bounded length) and class runs (clipped at the edges, stitched below)
+static bool findall_shardable(const mrx_regex *re) {
+  const Plan &pl = re->prog.findall;
+  if (pl.unsupported) return false;
+  return (pl.dense.valid && pl.direct && pl.dense.max_len < kMultiHalo) || pl.mode == MRX_MODE_CLASS_RUNS;
+}
+
+static int findall_host_multi(const mrx_regex *re_c, const uint8_t *host, size_t n, mrx_spans *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!out || (!host && n)) return fail(MRX_E_INVALID, "bad argument");
+  std::memset(out, 0, sizeof *out);
+  const int N = g_multi;
+  const bool runs = re_c->prog.findall.mode == MRX_MODE_CLASS_RUNS;
+  std::vector<mrx_spans> parts((size_t)N);
+  std::vector<int64_t> lo((size_t)N + 1);
+  for (int d = 0; d <= N; ++d) lo[(size_t)d] = (int64_t)((unsigned __int128)n * d / N);
+  rc = run_on_devices(N, [&](int d) {
+    const int64_t b0 = std::max<int64_t>(0, lo[(size_t)d] - kMultiHalo), b1 = std::min<int64_t>((int64_t)n, lo[(size_t)d + 1] + kMultiHalo);
+    return findall_host_shard_single(re_c, host + b0, (size_t)(b1 - b0), (size_t)(lo[(size_t)d] - b0), (size_t)(lo[(size_t)d + 1] - b0), b0,
+                                     &parts[(size_t)d]);
+  });
+  auto free_parts = [&]() { for (mrx_spans &p : parts) mrx_spans_free(&p); };
+  if (rc) { free_parts(); return rc; }
+  // class runs are clipped to the shard cores: a run that ends on a shard's end and one that starts on the next
+  // shard's begin are one run of the reference (it may swallow whole shards)
+  std::vector<int64_t> first((size_t)N, 0), count((size_t)N);  // slice [first, first + count) of every part survives
+  for (int d = 0; d < N; ++d) count[(size_t)d] = (int64_t)parts[(size_t)d].n;
+  if (runs) {
+    int d = 0;
+    while (d < N) {
+      mrx_spans &p = parts[(size_t)d];
+      if (count[(size_t)d] == 0 || p.start_end[2 * (first[(size_t)d] + count[(size_t)d] - 1) + 1] != lo[(size_t)d + 1]) { ++d; continue; }
+      int64_t *last_end = &p.start_end[2 * (first[(size_t)d] + count[(size_t)d] - 1) + 1];
+      int k = d + 1;
+      while (k < N) {
+        mrx_spans &q = parts[(size_t)k];
+        if (count[(size_t)k] == 0 || q.start_end[2 * first[(size_t)k]] != *last_end) break;
+        *last_end = q.start_end[2 * first[(size_t)k] + 1];  // the continuation joins the open run ...
+        ++first[(size_t)k];                                 // ... and leaves its own shard's list
+        --count[(size_t)k];
+        if (count[(size_t)k] > 0 || *last_end != lo[(size_t)k + 1]) break;  // the run ended inside shard k
+        ++k;                                                // shard k was one run from edge to edge: go on
+      }
+      d = std::max(k, d + 1);
+    }
+  }
+  int64_t total = 0;
+  std::vector<int64_t> at((size_t)N);
+  for (int d = 0; d < N; ++d) { at[(size_t)d] = total; total += count[(size_t)d]; }
+  void *h = nullptr;
+  if ((rc = host_alloc(sizeof(int64_t) * 2 * (size_t)std::max<int64_t>(total, 1), &h))) { free_parts(); return rc; }
+  {  // every worker copies its slice into place (the spans are a third of the text's size: not a job for one core)
+    std::vector<std::thread> threads;
+    for (int d = 0; d < N; ++d)
+      threads.emplace_back([&, d]() {
+        if (count[(size_t)d] > 0)
+          std::memcpy((int64_t *)h + 2 * at[(size_t)d], parts[(size_t)d].start_end + 2 * first[(size_t)d], sizeof(int64_t) * 2 * (size_t)count[(size_t)d]);
+      });
+    for (std::thread &t : threads) t.join();
+  }
+  free_parts();
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = h;
+  out->_owner = own;
+  out->start_end = (int64_t *)h;
+  out->n = (size_t)total;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
+extern "C" int mrx_search_batch_host(const mrx_regex *re_c, const uint8_t *host, size_t n, const int64_t *doc_offsets,
+                                     size_t n_docs, int64_t doc_stride, int64_t *out_start_end) {
+  if (g_multi <= 1 || !re_c || !out_start_end || n < (size_t)g_multi * kMultiMinBytes || n_docs < (size_t)g_multi * 1024 ||
+      (!doc_offsets && doc_stride <= 0))
+    return search_batch_host_single(re_c, host, n, doc_offsets, n_docs, doc_stride, out_start_end);
+  int rc = require_device();
+  if (rc) return rc;
+  const int N = g_multi;
+  if (doc_offsets) {
+    if (doc_offsets[0] < 0 || doc_offsets[n_docs] > (int64_t)n) return fail(MRX_E_INVALID, "doc_offsets outside the text");
+  } else if ((int64_t)(n_docs - 1) > (int64_t)n / doc_stride) {
+    return fail(MRX_E_INVALID, "more fixed-size documents than the text holds");
+  }
+  // documents are independent: contiguous document ranges, results written in place by every device
+  return run_on_devices(N, [&](int d) {
+    const size_t d0 = n_docs * (size_t)d / N, d1 = n_docs * (size_t)(d + 1) / N;
+    if (d1 <= d0) return (int)MRX_OK;
+    if (!doc_offsets) {
+      const size_t b0 = d0 * (size_t)doc_stride, b1 = std::min(n, d1 * (size_t)doc_stride);
+      return search_batch_host_single(re_c, host + b0, b1 - b0, nullptr, d1 - d0, doc_stride, out_start_end + 2 * d0);
+    }
+    std::vector<int64_t> rebased(d1 - d0 + 1);
+    for (size_t i = d0; i <= d1; ++i) rebased[i - d0] = doc_offsets[i] - doc_offsets[d0];
+    return search_batch_host_single(re_c, host + doc_offsets[d0], (size_t)(doc_offsets[d1] - doc_offsets[d0]), rebased.data(), d1 - d0,
+                                    doc_stride, out_start_end + 2 * d0);
+  });
+}
+
+// N contiguous parts of the text, every inner cut right after a byte no match can contain; empty when the pattern
+// has no such byte or the text none near the nominal cuts
+static std::vector<int64_t> device_cuts(const mrx_regex *re, const uint8_t *host, int64_t n, int N) {
+  bool dead[256];
+  std::vector<int64_t> c{0};
+  if (!dead_bytes(re->prog, dead)) return {};
+  for (int d = 1; d < N; ++d) {
+    const int64_t nominal = (int64_t)((unsigned __int128)n * d / N);
+    int64_t cut = -1;
+    for (int64_t q = std::max(nominal, c.back()); q < std::min<int64_t>(n, nominal + (4ll << 20)); ++q)
+      if (dead[host[q]]) { cut = q + 1; break; }
+    if (cut < 0 || cut >= n) return {};
+    c.push_back(cut);
+  }
+  c.push_back(n);
+  return c;
+}
+
+extern "C" int mrx_sub_host(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const uint8_t *host,
+                            size_t n, mrx_bytes *out) {
+  std::vector<int64_t> cuts;
+  if (g_multi > 1 && re_c && out && host && count == 0 && n >= (size_t)g_multi * kMultiMinBytes)
+    cuts = device_cuts(re_c, host, (int64_t)n, g_multi);
+  if (cuts.empty()) return sub_host_single(re_c, repl, repl_n, count, host, n, out);
+  int rc = require_device();
+  if (rc) return rc;
+  std::memset(out, 0, sizeof *out);
+  const int N = g_multi;
+  std::vector<mrx_bytes> parts((size_t)N);
+  rc = run_on_devices(N, [&](int d) {
+    return sub_host_single(re_c, repl, repl_n, 0, host + cuts[(size_t)d], (size_t)(cuts[(size_t)d + 1] - cuts[(size_t)d]), &parts[(size_t)d]);
+  });
+  auto free_parts = [&]() { for (mrx_bytes &p : parts) mrx_bytes_free(&p); };
+  if (rc) { free_parts(); return rc; }
+  size_t total = 0;
+  std::vector<size_t> at((size_t)N);
+  for (int d = 0; d < N; ++d) { at[(size_t)d] = total; total += parts[(size_t)d].n; }
+  void *h = nullptr;
+  if ((rc = host_alloc(total + 1, &h))) { free_parts(); return rc; }
+  {
+    std::vector<std::thread> threads;
+    for (int d = 0; d < N; ++d)
+      threads.emplace_back([&, d]() { if (parts[(size_t)d].n) std::memcpy((uint8_t *)h + at[(size_t)d], parts[(size_t)d].bytes, parts[(size_t)d].n); });
+    for (std::thread &t : threads) t.join();
+  }
+  free_parts();
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = h;
+  out->_owner = own;
+  out->bytes = (uint8_t *)h;
+  out->n = total;
+  out->location = MRX_OUT_HOST;
+  return MRX_OK;
+}
+
+extern "C" int mrx_split_host(const mrx_regex *re_c, const uint8_t *host, size_t n, int64_t maxsplit, mrx_pieces *out) {
+  std::vector<int64_t> cuts;
+  if (g_multi > 1 && re_c && out && host && maxsplit == 0 && n >= (size_t)g_multi * kMultiMinBytes)
+    cuts = device_cuts(re_c, host, (int64_t)n, g_multi);
+  if (cuts.empty()) return split_host_single(re_c, host, n, maxsplit, out);
+  int rc = require_device();
+  if (rc) return rc;
+  std::memset(out, 0, sizeof *out);
+  const int N = g_multi;
+  std::vector<mrx_pieces> parts((size_t)N);
+  rc = run_on_devices(N, [&](int d) {
+    return split_host_single(re_c, host + cuts[(size_t)d], (size_t)(cuts[(size_t)d + 1] - cuts[(size_t)d]), 0, &parts[(size_t)d]);
+  });
+  auto free_parts = [&]() { for (mrx_pieces &p : parts) mrx_pieces_free(&p); };
+  if (rc) { free_parts(); return rc; }
+  // a cut follows a byte that belongs to a piece: the last piece of a part and the first piece of the next part are
+  // one piece of the whole text.  Part d contributes its piece bytes and its INNER piece boundaries.
+  size_t nbytes = 0, nsep = 0;
+  std::vector<size_t> at_b((size_t)N), at_s((size_t)N);
+  for (int d = 0; d < N; ++d) {
+    at_b[(size_t)d] = nbytes; at_s[(size_t)d] = nsep;
+    nbytes += (size_t)parts[(size_t)d].offsets[parts[(size_t)d].n];
+    nsep += parts[(size_t)d].n - 1;
+  }
+  void *hb = nullptr, *ho = nullptr;
+  if ((rc = host_alloc(nbytes + 1, &hb))) { free_parts(); return rc; }
+  if ((rc = host_alloc(sizeof(int64_t) * (nsep + 2), &ho))) { host_release(hb); free_parts(); return rc; }
+  {
+    std::vector<std::thread> threads;
+    for (int d = 0; d < N; ++d)
+      threads.emplace_back([&, d]() {
+        const mrx_pieces &p = parts[(size_t)d];
+        const size_t pb = (size_t)p.offsets[p.n];
+        if (pb) std::memcpy((uint8_t *)hb + at_b[(size_t)d], p.bytes, pb);
+        int64_t *dst = (int64_t *)ho + 1 + at_s[(size_t)d];
+        for (size_t i = 1; i < p.n; ++i) dst[i - 1] = p.offsets[i] + (int64_t)at_b[(size_t)d];
+      });
+    for (std::thread &t : threads) t.join();
+  }
+  free_parts();
+  ((int64_t *)ho)[0] = 0;
+  ((int64_t *)ho)[nsep + 1] = (int64_t)nbytes;
+  OwnedOut *own = new OwnedOut();
+  own->host[0] = hb;
+  own->host[1] = ho;
+  out->_owner = own;
+  out->bytes = (uint8_t *)hb;
+  out->offsets = (int64_t *)ho;
   out->n = nsep + 1;
   out->location = MRX_OUT_HOST;
   return MRX_OK;

@@ -961,3 +961,64 @@ def test_fused_split_c5_corpus_tiles_and_long_runs(monkeypatch):
     # more separators than the first one makes the kernel run twice
     dense = np.frombuffer(b"a,b,c,d," * 40_000, dtype=np.uint8)
     assert _check_split(rx, orx, dense) is not None
+
+
+# ---- multi-device mode behind the C ABI (mrx_init_multi): one call, every GPU of the box --------------------------
+def _needs_gpus(n):
+    return pytest.mark.skipif(torch.cuda.device_count() < n, reason="needs %d GPUs" % n)
+
+
+@_needs_gpus(2)
+def test_multi_device_single_call_equals_single_device():
+    """findall / batch search / sub / split over host buffers: the sharded single call on 2 (and, when present, more)
+    GPUs returns bit for bit what one GPU returns -- class runs that straddle or swallow a shard included."""
+    n_dev = min(torch.cuda.device_count(), 8)
+    MiB = 1 << 20
+    texts = {}
+    for config in ("c1", "c2", "c4", "c5"):
+        t = corpora.make(config, n_dev * 40 * MiB + 12345)
+        if config == "c1":   # a digit run across the first shard edge, and one that swallows the whole second shard
+            edge = t.numel() // n_dev
+            t[edge - 9:edge + 7] = ord("5")
+            if n_dev >= 3:
+                t[edge * 1 + 100:edge * 2 + 50] = ord("8")
+        pinned = torch.empty(t.numel(), dtype=torch.uint8, pin_memory=True)
+        pinned.copy_(t)
+        texts[config] = pinned
+    lines = torch.empty(n_dev * 300_000 * 128, dtype=torch.uint8, pin_memory=True)
+    lines.copy_(corpora.make("c3", n_dev * 300_000))
+
+    def run_all():
+        res = {}
+        for config in ("c1", "c2"):
+            rx = mr.CompiledRegex(corpora.CONFIGS[config]["pattern"])
+            res[config] = rx.match_all_host(texts[config].data_ptr(), texts[config].numel()).spans.copy()
+        rx = mr.CompiledRegex(corpora.CONFIGS["c4"]["pattern"])
+        hb = rx.sub_host(corpora.CONFIGS["c4"]["repl"], texts["c4"].data_ptr(), texts["c4"].numel())
+        res["c4"] = hb.array.copy()
+        hb.close()
+        rx = mr.CompiledRegex(corpora.CONFIGS["c5"]["pattern"])
+        hp = rx.split_host(texts["c5"].data_ptr(), texts["c5"].numel())
+        res["c5"] = (hp.data.copy(), hp.offsets.copy())
+        hp.close()
+        rx = mr.CompiledRegex(corpora.CONFIGS["c3"]["pattern"])
+        out = np.empty(2 * n_dev * 300_000, dtype=np.int64)
+        res["c3"] = rx.search_batch_host(lines.data_ptr(), lines.numel(), out, doc_stride=128).copy()
+        return res
+
+    mr.clear_regex_cache()
+    try:
+        mr.init_multi(n_dev)
+        assert mr.device_count() == n_dev
+        multi = run_all()
+    finally:
+        mr.shutdown()
+        mr.init(0)
+    single = run_all()
+    for config in ("c1", "c2", "c3", "c4"):
+        assert np.array_equal(multi[config], single[config]), config
+    assert np.array_equal(multi["c5"][0], single["c5"][0]) and np.array_equal(multi["c5"][1], single["c5"][1])
+    # and the single-device results are the oracle's (bounded prefix: the oracle is slow)
+    want = oracle.compile(corpora.CONFIGS["c1"]["pattern"]).findall(texts["c1"].numpy()[: 8 * MiB])
+    got = single["c1"][single["c1"][:, 1] <= 8 * MiB - 64]
+    assert np.array_equal(got, want[: len(got)])
