@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(kSandThreads, 2) k_sand(const SandParams prm) 
 
 template <int K, bool TAIL, int ADDR>
 static void launch_sand_t(const SandParams &p, int grid, cudaStream_t st) {
-  static int resident = 0;
+  static int resident_dev[kLaunchDevSlots] = {};
+  int &resident = resident_dev[launch_dev()];
   const int smem = (int)sizeof(SandShared<K>);
   if (!resident) {
     cudaFuncSetAttribute(k_sand<K, TAIL, ADDR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -376,7 +376,8 @@ __global__ void __launch_bounds__(kThreads, 2) k_split(const SplitParams prm) {
 }
 
 void launch_split(const SplitParams &p, cudaStream_t st) {
-  static int resident = 0;
+  static int resident_dev[kLaunchDevSlots] = {};
+  int &resident = resident_dev[launch_dev()];
   const int smem = (int)sizeof(SplitShared);
   if (!resident) {
     cudaFuncSetAttribute(k_split, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -1874,7 +1874,8 @@ __global__ void __launch_bounds__(kThreads) k_assemble(const AsmParams p) {
 // host-side launchers
 template <int FILT>
 static void launch_scan_t(const ScanParams &p, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kLaunchDevSlots] = {};
+  bool &attr_set = attr_set_dev[launch_dev()];
   if (!attr_set) {
     cudaFuncSetAttribute(k_scan<FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(ScanShared));
     attr_set = true;
@@ -1909,7 +1910,8 @@ void launch_lines(LinesParams p, cudaStream_t st) {
                             (size_t)kReqWarps * ((size_t)kReqRing * pitch + kReqRing * sizeof(int64_t));
     if (staged && p.req_byte >= 0 && p.doc_stride <= 16 * kReqMaxVecs && req_smem <= 220 * 1024 &&
         !(env && env[0] == '0')) {
-      static size_t req_attr = 0;
+      static size_t req_attr_dev[kLaunchDevSlots] = {};
+      size_t &req_attr = req_attr_dev[launch_dev()];
       if (req_smem > req_attr) {
         cudaFuncSetAttribute(k_lines_req<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)req_smem);
         cudaFuncSetAttribute(k_lines_req<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)req_smem);
@@ -1924,7 +1926,8 @@ void launch_lines(LinesParams p, cudaStream_t st) {
     }
   }
   const int smem = (int)sizeof(LinesShared) + tables + (staged ? kThreads * pitch : 0);
-  static int attr_smem = 0;
+  static int attr_smem_dev[kLaunchDevSlots] = {};
+  int &attr_smem = attr_smem_dev[launch_dev()];
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_lines, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     attr_smem = smem;
@@ -1937,7 +1940,8 @@ void launch_lines(LinesParams p, cudaStream_t st) {
 }
 template <int FILT>
 static void launch_runs_t(const RunsParams &p, int grid, cudaStream_t st) {
-  static bool attr_set = false;
+  static bool attr_set_dev[kLaunchDevSlots] = {};
+  bool &attr_set = attr_set_dev[launch_dev()];
   if (!attr_set) {
     cudaFuncSetAttribute(k_runs<FILT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RunsShared));
     attr_set = true;
@@ -1954,7 +1958,8 @@ void launch_runs(const RunsParams &p, int grid, cudaStream_t st) {
 }
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st) {
   const int smem = (int)sizeof(DenseShared) + p.table_bytes;
-  static int attr_smem = 0, resident = 0;
+  static int attr_smem_dev[kLaunchDevSlots] = {}, resident_dev[kLaunchDevSlots] = {};
+  int &attr_smem = attr_smem_dev[launch_dev()], &resident = resident_dev[launch_dev()];
   if (smem > attr_smem) {
     cudaFuncSetAttribute(k_dense, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     cudaFuncSetAttribute(k_dense_first, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -2025,7 +2030,8 @@ void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, in
 }
 void launch_assemble(const AsmParams &p, cudaStream_t st) {
   if (p.total <= 0) return;
-  static bool attr_set = false;
+  static bool attr_set_dev[kLaunchDevSlots] = {};
+  bool &attr_set = attr_set_dev[launch_dev()];
   if (!attr_set) {
     cudaFuncSetAttribute(k_assemble, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(AsmShared));
     attr_set = true;

@@ -178,6 +178,16 @@ struct AsmParams {
   uint8_t *out;             // 16-byte aligned, at least total + 16 bytes
 };
 
+// Function attributes (opt-in dynamic shared memory) and occupancy are per DEVICE: the launchers keep what they have
+// set up in arrays indexed by the current device (multi-device mode launches from one worker thread per device, each
+// touching only its own slot).
+constexpr int kLaunchDevSlots = 16;
+inline int launch_dev() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & (kLaunchDevSlots - 1);
+}
+
 void launch_scan(const ScanParams &p, int grid, cudaStream_t st);
 void launch_lines(LinesParams p, cudaStream_t st);
 void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
