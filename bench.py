@@ -477,6 +477,76 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_single_process(args):
+    """Evidence for the multi-device mode of the C ABI (mrx_init_multi): ONE process, ONE calling thread, N GPUs;
+    every step is one host-buffer call of the public API on the whole N-shard corpus (end to end by construction:
+    pinned host input, host result).  Not the driver's contract line (that is one process per GPU under torchrun);
+    printed with "mode": "single-process"."""
+    import numpy as np
+    import torch
+
+    import mojo_regex_b200 as mr
+    from mojo_regex_b200 import corpora
+
+    n = args.gpus
+    assert "WORLD_SIZE" not in os.environ, "--single-process is not launched under torchrun"
+    mr.init_multi(n)
+    per_gpu = {"c1": 64 << 20, "c2": 1 << 30, "c3": 10_000_000, "c4": 1 << 30, "c5": 1 << 30}
+    out = {}
+    wanted = ["c2", "c1", "c3", "c4", "c5"] if args.configs == "all" else [c for c in args.configs.split(",") if c]
+    for config in wanted:
+        cfg = corpora.CONFIGS[config]
+        parts = [corpora.make(config, per_gpu[config], seed={"c1": 0xC1, "c2": 0xC2, "c3": 0xC3, "c4": 0xC4, "c5": 0xC5}[config] + 1000003 * r,
+                              device="cuda:0") for r in range(n)]
+        for p_ in parts:
+            if config in ("c4", "c5"):
+                p_[-1] = 32 if config == "c4" else 10
+        total = sum(p_.numel() for p_ in parts)
+        host = torch.empty(total, dtype=torch.uint8, pin_memory=True)
+        at = 0
+        for p_ in parts:
+            host[at:at + p_.numel()].copy_(p_)
+            at += p_.numel()
+        del parts
+        torch.cuda.synchronize()
+        rx = mr.compile_regex(cfg["pattern"])
+        res = np.empty(2 * n * per_gpu["c3"], dtype=np.int64) if config == "c3" else None
+
+        def step():
+            if cfg["op"] == "findall":
+                return len(rx.match_all_host(host.data_ptr(), total))
+            if cfg["op"] == "search_batch":
+                rx.search_batch_host(host.data_ptr(), total, res, doc_stride=128)
+                return n * per_gpu["c3"]
+            if cfg["op"] == "sub":
+                hb = rx.sub_host(cfg["repl"], host.data_ptr(), total)
+                k = hb.n
+                hb.close()
+                return k
+            hp = rx.split_host(host.data_ptr(), total)
+            k = hp.n
+            hp.close()
+            return k
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            units = step()
+        steps = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            units = step()
+        dt = (time.perf_counter() - t0) / steps
+        out[config] = {"value": total / dt / 1e9, "unit": "GB/s", "ms_per_step": dt * 1e3, "bytes_per_step": int(total),
+                       "units_per_step": int(units), "steps": steps}
+        del host
+    h = out[wanted[0]]
+    print(json.dumps({"mode": "single-process", "metric": "input GB/s scanned", "value": h["value"], "unit": "GB/s", "n_gpus": n,
+                      "higher_is_better": True, "scaling": "weak", "dtype": "u8", "data": "synthetic",
+                      "config": {"workload": CONFIG_DESCR[wanted[0]] + " -- one mrx_*_host call per step over all GPUs "
+                                             "(mrx_init_multi), host buffers in and out"},
+                      "e2e": {"value": h["value"], "unit": "GB/s"}, "configs": out}))
+    mr.shutdown()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -488,12 +558,16 @@ def main():
                                                      "always included); the others go under \"configs\" of the line")
     ap.add_argument("--size", type=int, default=0, help="bytes per GPU (c3: lines); default = BASELINE size")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--single-process", action="store_true",
+                    help="N GPUs from ONE process through mrx_init_multi (evidence for the C ABI's multi-device mode)")
     ap.add_argument("--traffic", type=float, default=None,
                     help="dram bytes per launch of the dominant kernel from an ncu --set full capture")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":
         run_reference(args)
+    elif args.single_process:
+        run_single_process(args)
     else:
         run_gpu(args)
 

@@ -155,7 +155,7 @@ struct DrainSideStreams {
 
 // the tables of a regex as they sit in one device's HBM, and what that device learned about the texts
 struct RegexOnDevice {
-  DevProg *d_findall = nullptr, *d_search = nullptr;
+  DevProg *d_findall = nullptr, *d_search = nullptr, *d_prefilter = nullptr;
   uint8_t *d_dense_findall = nullptr, *d_dense_search = nullptr;  // DenseHdr + table
   sand::Table *d_sand_findall = nullptr;                          // Shift-And table of the findall plan (k_sand)
   sepb::Table *d_sep_findall = nullptr;                           // class table of the fused split (k_split)
@@ -327,6 +327,7 @@ int ensure_uploaded(mrx_regex *re) {
   }
   if (!re->on().d_findall) { int rc = upload_devprog(re->prog, re->prog.findall, &re->on().d_findall); if (rc) return rc; }
   if (!re->on().d_search && !re->prog.search.unsupported) { int rc = upload_devprog(re->prog, re->prog.search, &re->on().d_search); if (rc) return rc; }
+  if (re->prog.search_via_prefilter && !re->on().d_prefilter) { int rc = upload_devprog(re->prog, re->prog.prefilter_plan, &re->on().d_prefilter); if (rc) return rc; }
   return MRX_OK;
 }
 
@@ -561,6 +562,7 @@ int select_list(DevSpans &pot, int64_t *keys, DevSpans &out) {
 }
 
 int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t out[2]);
+thread_local bool search_skip_prefilter = false;  // set while search_impl runs the search that follows the literal jump
 
 // Final ordered, selected match list for `pl` over the text's core window.
 int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const DevProg *dprog, DevSpans &out) {
@@ -602,6 +604,36 @@ int match_list(const mrx_regex *re, const mrx_text *t, const Plan &pl, const Dev
     case MRX_MODE_UNIFORM_RUN:
       return run_runs_list(job, out);
     default: {
+      if (&pl == &re->prog.search && re->prog.search_via_prefilter) {
+        // every potential match of the search plan, every occurrence of the prefilter literal, then the chain
+        // pos -> next literal -> next potential match (k_select_prefilter)
+        DevSpans pot, lits;
+        int rc = run_scan_list(job, false, pot, nullptr);
+        if (rc) return rc;
+        PoolBlock b_pot{pot.spans};
+        ListJob lj{re, t, &re->prog.prefilter_plan, re->on().d_prefilter, job.key_lo, job.key_hi, job.rebase};
+        if ((rc = run_scan_list(lj, false, lits, nullptr))) return rc;
+        PoolBlock b_lits{lits.spans};
+        if (pot.n == 0 || lits.n == 0) return MRX_OK;
+        const int64_t m = pot.n, tiles = (m + kThreads - 1) / kThreads;
+        DevTmp desc, sel;
+        PoolBlock b_out;
+        if ((rc = desc.get(sizeof(unsigned long long) * tiles))) return rc;
+        if ((rc = sel.get((size_t)m))) return rc;
+        if ((rc = dev_alloc(sizeof(int64_t) * 2 * m, &b_out.p))) return rc;
+        CUDA_TRY(cudaMemsetAsync(sel.p, 0, (size_t)m, g.stream));
+        CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+        CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+        CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+        launch_select_prefilter(pot.spans, m, lits.spans, lits.n, sel.as<uint8_t>(), g.stream);
+        launch_select_compact(pot.spans, sel.as<uint8_t>(), m, desc.as<unsigned long long>(), g.ticket, (int64_t *)b_out.p, g.scalars, g.stream);
+        g.launches += 2;
+        CUDA_TRY(cudaGetLastError());
+        if ((rc = read_scalars(0, 1))) return rc;
+        out.n = (int64_t)g.h_scalars[0];
+        out.spans = (int64_t *)b_out.take();
+        return MRX_OK;
+      }
       if (pl.direct) return run_scan_list(job, false, out, nullptr);
       DevSpans pot;
       int64_t *keys = nullptr;
@@ -622,6 +654,37 @@ int search_impl(const mrx_regex *re, const mrx_text *t, int64_t start, int64_t o
     return 0;
   }
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  if (re->prog.search_via_prefilter && !search_skip_prefilter) {
+    // matcher.mojo:784-796: c = first occurrence of the prefilter literal at or after start (none: no match), then
+    // match_next from c
+    if (start >= n) return 0;  // prefilter.mojo:421-422
+    const Plan &pre = re->prog.prefilter_plan;
+    ScanParams p{};
+    p.text = t->d; p.n = n; p.prog = re->on().d_prefilter; p.filt = make_filter(pre); p.mode = pre.mode;
+    p.search_start = start; p.key_lo = start; p.key_hi = n; p.out_kind = OUT_FIRST; p.best = g.scalars + 1;
+    launch_fill_u64(g.scalars + 1, 1, ~0ull, g.stream);
+    ++g.launches;
+    const int64_t origin = start & ~15ll, tiles = n_tiles_for(origin, n - 1);
+    int64_t done = 0, win = 64;
+    while (done < tiles) {
+      const int64_t cnt = std::min(win, tiles - done);
+      p.tile_origin = origin + done * kTile;
+      p.n_tiles = (int)cnt;
+      launch_scan(p, (int)cnt, g.stream);
+      ++g.launches;
+      CUDA_TRY(cudaGetLastError());
+      int rc = read_scalars(1, 1);
+      if (rc) return rc;
+      if (g.h_scalars[1] != ~0ull) break;
+      done += cnt;
+      win *= 4;
+    }
+    if (g.h_scalars[1] == ~0ull) return 0;
+    search_skip_prefilter = true;
+    const int rc = search_impl(re, t, (int64_t)g.h_scalars[1], out);
+    search_skip_prefilter = false;
+    return rc;
+  }
   if (pl.dense.valid && re->on().d_dense_search) {
     if (pl.mode == MRX_MODE_EXACT_LITERAL && start >= n) return 0;  // matcher.mojo:773-774
     if (start >= n) return 0;
@@ -1077,6 +1140,7 @@ void mrx_regex_free(mrx_regex *re) {
   for (RegexOnDevice &o : re->dev) {  // (UVA: a device pointer can be freed from any current device)
     if (o.d_findall) cudaFree(o.d_findall);
     if (o.d_search) cudaFree(o.d_search);
+    if (o.d_prefilter) cudaFree(o.d_prefilter);
     if (o.d_dense_findall) cudaFree(o.d_dense_findall);
     if (o.d_dense_search) cudaFree(o.d_dense_search);
     if (o.d_sand_findall) cudaFree(o.d_sand_findall);
@@ -1246,6 +1310,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if ((rc = ensure_uploaded(re))) return rc;
   const Plan &pl = re->prog.search;
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  if (re->prog.search_via_prefilter)
+    return fail(MRX_E_UNSUPPORTED, "batch search through a MemchrPrefilter whose literal is not a prefix of the match "
+                                   "(matcher.mojo:784-796): use mrx_search per document");
   if (n_docs == 0) return MRX_OK;
   const int64_t n = (int64_t)t->n;
   if (!doc_offsets && (int64_t)(n_docs - 1) > n / doc_stride) return fail(MRX_E_INVALID, "more fixed-size documents than the text holds");

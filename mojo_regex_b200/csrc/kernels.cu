@@ -1558,6 +1558,27 @@ __global__ void k_select_walk(const int64_t *spans, const int64_t *keys, const i
   }
 }
 
+// The restart chain of match_next behind a MemchrPrefilter (matcher.mojo:784-796 inside the loops of sub / findall
+// callers): pos -> c = next occurrence of the literal at or after pos -> the first potential match starting at or
+// after c -> pos = its end (one past its start for an empty match).  One thread walks the two sorted lists; this path
+// serves patterns whose prefilter literal is not a prefix of the match, a corner of the reference's behaviour
+// (SURVEY appendix B-10), not a throughput path.
+__global__ void k_select_prefilter(const int64_t *spans, int64_t m, const int64_t *lits, int64_t l, uint8_t *sel) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  int64_t pos = 0, i = 0, j = 0;
+  while (true) {
+    while (j < l && lits[2 * j] < pos) ++j;
+    if (j == l) break;
+    const int64_t c = lits[2 * j];
+    while (i < m && spans[2 * i] < c) ++i;
+    if (i == m) break;
+    sel[i] = 1;
+    const int64_t s = spans[2 * i], e = spans[2 * i + 1];
+    pos = e > s ? e : s + 1;
+    ++i;
+  }
+}
+
 __global__ void k_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
                                  unsigned int *ticket, int64_t *out, unsigned long long *total, int n_tiles) {
   __shared__ int s_tile;
@@ -2016,6 +2037,9 @@ void launch_select_prefix_max(const int64_t *spans, int64_t m, unsigned long lon
 void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel,
                         cudaStream_t st) {
   k_select_walk<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(spans, keys, pmax, m, sel);
+}
+void launch_select_prefilter(const int64_t *spans, int64_t m, const int64_t *lits, int64_t l, uint8_t *sel, cudaStream_t st) {
+  k_select_prefilter<<<1, 32, 0, st>>>(spans, m, lits, l, sel);
 }
 void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
                            unsigned int *ticket, int64_t *out, unsigned long long *total, cudaStream_t st) {

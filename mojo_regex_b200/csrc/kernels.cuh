@@ -209,6 +209,7 @@ void launch_select_prefix_max(const int64_t *spans, int64_t m, unsigned long lon
                               int64_t *pmax, cudaStream_t st);
 void launch_select_walk(const int64_t *spans, const int64_t *keys, const int64_t *pmax, int64_t m, uint8_t *sel,
                         cudaStream_t st);
+void launch_select_prefilter(const int64_t *spans, int64_t m, const int64_t *lits, int64_t l, uint8_t *sel, cudaStream_t st);
 void launch_select_compact(const int64_t *spans, const uint8_t *sel, int64_t m, unsigned long long *desc,
                            unsigned int *ticket, int64_t *out, unsigned long long *total, cudaStream_t st);
 void launch_seg_lengths(const int64_t *spans, int64_t M, int64_t n, int mode, int64_t repl_len,

@@ -656,10 +656,6 @@ void make_plans(Program &p) {
     se.cand[(uint8_t)p.exact[0]] = 1;
     se.direct = !literal_has_border(p.exact);
     choose_filter(se);
-  } else if (p.flag(BF_HAS_PREFILTER) && !p.flag(BF_HAS_ANCHORS_INFO)) {
-    se.mode = MRX_MODE_FIRST_CLASS;
-    se.unsupported = true;
-    se.why = "match_next goes through the MemchrPrefilter literal path (matcher.mojo:784-796), not built yet";
   } else if (p.flag(BF_START_ANCHOR)) {
     se.mode = MRX_MODE_ANCHORED;
     se.direct = true;
@@ -684,6 +680,37 @@ void make_plans(Program &p) {
   try_dense(p, fa);
   try_dense(p, se);
   build_reverse(p, se, se.rev);
+  // ---- match_next through the MemchrPrefilter: matcher.mojo:784-796
+  if (p.flag(BF_HAS_PREFILTER) && !p.flag(BF_HAS_ANCHORS_INFO) && !p.prefilter.empty() &&
+      !(p.flag(BF_EXACT_LITERAL) && !p.exact.empty())) {
+    // is the literal a prefix of every match?  (then "first match at or after the next literal" = "first match")
+    bool prefix = p.n_states > 0 && !p.start_accepting();
+    int st = p.start_state;
+    for (size_t i = 0; prefix && i < p.prefilter.size(); ++i) {
+      int live = 0, nxt = kDead;
+      for (int b = 0; b < 256; ++b) {
+        const int t = p.next(st, b);
+        if (t != kDead) { ++live; if (b == (uint8_t)p.prefilter[i]) nxt = t; }
+      }
+      prefix = live == 1 && nxt != kDead && (i + 1 == p.prefilter.size() || !p.accepting[nxt]);
+      st = nxt;
+    }
+    if (!prefix) {
+      if (se.unsupported || !(se.mode == MRX_MODE_FIRST_CLASS || se.mode == MRX_MODE_EVERY_POS || se.mode == MRX_MODE_LITERAL)) {
+        se.unsupported = true;
+        se.why = "match_next through the MemchrPrefilter (matcher.mojo:784-796) on a plan that is not an attempt plan";
+      } else {
+        p.search_via_prefilter = true;
+        Plan &pre = p.prefilter_plan;
+        pre = Plan();
+        pre.mode = MRX_MODE_EXACT_LITERAL;  // String.find semantics: every occurrence, overlapping ones included
+        pre.literal = p.prefilter;
+        pre.direct = true;
+        pre.cand[(uint8_t)p.prefilter[0]] = 1;
+        choose_filter(pre);
+      }
+    }
+  }
 }
 
 }  // namespace

@@ -114,6 +114,13 @@ struct Program {
   int32_t fixed_offsets[10] = {0}, fixed_widths[10] = {0};
   std::string blob;
   Plan findall, search;
+  // match_next through the MemchrPrefilter (matcher.mojo:784-796, prefilter.mojo:377-430): the search first jumps to
+  // the next occurrence of the prefilter literal and runs `search` from there (the engine starts AT the literal:
+  // matches that begin before a literal that is not a prefix are missed).  `prefilter_plan`
+  // finds the literal's occurrences.  When every match begins with the literal the jump changes nothing and the flag
+  // stays down.
+  bool search_via_prefilter = false;
+  Plan prefilter_plan;
 
   bool flag(uint32_t f) const { return (flags & f) != 0; }
   bool start_accepting() const { return n_states > 0 && accepting[start_state]; }

@@ -128,6 +128,11 @@ FUZZ = [
     (r"", "ab"),
     (r"\w+\s\w+", "ab_9 \t"),
     (r"[+]*\d+[-]*\d+", "+-019 "),
+    # match_next through the MemchrPrefilter (matcher.mojo:784-796): literal prefix / literal inside / at the end
+    (r"hello[a-z][A-Z]{2}", "heloAB "),
+    (r"[A-Z]{2}@x[a-z]", "AB@xa "),
+    (r"[a-z]hello[a-z]", "helo "),
+    (r"[a-z][A-Z]{2}ab", "abAB "),
 ]
 
 
