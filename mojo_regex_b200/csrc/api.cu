@@ -1310,9 +1310,6 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if ((rc = ensure_uploaded(re))) return rc;
   const Plan &pl = re->prog.search;
   if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
-  if (re->prog.search_via_prefilter)
-    return fail(MRX_E_UNSUPPORTED, "batch search through a MemchrPrefilter whose literal is not a prefix of the match "
-                                   "(matcher.mojo:784-796): use mrx_search per document");
   if (n_docs == 0) return MRX_OK;
   const int64_t n = (int64_t)t->n;
   if (!doc_offsets && (int64_t)(n_docs - 1) > n / doc_stride) return fail(MRX_E_INVALID, "more fixed-size documents than the text holds");
@@ -1351,7 +1348,7 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     }
     return MRX_OK;
   }
-  if (re->on().d_rev_search && re->on().d_search && !getenv("MRX_NO_LINES")) {
+  if (re->on().d_rev_search && re->on().d_search && !getenv("MRX_NO_LINES") && !re->prog.search_via_prefilter) {
     // reverse-automaton kernel: one thread per document, results written in place
     int64_t *outp = out_start_end;
     if (location == MRX_OUT_HOST) {
@@ -1378,13 +1375,32 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if ((rc = d_best.get(sizeof(unsigned long long) * n_docs))) return rc;
   launch_fill_u64(d_best.as<unsigned long long>(), (int64_t)n_docs, ~0ull, g.stream);
   ++g.launches;
+  const int64_t tiles = n_tiles_for(0, n - 1);
+  DevTmp d_lit;
+  if (re->prog.search_via_prefilter) {
+    // matcher.mojo:784-796 per document: the first occurrence of the prefilter literal, then the search from there
+    const Plan &pre = re->prog.prefilter_plan;
+    if ((rc = d_lit.get(sizeof(unsigned long long) * n_docs))) return rc;
+    launch_fill_u64(d_lit.as<unsigned long long>(), (int64_t)n_docs, ~0ull, g.stream);
+    ++g.launches;
+    if (tiles > 0) {
+      ScanParams q{};
+      q.text = t->d; q.n = n; q.prog = re->on().d_prefilter; q.filt = make_filter(pre); q.mode = pre.mode;
+      q.tile_origin = 0; q.key_lo = 0; q.key_hi = n; q.search_start = -1; q.n_tiles = (int)tiles;
+      q.out_kind = OUT_BATCH; q.doc_offsets = offs_dev; q.doc_stride = doc_stride; q.n_docs = (int64_t)n_docs;
+      q.doc_best = d_lit.as<unsigned long long>();
+      launch_scan(q, (int)tiles, g.stream);
+      ++g.launches;
+    }
+  }
   ScanParams p{};
   p.text = t->d; p.n = n; p.prog = re->on().d_search; p.filt = make_filter(pl); p.mode = pl.mode;
   p.tile_origin = 0; p.key_lo = 0; p.key_hi = n; p.search_start = -1;
   p.out_kind = OUT_BATCH; p.doc_offsets = offs_dev; p.doc_stride = doc_stride; p.n_docs = (int64_t)n_docs;
   p.doc_best = d_best.as<unsigned long long>();
+  p.doc_min = re->prog.search_via_prefilter ? d_lit.as<unsigned long long>() : nullptr;
   p.dominated = (re->search_dominated || pl.mode == MRX_MODE_CLASS_RUNS) ? 1 : 0;
-  const int64_t tiles = n_tiles_for(0, n - 1);
+  if (re->prog.search_via_prefilter) p.dominated = 0;  // a dominated candidate may be the first one at or after the literal
   if (tiles > 0) {
     p.n_tiles = (int)tiles;
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);

@@ -371,6 +371,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
             at.lo = doc_lo;
             at.n = prm.doc_offsets ? prm.doc_offsets[cur_doc + 1] : min(doc_lo + prm.doc_stride, prm.n);
           }
+          if (ok && prm.out_kind == OUT_BATCH && prm.doc_min) {  // matcher.mojo:784-796: the search starts at the literal
+            const unsigned long long lit = prm.doc_min[cur_doc];
+            if (lit == ~0ull || (unsigned long long)(pos - doc_lo) < (lit >> 32)) ok = false;
+          }
           if (ok && prm.dominated && pos > at.lo && pos > prm.search_start && pos < prm.n && cand[at.tv.at(pos - 1)]) ok = false;
           if (ok) hit = try_candidate(prm, at, pos, h);
         }

@@ -41,6 +41,8 @@ struct ScanParams {
   int64_t doc_stride;
   int64_t n_docs;
   unsigned long long *doc_best;
+  const unsigned long long *doc_min;  // OUT_BATCH behind a MemchrPrefilter: (first literal occurrence of the document,
+                                      // relative) << 32 | its end, ~0 = none; attempts before it are not made
 };
 
 struct RunsParams {
