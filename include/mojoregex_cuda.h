@@ -90,6 +90,9 @@ typedef struct {
   int32_t search_rev_states;           /* > 0: batch search runs the reverse-automaton kernel (k_lines)  */
   int32_t search_skip_byte;            /* >= 0: a byte every match contains, read off the automaton; the    */
                                        /* batch kernel does not walk documents without it (-1 = none)       */
+  int32_t findall_sand;                /* 1 = findall runs the Shift-And literal-set kernel (k_sand)         */
+  int32_t split_fused;                 /* 1 = split runs fused (k_split): the pattern has the shape X* c Y*  */
+  int32_t search_via_prefilter;        /* 1 = match_next jumps to the MemchrPrefilter literal first          */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */

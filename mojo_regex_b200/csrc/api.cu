@@ -1132,6 +1132,9 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
   o->findall_dense = p.findall.dense.valid; o->search_dense = p.search.dense.valid;
   o->search_rev_states = p.search.rev.valid ? p.search.rev.n_rev : 0;
   o->search_skip_byte = p.search.rev.valid ? p.search.rev.req_byte : -1;
+  o->findall_sand = p.findall.sand_valid ? 1 : 0;
+  o->split_fused = p.findall.sep_valid ? 1 : 0;
+  o->search_via_prefilter = p.search_via_prefilter ? 1 : 0;
   return MRX_OK;
 }
 

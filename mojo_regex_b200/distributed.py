@@ -425,7 +425,8 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
         kernel = getattr(shard, "_findall_kernel", None)
         if kernel is None:
             info = rx.info()
-            kernel = "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan")
+            kernel = ("k_sand" if info.findall_sand and not os.environ.get("MRX_NO_SAND") else
+                      "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan"))
             shard._findall_kernel = kernel
         return OpResult(ds.n, n + 16 * ds.n, kernel, ds, g)
     if cfg["op"] == "search_batch":
@@ -455,7 +456,8 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
         if multi:
             g = _gather_for(2, dev)
             g.gather([pc.n, total])
-        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_scan+k_seg_lengths+k_assemble", pc, g)
+        fused = rx.info().split_fused and not os.environ.get("MRX_NO_FUSED_SPLIT")
+        return OpResult(pc.n, n + total + 8 * (pc.n + 1), "k_split" if fused else "k_scan+k_seg_lengths+k_assemble", pc, g)
     raise ValueError(cfg["op"])
 
 
