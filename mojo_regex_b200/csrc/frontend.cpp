@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 
 #include "../../include/mojoregex_cuda.h"
@@ -1178,6 +1179,212 @@ void compile_dfa(const Ast &a, RawDfa &d) {  // compile_dfa_pattern, dfa.mojo:23
   d.start_state = 0;
 }
 
+// ---- the NFA side: PikeVM program -> LazyDFA state sets, built eagerly -------------------------------------------
+// Patterns without a DFAEngine go to NFAMatcher (matcher.mojo:273-431).  Its match_first / match_next / match_all all
+// run on the LazyDFA (pikevm.mojo:682-987: leftmost-longest over the Thompson state sets, cached on demand) exactly when
+// the PikeVM program fits (pikevm.mojo:364-366), has no `$` (matcher.mojo:341-350) and the backtracking engine has no
+// fast path of its own (literal, leading / trailing `.*`: matcher.mojo:362-385, nfa.mojo:96-139).  For those patterns
+// the LazyDFA's reachable states are built here by subset construction and handed on as an ordinary table: an attempt
+// at a position is "walk, remember the last accepting position" (pikevm.mojo:806-850) -- the same loop the kernels run
+// for a DFAEngine table -- and the callers' loops are the every-position ones (pikevm.mojo:757-803).  `^` is refused:
+// the LazyDFA builds its start state at position 0 (pikevm.mojo:714), so the anchor would hold at every start position.
+enum PikeOp { P_BYTE, P_RANGE, P_CLASS, P_ANY, P_SPLIT, P_JUMP, P_MATCH, P_START, P_END };
+struct PikeInst { int op, a0, a1; };
+struct PikeProgram {
+  std::vector<PikeInst> ins;
+  std::vector<std::array<uint8_t, 256>> classes;
+  int emit(int op, int a0 = 0, int a1 = 0) { ins.push_back({op, a0, a1}); return (int)ins.size() - 1; }
+  int add_class(const std::array<uint8_t, 256> &t) {  // pikevm.mojo:102-111
+    for (size_t i = 0; i < classes.size(); ++i) if (classes[i] == t) return (int)i;
+    classes.push_back(t);
+    return (int)classes.size() - 1;
+  }
+};
+struct PikeCompiler {
+  const Ast &a;
+  PikeProgram &p;
+  void node(int id) {  // pikevm.mojo:142-166
+    const Node &n = a.at(id);
+    switch (n.kind) {
+      case K_GROUP: for (int c : n.kids) quantified(c); break;  // :169-173
+      case K_OR: alt(id); break;
+      case K_ELEMENT: if (a.has_value(id)) p.emit(P_BYTE, (uint8_t)a.value(id)[0]); break;  // :260-266
+      case K_DIGIT: case K_WORD: case K_SPACE: case K_RANGE: char_class(id); break;
+      case K_WILDCARD: p.emit(P_ANY); break;
+      case K_START: p.emit(P_START); break;
+      case K_END: p.emit(P_END); break;
+      default: break;
+    }
+  }
+  void quantified(int id) {  // :176-233
+    const int mn = a.at(id).mn, mx = a.at(id).mx;
+    if (mn == 1 && mx == 1) { node(id); return; }
+    if (mn == 0 && mx == 1) {
+      const int sp = p.emit(P_SPLIT);
+      const int body = (int)p.ins.size();
+      node(id);
+      p.ins[sp].a0 = body; p.ins[sp].a1 = (int)p.ins.size();
+      return;
+    }
+    if (mn == mx && mn > 1) { for (int i = 0; i < mn; ++i) node(id); return; }
+    if (mx > 0) {
+      for (int i = 0; i < mn; ++i) node(id);
+      std::vector<int> splits;
+      for (int i = 0; i < mx - mn; ++i) { splits.push_back(p.emit(P_SPLIT)); node(id); }
+      const int after = (int)p.ins.size();
+      for (int s2 : splits) { p.ins[s2].a0 = s2 + 1; p.ins[s2].a1 = after; }
+      return;
+    }
+    if (mx == -1) {
+      for (int i = 0; i < mn; ++i) node(id);
+      const int sp = p.emit(P_SPLIT);
+      const int body = (int)p.ins.size();
+      node(id);
+      p.emit(P_JUMP, sp);
+      p.ins[sp].a0 = body; p.ins[sp].a1 = (int)p.ins.size();
+    }
+  }
+  void alt(int id) {  // :236-257 (children without their quantifiers; the first two only)
+    const Node &n = a.at(id);
+    if (n.kids.empty()) return;
+    if (n.kids.size() == 1) { node(n.kids[0]); return; }
+    const int sp = p.emit(P_SPLIT);
+    const int left = (int)p.ins.size();
+    node(n.kids[0]);
+    const int jp = p.emit(P_JUMP);
+    const int right = (int)p.ins.size();
+    node(n.kids[1]);
+    p.ins[sp].a0 = left; p.ins[sp].a1 = right;
+    p.ins[jp].a0 = (int)p.ins.size();
+  }
+  void char_class(int id) {  // :274-333
+    const Node &n = a.at(id);
+    std::array<uint8_t, 256> t{};
+    auto add = [&](const std::string &m) { for (unsigned char c : m) t[c] = 1; };
+    if (n.kind == K_DIGIT) add(kDigits);
+    else if (n.kind == K_WORD) add(kWord);
+    else if (n.kind == K_SPACE) add(" \t\n\r\f");
+    else if (a.has_value(id)) {
+      std::string raw = a.value(id);
+      std::string in = (raw.size() >= 2 && raw.front() == '[' && raw.back() == ']') ? raw.substr(1, raw.size() - 2) : raw;
+      size_t j = 0;
+      while (j < in.size()) {
+        if (j + 1 < in.size() && in[j] == '\\') {
+          const char nx = in[j + 1];
+          if (nx == 's') add(" \t\n\r\f");
+          else if (nx == 'd') add(kDigits);
+          else if (nx == 'w') add(kWord);
+          else t[(uint8_t)nx] = 1;
+          j += 2;
+        } else if (j + 2 < in.size() && in[j + 1] == '-') {
+          for (int c = (uint8_t)in[j]; c <= (int)(uint8_t)in[j + 2]; ++c) t[c] = 1;
+          j += 3;
+        } else {
+          t[(uint8_t)in[j]] = 1;  // (a leading '^' of a negated class is a member too: the value is the raw slice)
+          ++j;
+        }
+      }
+    }
+    if (!n.positive) for (int c = 0; c < 256; ++c) t[c] = 1 - t[c];
+    p.emit(P_CLASS, p.add_class(t));
+  }
+};
+
+// epsilon closure (PikeVMEngine._add_state, pikevm.mojo:604-653) of a set of entry pcs; anchors never hold (programs
+// that have them are refused before this is called).  Result: sorted leaf pcs.
+std::vector<int> pike_closure(const PikeProgram &p, const std::vector<int> &entry) {
+  std::vector<uint8_t> seen(p.ins.size(), 0);
+  std::vector<int> stack(entry), leaves;
+  while (!stack.empty()) {
+    const int pc = stack.back();
+    stack.pop_back();
+    if (pc >= (int)p.ins.size() || seen[pc]) continue;
+    const PikeInst &in = p.ins[pc];
+    if (in.op == P_START || in.op == P_END) continue;
+    seen[pc] = 1;
+    if (in.op == P_SPLIT) { stack.push_back(in.a0); stack.push_back(in.a1); }
+    else if (in.op == P_JUMP) stack.push_back(in.a0);
+    else leaves.push_back(pc);
+  }
+  std::sort(leaves.begin(), leaves.end());
+  return leaves;
+}
+bool pike_consumes(const PikeProgram &p, int pc, int ch) {
+  const PikeInst &in = p.ins[pc];
+  switch (in.op) {
+    case P_BYTE: return ch == in.a0;
+    case P_CLASS: return p.classes[in.a0][ch] != 0;
+    case P_ANY: return ch != 10;
+    case P_RANGE: return ch >= in.a0 && ch <= in.a1;
+    default: return false;
+  }
+}
+
+// fills `d` with the LazyDFA of the pattern, or throws UnsupportedError saying which other engine the reference uses
+void compile_lazy_dfa(const Ast &ast, const std::string &pattern, const std::string &why, RawDfa &d) {
+  PikeProgram prog;
+  PikeCompiler pc{ast, prog};
+  const Node &root = ast.at(ast.root);
+  if (root.kind == K_RE && !root.kids.empty()) pc.node(root.kids[0]);  // pikevm.mojo:124-139
+  prog.emit(P_MATCH);
+  if (prog.ins.size() > 512) throw UnsupportedError(why + "; PikeVM program above 512 instructions: backtracking NFA");
+  for (const PikeInst &in : prog.ins) {
+    if (in.op == P_END) throw UnsupportedError(why + "; `$` in an NFA-routed pattern: served by OnePass / the backtracking NFA");
+    if (in.op == P_START)
+      throw UnsupportedError(why + "; `^` in an NFA-routed pattern: the LazyDFA builds its start state at position 0 (pikevm.mojo:714)");
+  }
+  Lit best;
+  if (best_literal(ast, best) &&  // NFAEngine.__init__, nfa.mojo:96-126
+      ((best.prefix && best.required && best.text.size() >= 1) || (best.required && best.text.size() >= 3)))
+    throw UnsupportedError(why + "; the backtracking NFA has a literal fast path for this pattern: it serves match_next / match_all");
+  auto ends_with = [&](const std::string &x) { return pattern.size() >= x.size() && pattern.compare(pattern.size() - x.size(), x.size(), x) == 0; };
+  const bool ends = ends_with(".*") && !ends_with("\\.*");  // nfa.mojo:129-139
+  const bool starts = pattern.compare(0, 2, ".*") == 0 && !(pattern.size() > 2 && (pattern[2] == '?' || pattern[2] == '*' || pattern[2] == '+'));
+  if (ends || starts) throw UnsupportedError(why + "; leading / trailing `.*`: the backtracking NFA's fast path serves it");
+  // subset construction over the sets the LazyDFA would cache
+  std::map<std::vector<int>, int> index;
+  std::vector<std::vector<int>> order;
+  order.push_back(pike_closure(prog, {0}));
+  index[order[0]] = 0;
+  d = RawDfa();
+  for (size_t i = 0; i < order.size(); ++i) {
+    const std::vector<int> cur = order[i];
+    std::array<int32_t, 256> row;
+    row.fill(-1);
+    std::map<std::vector<int>, int> move_state;  // move set -> DFA state
+    for (int ch = 0; ch < 256; ++ch) {
+      std::vector<int> mv;
+      for (int q : cur) if (pike_consumes(prog, q, ch)) mv.push_back(q + 1);
+      if (mv.empty()) continue;
+      auto it = move_state.find(mv);
+      if (it == move_state.end()) {
+        const std::vector<int> nxt = pike_closure(prog, mv);
+        int id = -1;
+        if (!nxt.empty()) {  // an empty set is LAZY_DFA_DEAD (pikevm.mojo:923-924)
+          auto f = index.find(nxt);
+          if (f == index.end()) {
+            if (order.size() >= 254) throw UnsupportedError(why + "; more than 254 LazyDFA states");
+            id = (int)order.size();
+            index[nxt] = id;
+            order.push_back(nxt);
+          } else {
+            id = f->second;
+          }
+        }
+        it = move_state.emplace(mv, id).first;
+      }
+      row[ch] = it->second;
+    }
+    d.trans.push_back(row);
+  }
+  for (const std::vector<int> &st : order) {
+    bool acc = false;
+    for (int q : st) acc = acc || prog.ins[q].op == P_MATCH;
+    d.accepting.push_back(acc ? 1 : 0);
+  }
+  d.start_state = 0;
+}
+
 int rare_required_byte(const Ast &a, const std::array<uint8_t, 256> &lookup) {  // matcher.mojo:122-165
   int id = a.root;
   if (a.at(id).kids.size() == 1) id = a.at(id).kids[0];
@@ -1270,13 +1477,19 @@ int compile_frontend(const std::string &pattern, RawDfa &dfa, RegexMeta &meta, s
         if (pattern.find('|') == std::string::npos && best.text.size() >= 2) meta.prefilter = best.text;
       }
     }
-    if (complexity != C_SIMPLE) {
-      err = std::string("pattern classified ") + (complexity == C_MEDIUM ? "MEDIUM" : "COMPLEX") +
-            ": served by the reference's NFA engines, not by the DFA path";
-      return MRX_E_UNSUPPORTED;
+    bool nfa_routed = false;
+    if (complexity != C_SIMPLE) {  // matcher.mojo:665-675: no DFAEngine -> NFAMatcher; served when that means its LazyDFA
+      compile_lazy_dfa(ast, pattern, std::string("pattern classified ") + (complexity == C_MEDIUM ? "MEDIUM" : "COMPLEX") + " -> NFA engines", dfa);
+      nfa_routed = true;
+    } else {
+      try {
+        compile_dfa(ast, dfa);
+      } catch (const UnsupportedError &e) {  // DFA compilation raised: NFA only (matcher.mojo:668-672)
+        compile_lazy_dfa(ast, pattern, e.what(), dfa);
+        nfa_routed = true;
+      }
     }
-    compile_dfa(ast, dfa);
-    if (!meta.has_anchors_info && dfa.has_matcher) meta.required_byte = rare_required_byte(ast, dfa.lookup);  // :684-693
+    if (!nfa_routed && !meta.has_anchors_info && dfa.has_matcher) meta.required_byte = rare_required_byte(ast, dfa.lookup);  // :684-693
     precompute_fixed_sub(pattern, meta);
     return MRX_OK;
   } catch (const ParseError &e) {

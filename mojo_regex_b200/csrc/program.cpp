@@ -454,8 +454,33 @@ bool detect_separator_shape(const Program &p, sepb::Table &out) {
   return true;
 }
 
+// S0 --C--> S1(acc) --C--> S1 and nothing else (`\s+`, `(\d+)` as the LazyDFA builds them): an attempt at a class byte
+// runs to the end of the class run, so the every-position loops (pikevm.mojo:757-803) return exactly the maximal runs
+// -- the class-runs plan, without one attempt per byte of every run.
+bool detect_class_plus(const Program &p, std::array<uint8_t, 256> &cls) {
+  if (p.n_states != 2 || p.start_accepting() || p.flag(BF_START_ANCHOR) || p.flag(BF_END_ANCHOR) || p.flag(BF_HAS_MATCHER)) return false;
+  const int s0 = p.start_state, s1 = 1 - s0;
+  if (!p.accepting[s1]) return false;
+  bool any = false;
+  for (int b = 0; b < 256; ++b) {
+    const int t0 = p.next(s0, b), t1 = p.next(s1, b);
+    if (t0 == kDead && t1 == kDead) { cls[b] = 0; continue; }
+    if (t0 != s1 || t1 != s1) return false;
+    cls[b] = 1;
+    any = true;
+  }
+  return any;
+}
+
 void plan_attempt_mode(const Program &p, Plan &pl, bool first_class) {
   pl.shortcut = p.flag(BF_HAS_MATCHER) && p.n_states > 0 && (p.flag(BF_SCAN_ELIGIBLE) || p.start_accepting());
+  if (!first_class && detect_class_plus(p, pl.cand)) {
+    pl.mode = MRX_MODE_CLASS_RUNS;
+    pl.try_at_end = false;
+    pl.direct = true;
+    choose_filter(pl);
+    return;
+  }
   if (first_class) {
     pl.mode = MRX_MODE_FIRST_CLASS;
     pl.cand = p.lookup;

@@ -1901,6 +1901,27 @@ class Compiled:
     fixed_sub_offsets: List[int] = field(default_factory=lambda: [0] * 10)
     fixed_sub_widths: List[int] = field(default_factory=lambda: [0] * 10)
     fixed_sub_concat: bool = False
+    nfa_routed: bool = False      # served by the reference's LazyDFA (oracle/nfa.py); `dfa` then holds its state sets
+    program: object = None        # ... and this the PikeVM program
+
+
+def _route_to_lazy_dfa(c: Compiled, ast: Node, why: str) -> None:
+    """matcher.mojo:665-675: no DFAEngine -> NFAMatcher.  Served here when that means the LazyDFA (oracle/nfa.py)."""
+    import sys
+
+    from . import nfa
+
+    prog, reason = nfa.route(c.pattern, ast, sys.modules[__name__])
+    if prog is None:
+        raise Unsupported("%s; %s" % (why, reason))
+    built = nfa.subset_construction(prog)
+    if built is None:
+        raise Unsupported("%s; more than 254 LazyDFA states" % why)
+    d = DFA()
+    d.trans, d.accepting, d.start_state = built
+    c.dfa = d
+    c.nfa_routed = True
+    c.program = prog
 
 
 def compile_regex(pattern: bytes) -> Compiled:
@@ -1930,10 +1951,13 @@ def compile_regex(pattern: bytes) -> Compiled:
         if b"|" not in pattern and best_opt is not None and len(best_opt) >= 2:
             c.prefilter_literal = best_opt
     if c.complexity != SIMPLE:
-        raise Unsupported("pattern classified %s -> NFA engines (out of scope)"
-                          % ("MEDIUM" if c.complexity == MEDIUM else "COMPLEX"))
-    c.dfa = compile_dfa_pattern(ast)  # raises Unsupported -> NFA fallback in the reference
-    if (not c.has_anchors_info) and c.dfa.matcher is not None:  # matcher.mojo:684-693
+        _route_to_lazy_dfa(c, ast, "pattern classified %s -> NFA engines" % ("MEDIUM" if c.complexity == MEDIUM else "COMPLEX"))
+    else:
+        try:
+            c.dfa = compile_dfa_pattern(ast)
+        except Unsupported as e:  # DFA compilation raised: NFA only (matcher.mojo:668-672)
+            _route_to_lazy_dfa(c, ast, str(e))
+    if (not c.nfa_routed) and (not c.has_anchors_info) and c.dfa.matcher is not None:  # matcher.mojo:684-693
         c.required_byte = find_rare_required_byte(ast, c.dfa.matcher.lookup)
     _precompute_fixed_sub(c)
     return c

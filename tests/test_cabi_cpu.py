@@ -62,7 +62,11 @@ PATTERNS = sorted({v["pattern"] for v in load_vectors()["vectors"]} | {
     r"a*", r"ab+", r"x?", r".+", r".?", r".", r"[0-9]+\.?[0-9]*", r"^[0-9]+\.?[0-9]*$", r"(?:00|33|44)[0-9]{2}",
     r"ab[0-9]{2}[a-z]{3}", r"\w+\s\w+", r"(\w+) (\w+)", r"[+]*\d+[-]*\d+", r"[abc]+", r"[^x]", r"a{2}b{3}",
     r".*", r"", r"^", r"$", r"^$", r"\t", r"a|b|c", r"(a|b)|(c|d)", r"[a-f0-9]{8}-[a-f0-9]{4}", r"\d{1,3}\.\d{1,3}",
-})
+    # the reference's LazyDFA route (NFAMatcher): subset construction in both front ends
+    r"\s+", r"(\d+)", r"\d|\w", r"(\w\d)+", r"(a|b)x", r"\w*@", r"\s", r"3[02]|40", r"3[02]|40|[68]9",
+    r"24|[346]|7[2-57-9]|9[2-9]", r"[^ab]+x", r"(a|ab)(c|bcd)", r"(ab)*c?", r"(?:hello) (\w+)", r"[\s\d]+x?", r"(x|y)*z{2,3}",
+    r"h[ae]llo", r"(hello)", r"^[a-z]+$", r"hello.world", r"\d*abc", r"a.c", r".*x", r"x.*", r"(a|b){300}",
+} | {v["pattern"] for v in load_vectors()["group_sub"]})
 
 
 @pytest.mark.parametrize("pattern", PATTERNS, ids=lambda p: p or "<empty>")

@@ -128,6 +128,19 @@ FUZZ = [
     (r"", "ab"),
     (r"\w+\s\w+", "ab_9 \t"),
     (r"[+]*\d+[-]*\d+", "+-019 "),
+    # the reference's LazyDFA route (NFAMatcher, matcher.mojo:273-431): tables from the eager subset construction
+    (r"\s+", "ab \t\n\x0b"),
+    (r"(\d+)", "019a "),
+    (r"\d|\w", "a9_ @"),
+    (r"(\w\d)+", "a1b2 _9x"),
+    (r"(a|b)x", "abx "),
+    (r"\w*@", "ab_@ "),
+    (r"3[02]|40|[68]9", "0234689 "),
+    (r"[^ab]+x", "abx^c "),
+    (r"(a|ab)(c|bcd)", "abcd "),
+    (r"(ab)*c?", "abc "),
+    (r"(?:ab) (\w+)", "ab _9"),
+    (r"(x|y)*z{2,3}", "xyz "),
     # match_next through the MemchrPrefilter (matcher.mojo:784-796): literal prefix / literal inside / at the end
     (r"hello[a-z][A-Z]{2}", "heloAB "),
     (r"[A-Z]{2}@x[a-z]", "AB@xa "),
@@ -1027,3 +1040,11 @@ def test_multi_device_single_call_equals_single_device():
     want = oracle.compile(corpora.CONFIGS["c1"]["pattern"]).findall(texts["c1"].numpy()[: 8 * MiB])
     got = single["c1"][single["c1"][:, 1] <= 8 * MiB - 64]
     assert np.array_equal(got, want[: len(got)])
+
+
+@pytest.mark.parametrize("v", DATA["group_sub"], ids=lambda v: "%s:%s" % (v["pattern"], v["src"].split("/")[-1]))
+def test_group_sub_is_refused_until_the_capture_kernel_exists(v):
+    rx = mr.compile_regex(v["pattern"])
+    with pytest.raises(mr.UnsupportedPattern):
+        rx.sub(v["repl"], v["text"])
+    assert rx.sub("<>", v["text"]) == oracle.compile(v["pattern"]).sub(b"<>", v["text"].encode())
