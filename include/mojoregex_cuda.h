@@ -93,6 +93,8 @@ typedef struct {
   int32_t findall_sand;                /* 1 = findall runs the Shift-And literal-set kernel (k_sand)         */
   int32_t split_fused;                 /* 1 = split runs fused (k_split): the pattern has the shape X* c Y*  */
   int32_t search_via_prefilter;        /* 1 = match_next jumps to the MemchrPrefilter literal first          */
+  int32_t sub_fused_width;             /* > 0: every match is a run of exactly this many bytes of one class: */
+                                       /* sub runs fused (k_subst) for replacements of up to 64 bytes         */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */

@@ -68,7 +68,8 @@ class Info(ctypes.Structure):
         "has_matcher", "scan_eligible", "required_byte", "is_wildcard_any", "is_exact_literal",
         "has_prefilter", "findall_mode", "search_mode", "findall_direct", "search_direct",
         "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat", "findall_dense", "search_dense",
-        "search_rev_states", "search_skip_byte", "findall_sand", "split_fused", "search_via_prefilter")]
+        "search_rev_states", "search_skip_byte", "findall_sand", "split_fused", "search_via_prefilter",
+        "sub_fused_width")]
 
 
 class DfaDesc(ctypes.Structure):

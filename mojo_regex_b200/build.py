@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libmojoregex_cuda.so")
-SOURCES = ["frontend.cpp", "program.cpp", "kernels.cu", "k_sand.cu", "k_split.cu", "api.cu"]
+SOURCES = ["frontend.cpp", "program.cpp", "kernels.cu", "k_sand.cu", "k_split.cu", "k_subst.cu", "api.cu"]
 HEADERS = ["frontend.hpp", "program.hpp", "kernels.cuh", "device.cuh", "sand.hpp", "sepbits.hpp", "../../include/mojoregex_cuda.h"]
 
 

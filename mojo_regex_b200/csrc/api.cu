@@ -1135,6 +1135,12 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
   o->findall_sand = p.findall.sand_valid ? 1 : 0;
   o->split_fused = p.findall.sep_valid ? 1 : 0;
   o->search_via_prefilter = p.search_via_prefilter ? 1 : 0;
+  {
+    const Plan &sp = p.search;
+    const bool ok = sp.mode == MRX_MODE_UNIFORM_RUN && sp.run_min == sp.run_max && sp.run_min >= 4 && sp.run_min <= 32 &&
+                    !p.flag(BF_WILDCARD_ANY);
+    o->sub_fused_width = ok ? sp.run_min : 0;
+  }
   return MRX_OK;
 }
 
@@ -1434,6 +1440,77 @@ static bool repl_has_group_refs(const uint8_t *r, size_t n) {
   return false;
 }
 
+// sub() in one pass (k_subst): every match of the plan is a run of exactly W bytes of one class, every replacement
+// R bytes long
+static int subst_stage_bytes(int W, int R) {
+  const int grow = R > W ? (R - W) * (kTile / W + 1) : 0;
+  return (kTile + grow + 32 + 127) & ~127;
+}
+static bool sub_fused_applies(const Program &p, const std::vector<int32_t> &flat) {
+  const Plan &pl = p.search;
+  if (pl.mode != MRX_MODE_UNIFORM_RUN || pl.run_min != pl.run_max) return false;
+  const int W = pl.run_min, R = (int)flat.size();
+  if (W < 4 || W > 32 || R > kSubstMaxRepl || p.flag(BF_WILDCARD_ANY)) return false;
+  for (int32_t src : flat)
+    if (src >= W) return false;
+  return subst_stage_bytes(W, R) <= kSubstMaxStage;
+}
+static int sub_fused(mrx_regex *re, const mrx_text *t, const std::vector<int32_t> &flat, int location, mrx_bytes *out,
+                     OwnedOut *own) {
+  const Plan &pl = re->prog.search;
+  const int64_t n = (int64_t)t->n;
+  const int W = pl.run_min, R = (int)flat.size();
+  const int64_t tiles = (n + kTile - 1) / kTile;
+  if (tiles > 0x7fffffff) return fail(MRX_E_INVALID, "text too large for one launch");
+  int rc;
+  DevTmp desc, trail, allf, carry, d_tpl;
+  if ((rc = desc.get(sizeof(unsigned long long) * tiles))) return rc;
+  if ((rc = trail.get(sizeof(long long) * tiles))) return rc;
+  if ((rc = allf.get(sizeof(int) * tiles))) return rc;
+  if ((rc = carry.get(sizeof(long long) * tiles))) return rc;
+  if ((rc = d_tpl.get(sizeof(int32_t) * (kSubstMaxRepl + 4)))) return rc;
+  if (R) CUDA_TRY(cudaMemcpyAsync(d_tpl.p, flat.data(), sizeof(int32_t) * R, cudaMemcpyHostToDevice, g.stream));
+  // every match grows the text by R - W bytes and there is at most one match per W bytes
+  const int64_t out_bound = n + (R > W ? (int64_t)(R - W) * (n / W) : 0);
+  void *d_out = nullptr;
+  if ((rc = dev_alloc((size_t)out_bound + 32, &d_out))) return rc;
+  own->dev[0] = d_out;
+  CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
+  CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 16, g.stream));
+  ProfOuter prof;
+  prof.arm();
+  launch_tile_trailing(t->d, n, 0, (int)tiles, re->on().d_search, trail.as<long long>(), allf.as<int>(), g.stream);
+  launch_carry_scan((int)tiles, trail.as<long long>(), allf.as<int>(), carry.as<long long>(), nullptr, g.stream);
+  SubstParams sp{};
+  sp.text = t->d; sp.n = n; sp.prog = re->on().d_search; sp.filt = make_filter(pl); sp.width = W; sp.repl_len = R;
+  sp.tpl = d_tpl.as<int32_t>(); sp.n_tiles = (int)tiles; sp.stage_bytes = subst_stage_bytes(W, R);
+  sp.tile_carry = carry.as<long long>(); sp.out = (uint8_t *)d_out; sp.desc = desc.as<unsigned long long>();
+  sp.ticket = g.ticket; sp.totals = g.scalars;
+  launch_subst(sp, g.stream);
+  if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+  prof.disarm();
+  g.launches += 3;
+  CUDA_TRY(cudaGetLastError());
+  if ((rc = read_scalars(0, 2))) return rc;
+  const int64_t total = (int64_t)g.h_scalars[0];
+  if (total > out_bound) return fail(MRX_E_CUDA, "fused sub wrote past its bound");
+  out->n = (size_t)total;
+  if (location == MRX_OUT_DEVICE) {
+    out->bytes = (uint8_t *)d_out;
+    return MRX_OK;
+  }
+  void *h = nullptr;
+  if ((rc = host_alloc((size_t)total + 1, &h))) return rc;
+  own->host[0] = h;
+  if (total) CUDA_TRY(cudaMemcpyAsync(h, d_out, (size_t)total, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  dev_release(d_out);
+  own->dev[0] = nullptr;
+  out->bytes = (uint8_t *)h;
+  return MRX_OK;
+}
+
 int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t count, const mrx_text *t,
             int location, mrx_bytes *out) {
   int rc = require_device();
@@ -1491,6 +1568,18 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
     return MRX_OK;
   }
   if ((rc = ensure_uploaded(re))) return bail(rc);
+  // flattened replacement: one int32 per output byte of the template (see k_assemble, k_subst)
+  std::vector<int32_t> flat;
+  flat.reserve((size_t)repl_len);
+  for (int k = 0; k < tpl.n_segs; ++k)
+    for (int i = 0; i < tpl.len[k]; ++i)
+      flat.push_back(tpl.group_off[k] >= 0 ? tpl.group_off[k] + i : -1 - (int32_t)repl[tpl.lit_off[k] + i]);
+  if (count <= 0 && sub_fused_applies(p, flat) && !getenv("MRX_NO_FUSED_SUB")) {
+    // a fixed-width chain over one class (config 4): finder, template expansion and output in one kernel
+    if ((rc = sub_fused(re, t, flat, location, out, own))) return bail(rc);
+    og.commit();
+    return MRX_OK;
+  }
   DevSpans ms;
   ProfOuter prof;
   prof.arm();
@@ -1519,12 +1608,6 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
   if (count > 0 && M > count) M = count;
   DevTmp d_tpl, d_offs, d_desc, d_bad, d_tseg;
   struct SpansGuard { int64_t *p; ~SpansGuard() { dev_release(p); } } guard{ms.spans};
-  // flattened replacement: one int32 per output byte of the template (see k_assemble)
-  std::vector<int32_t> flat;
-  flat.reserve((size_t)repl_len);
-  for (int k = 0; k < tpl.n_segs; ++k)
-    for (int i = 0; i < tpl.len[k]; ++i)
-      flat.push_back(tpl.group_off[k] >= 0 ? tpl.group_off[k] + i : -1 - (int32_t)repl[tpl.lit_off[k] + i]);
   if ((rc = d_tpl.get(sizeof(int32_t) * (flat.size() + 4)))) return bail(rc);
   if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(d_tpl.p, flat.data(), sizeof(int32_t) * flat.size(), cudaMemcpyHostToDevice, g.stream));
   const int64_t seg_tiles = (M + 1 + kSegTile - 1) / kSegTile;

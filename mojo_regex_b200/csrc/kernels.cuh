@@ -131,6 +131,26 @@ struct SplitParams {
   int *flags;                  // zeroed; bit 0: a run the window cannot measure, bit 1: overlapping separators
 };
 
+// Fused sub for fixed-width chain automata over one class (k_subst)
+constexpr int kSubstMaxRepl = 64;     // bytes of one expanded replacement
+constexpr int kSubstMaxStage = 72 * 1024;
+struct SubstParams {
+  const uint8_t *text;
+  int64_t n;
+  const DevProg *prog;         // cand[] = the class
+  Filter filt;
+  int32_t width;               // W: bytes per match, 4..32
+  int32_t repl_len;            // R: bytes per expanded replacement, <= kSubstMaxRepl
+  const int32_t *tpl;          // R entries: >= 0 byte of the match at this offset, < 0 literal byte -1 - value
+  int32_t n_tiles;             // ceil(n / kTile)
+  int32_t stage_bytes;         // shared-memory staging: >= kTile + max(0, R - W) * (kTile / W + 1) + 32
+  const long long *tile_carry; // in-class bytes immediately before every tile (k_tile_trailing + k_carry_scan)
+  uint8_t *out;                // n + max(0, R - W) * (n / W) + 16 bytes
+  unsigned long long *desc;    // one word per tile, zeroed: (1 << 62) | matches that start in the tile
+  unsigned int *ticket;        // zeroed
+  unsigned long long *totals;  // [0] output bytes, [1] matches
+};
+
 // Per-document search (k_lines): one thread per document.
 struct LinesParams {
   const uint8_t *text;
@@ -196,6 +216,7 @@ void launch_runs(const RunsParams &p, int grid, cudaStream_t st);
 void launch_dense(const DenseParams &p, int grid, cudaStream_t st);
 void launch_sand(const SandParams &p, int k, bool tail, int grid, cudaStream_t st);
 void launch_split(const SplitParams &p, cudaStream_t st);
+void launch_subst(const SubstParams &p, cudaStream_t st);
 void launch_tile_trailing(const uint8_t *text, int64_t n, int64_t origin, int n_tiles, const DevProg *prog,
                           long long *trail, int *all, cudaStream_t st);
 void launch_carry_scan(int n_tiles, const long long *trail, const int *all, long long *carry, const long long *carry0,

@@ -448,7 +448,8 @@ def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
         if multi:
             g = _gather_for(1, dev)
             g.gather([ob.n])
-        return OpResult(n, n + ob.n, "k_runs+k_seg_lengths+k_assemble", ob, g)
+        fused = rx.info().sub_fused_width > 0 and not os.environ.get("MRX_NO_FUSED_SUB")
+        return OpResult(n, n + ob.n, "k_subst" if fused else "k_runs+k_seg_lengths+k_assemble", ob, g)
     if cfg["op"] == "split":
         pc = rx.split_device(shard.text)
         total = int(pc.offsets_tensor()[-1].item())

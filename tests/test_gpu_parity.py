@@ -1048,3 +1048,88 @@ def test_group_sub_is_refused_until_the_capture_kernel_exists(v):
     with pytest.raises(mr.UnsupportedPattern):
         rx.sub(v["repl"], v["text"])
     assert rx.sub("<>", v["text"]) == oracle.compile(v["pattern"]).sub(b"<>", v["text"].encode())
+
+
+# ---- k_subst (fused sub for fixed-width chains over one class) against the oracle and against the general path -----
+def _sub_both_paths(pattern, repl, text, monkeypatch):
+    rx = mr.compile_regex(pattern)
+    monkeypatch.delenv("MRX_NO_FUSED_SUB", raising=False)
+    fused = rx.sub(repl, text)
+    monkeypatch.setenv("MRX_NO_FUSED_SUB", "1")
+    general = rx.sub(repl, text)
+    monkeypatch.delenv("MRX_NO_FUSED_SUB", raising=False)
+    return fused, general
+
+
+SUBST_CASES = [
+    # (pattern, replacement, width)                              what it stresses
+    (r"(\d{3})(\d{3})(\d{4})", rb"\1-\2-\3", 10),                # config 4: the text grows by 2 bytes per match
+    (r"(\d{3})(\d{3})(\d{4})", rb"\3\1", 10),                    # groups out of order, a group dropped: shrinks
+    (r"(\d{3})(\d{3})(\d{4})", rb"", 10),                        # matches deleted
+    (r"(\d{3})(\d{3})(\d{4})", rb"(\1) \2-\3 [\2\2\2] " + b"x" * 30, 10),   # 59 bytes per replacement
+    (r"\d{4}", rb"<#>", 4),                                      # the narrowest width, no group references
+    (r"[a-c]{32}", rb"_", 32),                                   # the widest
+    (r"([0-9a-f]{4})([0-9a-f]{3})", rb"<hex>", 7),               # class read from the table
+    (r"[ab]{5}", rb"ZZZZZZZ", 5),                                # needle filter
+]
+
+
+@pytest.mark.parametrize("pattern,repl,width", SUBST_CASES)
+def test_fused_sub_equals_oracle_and_general_path(pattern, repl, width, monkeypatch):
+    assert mr.compile_regex(pattern).info().sub_fused_width == width
+    orx = oracle.compile(pattern)
+    rng = np.random.default_rng(width * 131 + len(repl))
+    cls = {10: b"0123456789", 4: b"0123456789", 32: b"abc", 7: b"0123456789abcdef", 5: b"ab"}[width]
+    other = b" xyz-,."
+    texts = []
+    # runs of every length around the width and its multiples, separated by 1..3 other bytes
+    parts = []
+    for _ in range(30_000):
+        k = int(rng.integers(0, 4 * width + 3))
+        parts.append(bytes(cls[i] for i in rng.integers(0, len(cls), k)))
+        parts.append(bytes(other[i] for i in rng.integers(0, len(other), int(rng.integers(1, 4)))))
+    texts.append(b"".join(parts))
+    # sparse matches in long stretches of other bytes; a text that is one run; runs across tile and chunk edges
+    texts.append(b"".join(bytes(other[i] for i in rng.integers(0, len(other), int(rng.integers(0, 900)))) +
+                          bytes(cls[i] for i in rng.integers(0, len(cls), width)) for _ in range(600)))
+    texts.append(bytes(cls[i] for i in rng.integers(0, len(cls), 100_003)))
+    edge = bytearray(b"." * (3 * 36864 + 500))
+    for at in (36864, 2 * 36864, 36864 + 144 * 7, 3 * 36864 + 400):
+        for back in (1, width - 1, width, 2 * width + 3):
+            lo = at - back
+            edge[lo:lo + 3 * width + 1] = bytes(cls[i] for i in rng.integers(0, len(cls), 3 * width + 1))
+            fused, general = _sub_both_paths(pattern, repl, bytes(edge), monkeypatch)
+            assert fused == general == orx.sub(repl, np.frombuffer(bytes(edge), np.uint8)), (at, back)
+            edge[lo:lo + 3 * width + 1] = b"." * (3 * width + 1)
+    for n_cut in (0, 1, width - 1, width, 143, 144, 145, 36863, 36864, 36865):
+        texts.append(texts[0][:n_cut])
+        texts.append(texts[2][:n_cut])
+    for text in texts:
+        fused, general = _sub_both_paths(pattern, repl, text, monkeypatch)
+        want = orx.sub(repl, np.frombuffer(text, np.uint8)) if text else b""
+        assert len(fused) == len(want)
+        assert fused == want
+        assert general == want
+
+
+def test_fused_sub_on_the_config4_corpus_and_with_a_limit(monkeypatch):
+    cfg = corpora.CONFIGS["c4"]
+    text = _corpus("c4", 16 << 20)
+    fused, general = _sub_both_paths(cfg["pattern"], cfg["repl"], text, monkeypatch)
+    assert fused == general
+    small = text[: 1 << 20]
+    assert mr.compile_regex(cfg["pattern"]).sub(cfg["repl"], small) == oracle.compile(cfg["pattern"]).sub(cfg["repl"].encode(), small)
+    # a replacement limit is the general path's business
+    assert mr.compile_regex(cfg["pattern"]).sub(cfg["repl"], small, 5) == oracle.compile(cfg["pattern"]).sub(cfg["repl"].encode(), small, 5)
+
+
+def test_fused_sub_giant_run_spanning_many_tiles(monkeypatch):
+    """One run of digits over 40 tiles: the phase of every chunk comes from the carry pre-pass."""
+    n = 40 * 36864 + 77
+    text = np.full(n, ord("7"), dtype=np.uint8)
+    text[13] = ord("x")                       # the run starts at 14: starts at 14 + 10 k
+    text[n - 40] = ord("y")
+    fused, general = _sub_both_paths(r"(\d{3})(\d{3})(\d{4})", rb"\1-\2-\3", text, monkeypatch)
+    assert fused == general
+    body = (n - 40 - 14) // 10                # + one match in the 13 digits before the x, three in the 39 after the y
+    assert len(fused) == n + 2 * (body + 4)
