@@ -1444,7 +1444,7 @@ static bool repl_has_group_refs(const uint8_t *r, size_t n) {
 // R bytes long
 static int subst_stage_bytes(int W, int R) {
   const int grow = R > W ? (R - W) * (kTile / W + 1) : 0;
-  return (kTile + grow + 32 + 127) & ~127;
+  return (kTile + grow + 96 + 127) & ~127;  // + the bytes of a match that reaches past the tile, + the copy-out's read-ahead
 }
 static bool sub_fused_applies(const Program &p, const std::vector<int32_t> &flat) {
   const Plan &pl = p.search;

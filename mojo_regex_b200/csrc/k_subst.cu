@@ -27,17 +27,19 @@
 //      the next tile's text is already in flight.
 // Tiles by ticket; persistent CTAs, every CTA resident (a tile waits for the aggregates of the tiles before it).
 #include <cstddef>
+#include <cstdint>
 
 #include "kernels.cuh"
 
 namespace mrx {
 
+constexpr int32_t kTplSkip = INT32_MIN;  // template entry past the replacement's end
 constexpr int kSubstPost = 64;  // staged bytes after the tile (W <= 32: a match reaches at most 31 bytes over)
 
 struct SubstShared {
   alignas(128) uint8_t text[kTile + kSubstPost];
   uint8_t lut[256];            // class membership (FILT_LUT only)
-  int32_t tpl[kSubstMaxRepl];  // flattened template: >= 0: byte of the match at this offset, < 0: literal -1 - value
+  alignas(16) int32_t tpl[kSubstMaxRepl];  // flattened template: >= 0: byte of the match at this offset, < 0: literal -1 - value
   uint32_t head_bits[kThreads + 1];
   alignas(8) uint64_t bar;
   unsigned long long red_ws[kThreads / 32];
@@ -75,6 +77,19 @@ __device__ __forceinline__ void sts_u8(uint32_t addr, uint32_t v) {
   asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
+// out[16 i, +16) = bytes [4 HW + sh8 / 8 + 16 i, +16) of the staging buffer: two conflict-free 16-byte loads each
+template <int HW>
+__device__ __forceinline__ void subst_copy_body(const uint4 *sv, uint8_t *dst, int body, int sh8, int tid) {
+  for (int i = tid; i < body; i += kThreads) {
+    const uint4 a = sv[i], b = sv[i + 1];
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint4 o;
+    o.x = __funnelshift_r(w[HW], w[HW + 1], sh8); o.y = __funnelshift_r(w[HW + 1], w[HW + 2], sh8);
+    o.z = __funnelshift_r(w[HW + 2], w[HW + 3], sh8); o.w = __funnelshift_r(w[HW + 3], w[HW + 4], sh8);
+    *reinterpret_cast<uint4 *>(dst + 16 * i) = o;
+  }
+}
+
 template <int FILT>
 __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -89,7 +104,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
     fence_proxy_async();
   }
   sh.lut[tid] = prm.prog->cand[tid];  // kThreads == 256
-  if (tid < kSubstMaxRepl) sh.tpl[tid] = tid < R ? prm.tpl[tid] : 0;
+  if (tid < kSubstMaxRepl) sh.tpl[tid] = tid < R ? prm.tpl[tid] : kTplSkip;
   __syncthreads();
 
   auto issue_load = [&](int t) {  // thread 0 only
@@ -153,9 +168,10 @@ __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
     const int chunk_rel = tid * kChunk;
     const int cv = max(0, min(kChunk, valid - chunk_rel));
     uint32_t cb[5] = {0, 0, 0, 0, 0};
+    uint4 mine[kVecs];  // my chunk's text, kept for step 5
 #pragma unroll
     for (int v = 0; v < kVecs; ++v) {
-      const uint4 tv = *reinterpret_cast<const uint4 *>(sh.text + chunk_rel + 16 * v);
+      const uint4 tv = mine[v] = *reinterpret_cast<const uint4 *>(sh.text + chunk_rel + 16 * v);
       uint32_t m = subst_bits16<FILT>(tv, prm.filt, sh.lut);
       const int live = cv - 16 * v;
       if (live < 16) m &= live <= 0 ? 0u : ((1u << live) - 1u);
@@ -325,8 +341,7 @@ __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
       uint32_t o = smem_u32(sh.stage) + (uint32_t)base0;
 #pragma unroll
       for (int v = 0; v < kVecs; ++v) {
-        const uint4 tv = *reinterpret_cast<const uint4 *>(sh.text + chunk_rel + 16 * v);
-        const uint32_t ws[4] = {tv.x, tv.y, tv.z, tv.w};
+        const uint32_t ws[4] = {mine[v].x, mine[v].y, mine[v].z, mine[v].w};
 #pragma unroll
         for (int wi = 0; wi < 4; ++wi) {
           const int k = 4 * v + wi, bit = 4 * (k & 7);
@@ -346,10 +361,12 @@ __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
       const int s = list[m];
       const uint8_t *src0 = sh.text + s;
       uint8_t *dst = sh.stage + (s - sk0 + delta * m);
-#pragma unroll 4
-      for (int r = 0; r < R; ++r) {
-        const int32_t src = sh.tpl[r];
-        dst[r] = src >= 0 ? src0[src] : (uint8_t)(-1 - src);
+      for (int r = 0; r < R; r += 4) {  // (entries past R: kTplSkip)
+        const int4 t4 = *reinterpret_cast<const int4 *>(sh.tpl + r);
+        const int32_t src[4] = {t4.x, t4.y, t4.z, t4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (src[q] != kTplSkip) dst[r + q] = src[q] >= 0 ? src0[src[q]] : (uint8_t)(-1 - src[q]);
       }
     }
     const unsigned long long wsum = window_sum(tile);
@@ -374,14 +391,14 @@ __global__ void __launch_bounds__(kThreads, 2) k_subst(const SubstParams prm) {
       if (head > nout) head = nout;
       if (tid < head) dst[tid] = sh.stage[tid];
       const int body = (nout - head) >> 4;
-      const int sh8 = (head & 3) * 8;
-      const uint32_t *sw = reinterpret_cast<const uint32_t *>(sh.stage + (head & ~3));
-      for (int i = tid; i < body; i += kThreads) {
-        const uint32_t a0 = sw[4 * i], a1 = sw[4 * i + 1], a2 = sw[4 * i + 2], a3 = sw[4 * i + 3], a4 = sw[4 * i + 4];
-        uint4 o;
-        o.x = __funnelshift_r(a0, a1, sh8); o.y = __funnelshift_r(a1, a2, sh8);
-        o.z = __funnelshift_r(a2, a3, sh8); o.w = __funnelshift_r(a3, a4, sh8);
-        *reinterpret_cast<uint4 *>(dst + head + 16 * i) = o;
+      // 16 output bytes = stage[head + 16 i, +16): the aligned vectors i and i + 1, shifted by `head` bytes (uniform)
+      const uint4 *sv = reinterpret_cast<const uint4 *>(sh.stage);
+      uint8_t *body_dst = dst + head;
+      switch (head >> 2) {
+        case 0: subst_copy_body<0>(sv, body_dst, body, (head & 3) * 8, tid); break;
+        case 1: subst_copy_body<1>(sv, body_dst, body, (head & 3) * 8, tid); break;
+        case 2: subst_copy_body<2>(sv, body_dst, body, (head & 3) * 8, tid); break;
+        default: subst_copy_body<3>(sv, body_dst, body, (head & 3) * 8, tid); break;
       }
       const int done = head + 16 * body;
       if (tid < nout - done) dst[done + tid] = sh.stage[done + tid];

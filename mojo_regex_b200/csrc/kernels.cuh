@@ -143,7 +143,7 @@ struct SubstParams {
   int32_t repl_len;            // R: bytes per expanded replacement, <= kSubstMaxRepl
   const int32_t *tpl;          // R entries: >= 0 byte of the match at this offset, < 0 literal byte -1 - value
   int32_t n_tiles;             // ceil(n / kTile)
-  int32_t stage_bytes;         // shared-memory staging: >= kTile + max(0, R - W) * (kTile / W + 1) + 32
+  int32_t stage_bytes;         // shared-memory staging: >= kTile + max(0, R - W) * (kTile / W + 1) + 96
   const long long *tile_carry; // in-class bytes immediately before every tile (k_tile_trailing + k_carry_scan)
   uint8_t *out;                // n + max(0, R - W) * (n / W) + 16 bytes
   unsigned long long *desc;    // one word per tile, zeroed: (1 << 62) | matches that start in the tile
