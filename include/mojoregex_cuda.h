@@ -95,6 +95,10 @@ typedef struct {
   int32_t search_via_prefilter;        /* 1 = match_next jumps to the MemchrPrefilter literal first          */
   int32_t sub_fused_width;             /* > 0: every match is a run of exactly this many bytes of one class: */
                                        /* sub runs fused (k_subst) for replacements of up to 64 bytes         */
+  int32_t findall_leading_run;         /* 1 = the pattern begins with X+ and never reads X again: match_all   */
+                                       /* attempts only the first byte of every run of X (dfa.mojo:2097-2128) */
+  int32_t search_dominated;            /* 1 = match_next skips candidates whose predecessor is a candidate:   */
+                                       /* their attempt fails whenever the predecessor's does                 */
 } mrx_info;
 
 #define MRX_MODE_WILDCARD_ANY 0  /* `.*`                         matcher.mojo:809-813            */

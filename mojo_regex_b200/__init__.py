@@ -69,7 +69,7 @@ class Info(ctypes.Structure):
         "has_prefilter", "findall_mode", "search_mode", "findall_direct", "search_direct",
         "fixed_sub_total_width", "fixed_sub_num_groups", "fixed_sub_concat", "findall_dense", "search_dense",
         "search_rev_states", "search_skip_byte", "findall_sand", "split_fused", "search_via_prefilter",
-        "sub_fused_width")]
+        "sub_fused_width", "findall_leading_run", "search_dominated")]
 
 
 class DfaDesc(ctypes.Structure):

@@ -167,6 +167,7 @@ struct RegexOnDevice {
 struct mrx_regex {
   Program prog;
   bool search_dominated = false;
+  bool findall_leading_run = false;  // compute_leading_run(findall plan)
   RegexOnDevice dev[16];  // by device index (kMaxDevices); a worker thread only touches its own device's slot
   RegexOnDevice &on() { return dev[g_cur->device < 0 ? 0 : g_cur->device]; }
   const RegexOnDevice &on() const { return dev[g_cur->device < 0 ? 0 : g_cur->device]; }
@@ -362,6 +363,49 @@ bool compute_dominated(const Program &p, const Plan &pl) {
   return true;
 }
 
+// match_all (dfa.mojo:2097-2128) makes an attempt at every candidate that no earlier match covers.  For patterns that
+// begin with X+ and never read a byte of X again (`[a-z]+[0-9]+`, `a+b`) only the first byte of a run of X can start a
+// match that is reported.  Condition on the automaton: R = the states reached from the start state by bytes of X
+// alone; all of R agree on acceptance and on every byte outside X (so how many bytes of X an attempt has read does
+// not matter), and every state outside R and the start state is dead on X.  Then the attempt at the first byte of a
+// run walks the whole run inside R: it either covers the run or fails, and every later attempt in the run, being in
+// R at the end of the run too, fails the same way; no match ends inside a run it did not start in (it would have to
+// read a byte of X outside its leading run).  Without this a text that is one long run costs run^2 / 2 walked bytes.
+// (`a+1a?` is not in the family: "a1aa1" -> (0,3), (3,5), the second match starts on an `a` that follows an `a`.)
+bool compute_leading_run(const Program &p, const Plan &pl) {
+  if (pl.shortcut || p.start_accepting() || p.n_states == 0) return false;
+  if (pl.mode != MRX_MODE_FIRST_CLASS && pl.mode != MRX_MODE_EVERY_POS) return false;
+  const int nc = p.n_classes, s0 = p.start_state;
+  std::vector<uint8_t> ccls(nc, 0);
+  for (int b = 0; b < 256; ++b) if (pl.cand[b]) ccls[p.byte_class[b]] = 1;
+  for (int b = 0; b < 256; ++b) if ((pl.cand[b] != 0) != (ccls[p.byte_class[b]] != 0)) return false;
+  std::vector<uint8_t> inR(p.n_states, 0);
+  std::vector<int> work{s0};
+  int first = -1;
+  while (!work.empty()) {
+    const int s = work.back();
+    work.pop_back();
+    for (int a = 0; a < nc; ++a) {
+      if (!ccls[a]) continue;
+      const int to = p.trans[(size_t)s * nc + a];
+      if (to == kDead || to == s0) return false;  // a run of X must keep the attempt alive, and not restart it
+      if (!inR[to]) { inR[to] = 1; work.push_back(to); if (first < 0) first = to; }
+    }
+  }
+  if (first < 0) return false;
+  for (int s = 0; s < p.n_states; ++s) {
+    if (inR[s]) {
+      if (p.accepting[s] != p.accepting[first]) return false;
+      for (int a = 0; a < nc; ++a)
+        if (!ccls[a] && p.trans[(size_t)s * nc + a] != p.trans[(size_t)first * nc + a]) return false;
+    } else if (s != s0) {
+      for (int a = 0; a < nc; ++a)
+        if (ccls[a] && p.trans[(size_t)s * nc + a] != kDead) return false;
+    }
+  }
+  return true;
+}
+
 struct DevSpans {
   int64_t *spans = nullptr;  // pool block
   int64_t n = 0;
@@ -434,7 +478,8 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     ScanParams p{};
     p.text = job.t->d; p.n = n; p.tile_origin = origin; p.key_lo = job.key_lo; p.key_hi = job.key_hi;
     p.key_hi_inclusive_n = at_end ? 1 : 0; p.try_at_end = at_end ? 1 : 0; p.search_start = job.key_lo;
-    p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS; p.dominated = 0;
+    p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS;
+    p.dominated = (job.pl == &job.re->prog.findall && job.re->findall_leading_run) ? 1 : 0;
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
     p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
@@ -1040,6 +1085,7 @@ static int regex_from_blob(const std::string &blob, mrx_regex **out) {
     return fail(MRX_E_INVALID, err);
   }
   re->search_dominated = compute_dominated(re->prog, re->prog.search);
+  re->findall_leading_run = compute_leading_run(re->prog, re->prog.findall);
   *out = re;
   return MRX_OK;
 }
@@ -1141,6 +1187,8 @@ int mrx_regex_info(const mrx_regex *re, mrx_info *o) {
                     !p.flag(BF_WILDCARD_ANY);
     o->sub_fused_width = ok ? sp.run_min : 0;
   }
+  o->findall_leading_run = re->findall_leading_run ? 1 : 0;
+  o->search_dominated = re->search_dominated ? 1 : 0;
   return MRX_OK;
 }
 

@@ -96,6 +96,13 @@ struct Attempt {
     if ((p->flags & DF_END_ANCHOR) && q != n) return -1;
     return q;
   }
+  // sixteen bytes at q can be read from HBM with one aligned load (q is past the staged window)
+  __device__ __forceinline__ bool global16(int64_t q) const {
+    const bool ok = q + 16 <= n && (q < tv.s_begin || q >= tv.s_end) && (reinterpret_cast<uintptr_t>(tv.g + q) & 15) == 0;
+    // one thread streaming through HBM: pull the lines 4 KB ahead into L2 (the walk is latency-bound)
+    if (ok && (q & 127) == 0 && q + 4096 + 128 <= n) asm volatile("prefetch.global.L2 [%0];" ::"l"(tv.g + q + 4096));
+    return ok;
+  }
   __device__ __forceinline__ int64_t dfa(int64_t start) const {
     if (p->flags & DF_SHORTCUT) {
       int64_t e = simd_shortcut(start);
@@ -120,6 +127,21 @@ struct Attempt {
         q = s == 0 ? n : tv.s_begin + r;
       }
       while (q < n) {  // continuation past the staged window (rare) or start outside it
+        if (global16(q)) {
+          // a state that loops on its input (X+ inside a run longer than the tile): sixteen independent lookups
+          // instead of a chain of sixteen
+          const uint4 w = *reinterpret_cast<const uint4 *>(tv.g + q);
+          const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+          bool all = true;
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            all = all && *reinterpret_cast<const uint16_t *>(fwd + s + 2u * ((ws[i >> 2] >> (8 * (i & 3))) & 255u)) == s;
+          if (all) {
+            q += 16;
+            if (s & 4u) last = q;
+            continue;
+          }
+        }
         s = *reinterpret_cast<const uint16_t *>(fwd + s + 2u * tv.at(q));
         if (s == 0) break;
         ++q;
@@ -147,6 +169,19 @@ struct Attempt {
       if (dead) q = n;  // skip the slow continuation
     }
     while (q < n) {  // continuation past the staged window (rare) or start outside it
+      if (global16(q)) {  // (as above: skip sixteen bytes on which the state loops)
+        const uint4 w = *reinterpret_cast<const uint4 *>(tv.g + q);
+        const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
+        bool all = true;
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          all = all && p->trans[state * nc + p->byte_class[(ws[i >> 2] >> (8 * (i & 3))) & 255u]] == state;
+        if (all) {
+          q += 16;
+          if (p->accepting[state]) last = q;
+          continue;
+        }
+      }
       const int nx = p->trans[state * nc + p->byte_class[tv.at(q)]];
       if (nx == 0xFF) break;
       state = nx;
@@ -294,14 +329,25 @@ __global__ void __launch_bounds__(kThreads, 3) k_scan(const ScanParams prm) {
         const uint4 w = *reinterpret_cast<const uint4 *>(sh.text + rel0);
         const uint32_t ws[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-        for (int wi = 0; wi < 4; ++wi) m |= flags_to_nibble(filter_word<FILT>(ws[wi], prm.filt, cand)) << (4 * wi);
+        for (int wi = 0; wi < 4; ++wi) {
+          uint32_t fl;
+          if (FILT == FILT_NEEDLES && prm.dominated) {  // the pruning below needs exact flags
+            fl = swar_eq(ws[wi], prm.filt.n0);
+            if (prm.filt.n_needles > 1) fl |= swar_eq(ws[wi], prm.filt.n1);
+            if (prm.filt.n_needles > 2) fl |= swar_eq(ws[wi], prm.filt.n2);
+            if (prm.filt.n_needles > 3) fl |= swar_eq(ws[wi], prm.filt.n3);
+          } else {
+            fl = filter_word<FILT>(ws[wi], prm.filt, cand);
+          }
+          m |= flags_to_nibble(fl) << (4 * wi);
+        }
         if (pos0 + 16 > key_hi) m &= (1u << (int)(key_hi - pos0)) - 1u;
         if (pos0 < key_lo) m &= ~((1u << (int)(key_lo - pos0)) - 1u);
       }
-      // dominated candidates (search / batch search, exact filters only): a candidate whose predecessor
-      // byte is a candidate too can never be the leftmost match start -- drop it here, before the queue.
-      // Document starts and the search start itself are kept.
-      if (FILT != FILT_NEEDLES && prm.dominated && m && (prm.out_kind != OUT_BATCH || prm.doc_offsets == nullptr)) {
+      // dominated candidates (search / batch search; findall for the leading-run family, api.cu
+      // compute_leading_run): a candidate whose predecessor byte is a candidate too can never start a reported
+      // match -- drop it here, before the queue.  Document starts and the search start itself are kept.
+      if (prm.dominated && m && (prm.out_kind != OUT_BATCH || prm.doc_offsets == nullptr)) {
         const uint32_t prev = (pos0 > 0 && cand[at.tv.at(pos0 - 1)]) ? 1u : 0u;
         uint32_t keep = 0;
         if (prm.out_kind == OUT_BATCH) {

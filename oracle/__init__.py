@@ -49,7 +49,18 @@ class _CRegex(ctypes.Structure):
         ("fixed_total_width", ctypes.c_int32), ("fixed_num_groups", ctypes.c_int32),
         ("fixed_concat", ctypes.c_int32),
         ("fixed_offsets", ctypes.c_int32 * 10), ("fixed_widths", ctypes.c_int32 * 10),
+        ("nib_lookup", ctypes.c_uint8 * 32), ("nib_simd", ctypes.c_uint8 * 32), ("use_avx2", ctypes.c_int32),
     ]
+
+
+def _nibble_rows(table) -> list:
+    """scan.c member32: per low nibble the membership bits of the high nibbles 0-7 ([0..15]) and 8-15 ([16..31])."""
+    rows = [0] * 32
+    for b in range(256):
+        if table[b]:
+            lo, hi = b & 15, b >> 4
+            rows[lo + (16 if hi >= 8 else 0)] |= 1 << (hi & 7)
+    return rows
 
 
 class _Seg(ctypes.Structure):
@@ -128,6 +139,10 @@ class OracleRegex:
                 for i in range(256):
                     cr.lookup[i] = d.matcher.lookup[i]
                     cr.simd_cand[i] = d.matcher.simd_candidates[i]
+                for i, (a, b) in enumerate(zip(_nibble_rows(d.matcher.lookup), _nibble_rows(d.matcher.simd_candidates))):
+                    cr.nib_lookup[i] = a
+                    cr.nib_simd[i] = b
+        cr.use_avx2 = 0 if os.environ.get("ORACLE_NO_AVX2") else 1
         cr.simd_width = simd_width
         cr.is_wildcard_any = int(c.is_wildcard_match_any)
         cr.is_exact_literal = int(c.is_exact_literal)

@@ -34,6 +34,11 @@ typedef struct {
   /* CompiledRegex fixed-width sub metadata (matcher.mojo:946-962) */
   int32_t fixed_total_width, fixed_num_groups, fixed_concat;
   int32_t fixed_offsets[10], fixed_widths[10];
+  /* AVX2 forms of lookup[] and simd_cand[] (oracle/__init__.py fills them): per LOW nibble the membership bits of
+   * the high nibbles 0-7 ([0..15]) and 8-15 ([16..31]).  use_avx2 = 0 keeps the scalar loops (the tests hold the
+   * two equal); the host must support AVX2 as well. */
+  uint8_t nib_lookup[32], nib_simd[32];
+  int32_t use_avx2;
 } orx_regex;
 
 typedef struct {
@@ -88,12 +93,63 @@ static int64_t simd_search(const uint8_t *pat, int64_t m, const uint8_t *t, int6
   return -1;
 }
 
+#if defined(__x86_64__)
+#include <immintrin.h>
+/* The reference's loops are SIMD (SIMD_WIDTH bytes per step through two nibble shuffles, simd_ops.mojo:565-786); a
+ * scalar port would flatter the GPU.  Exact membership of 32 bytes in an arbitrary byte set: row = nib[low nibble]
+ * (bits of the high nibbles 0-7, or 8-15), tested against 1 << (high nibble & 7). */
+__attribute__((target("avx2"))) static inline uint32_t member32(const uint8_t *nib, const uint8_t *p) {
+  const __m256i v = _mm256_loadu_si256((const __m256i *)p);
+  const __m256i a_tab = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i *)nib));
+  const __m256i b_tab = _mm256_broadcastsi128_si256(_mm_loadu_si128((const __m128i *)(nib + 16)));
+  const __m256i bit_tab = _mm256_setr_epi8(1, 2, 4, 8, 16, 32, 64, -128, 1, 2, 4, 8, 16, 32, 64, -128,
+                                           1, 2, 4, 8, 16, 32, 64, -128, 1, 2, 4, 8, 16, 32, 64, -128);
+  const __m256i low = _mm256_and_si256(v, _mm256_set1_epi8(0x0f));
+  const __m256i high = _mm256_and_si256(_mm256_srli_epi16(v, 4), _mm256_set1_epi8(0x0f));
+  const __m256i row = _mm256_blendv_epi8(_mm256_shuffle_epi8(a_tab, low), _mm256_shuffle_epi8(b_tab, low), v);
+  const __m256i hit = _mm256_and_si256(row, _mm256_shuffle_epi8(bit_tab, high));
+  return ~(uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(hit, _mm256_setzero_si256()));
+}
+/* first position in [pos, end) whose byte is (want = 1) / is not (want = 0) in the set; end if none */
+__attribute__((target("avx2"))) static int64_t scan_set_avx2(const uint8_t *nib, const uint8_t *tab, const uint8_t *t,
+                                                             int64_t pos, int64_t end, int want) {
+  for (int k = 0; k < 4 && pos < end; ++k, ++pos)  /* the next hit is usually a few bytes away */
+    if ((tab[t[pos]] != 0) == (want != 0)) return pos;
+  while (pos + 32 <= end) {
+    uint32_t m = member32(nib, t + pos);
+    if (!want) m = ~m;
+    if (m) return pos + __builtin_ctz(m);
+    pos += 32;
+  }
+  while (pos < end && (tab[t[pos]] != 0) != (want != 0)) ++pos;
+  return pos;
+}
+static int have_avx2(void) {
+  static int v = -1;
+  if (v < 0) v = __builtin_cpu_supports("avx2") ? 1 : 0;
+  return v;
+}
+#else
+static int have_avx2(void) { return 0; }
+static int64_t scan_set_avx2(const uint8_t *nib, const uint8_t *tab, const uint8_t *t, int64_t pos, int64_t end, int want) {
+  (void)nib; (void)tab; (void)t; (void)end; (void)want;
+  return pos;
+}
+#endif
+
 /* CharacterClassSIMD.find_first_nibble_match, simd_ops.mojo:565-648.  The vector body
  * accepts simd_cand[] (exact for 1..3 ranges, nibble-product otherwise, :117-126); the
  * scalar tail -- the last (n - start) % SIMD_WIDTH bytes -- uses the exact lookup. */
 static int64_t find_first_nibble_match(const orx_regex *re, const uint8_t *t, int64_t start, int64_t n) {
   int64_t pos = start;
   const int64_t w = re->simd_width;
+  if (re->use_avx2 && have_avx2() && start < n) {
+    const int64_t body_end = start + (n - start) / w * w;  /* where the reference's vector body stops */
+    pos = scan_set_avx2(re->nib_simd, re->simd_cand, t, start, body_end, 1);
+    if (pos < body_end) return pos;
+    pos = scan_set_avx2(re->nib_lookup, re->lookup, t, body_end, n, 1);
+    return pos < n ? pos : -1;
+  }
   while (pos + w <= n) {
     for (int64_t i = 0; i < w; ++i)
       if (re->simd_cand[t[pos + i]]) return pos + i;
@@ -109,6 +165,7 @@ static int64_t find_first_nibble_match(const orx_regex *re, const uint8_t *t, in
 /* CharacterClassSIMD.count_consecutive_matches, simd_ops.mojo:650-786 (exact lookup) */
 static int64_t count_consecutive_matches(const orx_regex *re, const uint8_t *t, int64_t start, int64_t n) {
   int64_t pos = start;
+  if (re->use_avx2 && have_avx2() && start < n) return scan_set_avx2(re->nib_lookup, re->lookup, t, start, n, 0) - start;
   while (pos < n && re->lookup[t[pos]]) ++pos;
   return pos - start;
 }

@@ -310,3 +310,18 @@ def test_skip_byte_is_required_according_to_the_oracle():
                 break
         checked += 1 if hit else 0
     assert checked >= 6
+
+
+def test_leading_run_family_is_recognised_only_where_the_argument_holds():
+    """compute_leading_run (api.cu): findall attempts only the first byte of a run of X when the pattern begins with
+    X+ and never reads X again.  `a+1a?` begins with a+ but reads an `a` after the 1: "a1aa1" -> (0,3), (3,5), and
+    the second match starts on an `a` whose predecessor is an `a` -- pruning it would lose the match."""
+    yes = [r"[a-z]+[0-9]+", r"[ab]+c", r"\d+x", r"[a-z]+\d*"]
+    # (`a+b`: the reference's builder makes 0 -a-> 2 -b-> 3 -a-> 1, no loop and an `a` read after the b;
+    #  `[a-z]+@[0-9]+` goes through the required-byte plan, not through per-candidate attempts)
+    no = [r"a+1a?", r"a+b", r"[a-z]+@[0-9]+", r"[a-z]+[a-z0-9]+x", r"ab+", r"[a-z]+", r"(\d{3})(\d{3})(\d{4})",
+          r"hello", r"a*b"]
+    for pat in yes:
+        assert mr.CompiledRegex(pat).info().findall_leading_run == 1, pat
+    for pat in no:
+        assert mr.CompiledRegex(pat).info().findall_leading_run == 0, pat

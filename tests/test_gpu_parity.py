@@ -2,6 +2,7 @@
 
 Bit-exact bar: spans, sub output bytes and split pieces must be identical.
 """
+import os
 import random
 
 import numpy as np
@@ -1133,3 +1134,98 @@ def test_fused_sub_giant_run_spanning_many_tiles(monkeypatch):
     assert fused == general
     body = (n - 40 - 14) // 10                # + one match in the 13 digits before the x, three in the 39 after the y
     assert len(fused) == n + 2 * (body + 4)
+
+
+# ---- adversarial shapes: texts that are one giant run ---------------------------------------------------------------
+def _timed_ms(fn):
+    import time
+
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    r = fn()
+    torch.cuda.synchronize()
+    return r, (time.perf_counter() - t0) * 1e3
+
+
+def _record_timing(name, ms, nbytes):
+    """Wall time of adversarial cases, kept for DESIGN.md (gpurun_out/ is scratch: copied to profiles/ by hand)."""
+    import json
+
+    os.makedirs("gpurun_out", exist_ok=True)
+    path = "gpurun_out/adversarial_timings.json"
+    rec = json.load(open(path)) if os.path.exists(path) else {}
+    rec[name] = {"ms": round(ms, 3), "bytes": nbytes}
+    json.dump(rec, open(path, "w"), indent=1)
+
+
+def _spans_of(ds):
+    return ds.tensor().cpu().numpy().reshape(-1, 2)
+
+
+def test_adversarial_one_run_of_letters_then_a_digit():
+    """`[a-z]+[0-9]+` over a...a1: the reference makes ONE attempt (at 0) that walks the text; every other byte is a
+    candidate too, and without the leading-run pruning each would walk to the end of the text (n^2 / 2 bytes)."""
+    rx = mr.compile_regex(r"[a-z]+[0-9]+")
+    assert rx.info().findall_leading_run == 1
+    small = np.full(300_000, ord("a"), dtype=np.uint8)
+    small[-1] = ord("7")
+    assert np.array_equal(rx.match_all(small).spans, oracle.compile(r"[a-z]+[0-9]+").findall(small))
+    for n in (1 << 20, 32 << 20):
+        t = torch.full((n,), ord("a"), dtype=torch.uint8, device="cuda")
+        t[n - 2:] = ord("1")
+        txt = mr.Text.from_tensor(t)
+        ds, ms = _timed_ms(lambda: rx.match_all_device(txt))
+        assert _spans_of(ds).tolist() == [[0, n]]
+        _record_timing("letters_then_digit_findall_%dMiB" % (n >> 20), ms, n)
+        m, ms = _timed_ms(lambda: rx.match_next(txt, 5))
+        assert (m.start_idx, m.end_idx) == (5, n)
+        _record_timing("letters_then_digit_search_%dMiB" % (n >> 20), ms, n)
+    # no digit at all: the one attempt fails at the end of the text, the pruned ones would have failed too
+    t = torch.full((8 << 20,), ord("q"), dtype=torch.uint8, device="cuda")
+    txt = mr.Text.from_tensor(t)
+    ds, ms = _timed_ms(lambda: rx.match_all_device(txt))
+    assert _spans_of(ds).shape[0] == 0
+    _record_timing("letters_only_findall_8MiB", ms, 8 << 20)
+    assert rx.match_next(txt, 0) is None
+
+
+def test_adversarial_leading_run_family_on_mixed_runs():
+    """Runs of every length against the oracle: the pruned candidates never carry a reported match."""
+    rng = np.random.default_rng(77)
+    for pattern, alphabet in ((r"[a-z]+[0-9]+", b"abz019 -"), (r"[ab]+c", b"abcc d"), (r"\d+x", b"0189xx y"),
+                              (r"[a-z]+\d*", b"ab12 ,"), (r"a+1a?", b"a1 "), (r"a+b", b"ab ")):
+        orx, rx = oracle.compile(pattern), mr.compile_regex(pattern)
+        for n in (0, 1, 2, 17, 4097, 150_001):
+            text = np.frombuffer(alphabet, dtype=np.uint8)[rng.integers(0, len(alphabet), n)].copy()
+            assert np.array_equal(rx.match_all(text).spans, orx.findall(text)), (pattern, n)
+            t = mr.Text(text)
+            assert np.array_equal(_spans_of(rx.match_all_device(t)), orx.findall(text)), (pattern, n)
+
+
+def test_adversarial_all_digits_and_a_line_without_the_required_byte():
+    n = 256 << 20
+    t = torch.full((n,), ord("5"), dtype=torch.uint8, device="cuda")
+    txt = mr.Text.from_tensor(t)
+    rx = mr.compile_regex(r"\d+")
+    ds, ms = _timed_ms(lambda: rx.match_all_device(txt))
+    assert _spans_of(ds).tolist() == [[0, n]]
+    _record_timing("all_digits_findall_256MiB", ms, n)
+    # C4's pattern over all digits: every 10 bytes a match, the phase carried across 7282 tiles
+    c4 = corpora.CONFIGS["c4"]
+    rx4 = mr.compile_regex(c4["pattern"])
+    ob, ms = _timed_ms(lambda: rx4.sub_device(c4["repl"], txt))
+    assert ob.n == n + 2 * (n // 10)
+    _record_timing("all_digits_sub_256MiB", ms, n)
+    head = ob.tensor()[:24].cpu().numpy().tobytes()
+    assert head == b"555-555-5555" * 2
+    # e-mail search on a 1 MiB line that has no '@': one attempt (the others are dominated) walks the line
+    email = r"[a-zA-Z0-9._%+-]+@[a-zA-Z0-9.-]+\.[a-zA-Z]{2,}"
+    rxe = mr.compile_regex(email)
+    assert rxe.info().search_dominated == 1
+    line = torch.full((1 << 20,), ord("k"), dtype=torch.uint8, device="cuda")
+    ltxt = mr.Text.from_tensor(line)
+    m, ms = _timed_ms(lambda: rxe.match_next(ltxt, 0))
+    assert m is None
+    _record_timing("email_search_1MiB_line_without_at", ms, 1 << 20)
+    ds, ms = _timed_ms(lambda: rxe.match_all_device(ltxt))
+    assert _spans_of(ds).shape[0] == 0
