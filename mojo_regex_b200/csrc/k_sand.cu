@@ -35,7 +35,9 @@ namespace mrx {
 // Geometry: 256 threads x 144 bytes (9 x LDS.128; 9 is odd, so a quarter-warp's vectors hit 8 distinct bank groups),
 // two CTAs per SM.  Smaller chunks were measured (512 threads x 80 bytes, 32 warps per SM: 0.62 ms per GiB against
 // 0.50): the per-thread work of a tile that does not depend on the chunk length (scan, window, sums, warm-up) costs
-// more than the extra warps hide.
+// more than the extra warps hide.  Three chains of 48 bytes per thread instead of two (64 + 80) were measured too:
+// 0.481 ms against 0.471 -- the third warm-up costs more than the extra chain in flight gains, the walk is not
+// latency-bound.
 constexpr int kSandThreads = 256;
 constexpr int kSandChunk = kSandTileBytes / kSandThreads;  // 144
 constexpr int kSandVecs = kSandChunk / 16;                 // 9
