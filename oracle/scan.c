@@ -113,7 +113,7 @@ __attribute__((target("avx2"))) static inline uint32_t member32(const uint8_t *n
 /* first position in [pos, end) whose byte is (want = 1) / is not (want = 0) in the set; end if none */
 __attribute__((target("avx2"))) static int64_t scan_set_avx2(const uint8_t *nib, const uint8_t *tab, const uint8_t *t,
                                                              int64_t pos, int64_t end, int want) {
-  for (int k = 0; k < 4 && pos < end; ++k, ++pos)  /* the next hit is usually a few bytes away */
+  for (int k = 0; k < 16 && pos < end; ++k, ++pos) /* the next hit is usually a few bytes away */
     if ((tab[t[pos]] != 0) == (want != 0)) return pos;
   while (pos + 32 <= end) {
     uint32_t m = member32(nib, t + pos);
