@@ -21,6 +21,7 @@ instead (the reference itself is Mojo and cannot be built here).  With N > 1 the
 the library's own NCCL communicator (mrx_comm_*), off the scan stream.
 """
 import argparse
+import collections
 import json
 import os
 import subprocess
@@ -309,9 +310,33 @@ def measure_config(args, config: str, ctx, headline: bool) -> dict:
     if shard.buffer.numel() < 2 * L2_BYTES:
         flush = torch.empty(2 * L2_BYTES, dtype=torch.uint8, device=dev)
 
+    # findall steps are queued without a host round trip (mrx_findall_async: the span count stays in HBM and is
+    # exchanged from there); a result is released two steps later, when its kernel has long finished.  The other
+    # operations return their sizes to the host by contract and are timed as they are.
+    lag = collections.deque()
+
+    def step():
+        r = mrd.run_op_device(rx, cfg, shard, asynchronous=True)
+        lag.append(r)
+        if len(lag) > 2:
+            lag.popleft().close()
+        return r
+
+    def drain():
+        last = None
+        while lag:
+            last = lag.popleft()
+            last.wait()
+            if lag:
+                last.close()
+        return last
+
     clocks = ClockSampler(local_rank) if headline else None
-    for _ in range(warmup):
-        mrd.run_op_device(rx, cfg, shard).close()
+    step()
+    drain().close()  # the first result's count sizes the span arrays of the calls after it
+    for _ in range(max(warmup, 3)):  # (three results in flight: the pool holds their blocks before the timed steps)
+        step()
+    drain().close()
     mr.set_profiling(True)
     sync_all()
     launches0 = mr.launch_count()
@@ -322,14 +347,15 @@ def measure_config(args, config: str, ctx, headline: bool) -> dict:
         with torch.cuda.stream(lib_stream):
             ev0.record(lib_stream)
             for _ in range(steps):
-                res = mrd.run_op_device(rx, cfg, shard)
-                kernel_ms.append(mr.last_kernel_ms())
-                units, alg_bytes = res.units, res.algorithmic_bytes
-                res.close()
+                step()
             mrd.join_exchanges(lib_stream)  # the count all-gathers run on their own stream: include them
             ev1.record(lib_stream)
         sync_all()
         dev_ms = ev0.elapsed_time(ev1)
+        kernel_ms = mr.kernel_ms_history(min(steps, 60))
+        res = drain()
+        units, alg_bytes = res.units, res.algorithmic_bytes
+        res.close()
     else:
         pairs = []
         for _ in range(steps):
@@ -338,15 +364,19 @@ def measure_config(args, config: str, ctx, headline: bool) -> dict:
             with torch.cuda.stream(lib_stream):
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(lib_stream)
-                res = mrd.run_op_device(rx, cfg, shard)
+                step()
                 mrd.join_exchanges(lib_stream)
                 e1.record(lib_stream)
             kernel_ms.append(mr.last_kernel_ms())
-            units, alg_bytes = res.units, res.algorithmic_bytes
-            res.close()
             pairs.append((e0, e1))
         sync_all()
         dev_ms = sum(a.elapsed_time(b) for a, b in pairs)
+        if os.environ.get("MRX_BENCH_DEBUG"):
+            print("[debug] %s per-step ms %s kernel ms %s" % (config, [round(a.elapsed_time(b), 3) for a, b in pairs],
+                                                              [round(k, 3) for k in kernel_ms]), file=sys.stderr)
+        res = drain()
+        units, alg_bytes = res.units, res.algorithmic_bytes
+        res.close()
     launches = mr.launch_count() - launches0
     t_end = time.time()
     mr.set_profiling(False)

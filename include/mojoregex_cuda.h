@@ -137,6 +137,9 @@ int mrx_synchronize(void);
  * by CUDA events on the library stream; mrx_last_kernel_ms() returns its duration. */
 int mrx_set_profiling(int enabled);
 double mrx_last_kernel_ms(void);
+/* The times of the last n profiled calls, oldest first (one synchronisation; for loops of asynchronous calls).
+ * Returns how many were written (at most 63). */
+int mrx_kernel_ms_history(double *out_ms, int n);
 
 /* ---- front end ------------------------------------------------------------------------ */
 /* Replaces compile_regex()/CompiledRegex(pattern) (matcher.mojo:964-978, 1292-1315) for
@@ -186,6 +189,15 @@ void mrx_text_free(mrx_text *t);
 /* ---- matching (all of these launch CUDA kernels) ----------------------------------------- */
 /* CompiledRegex.match_all / findall (matcher.mojo:1078-1089, 1341-1354). */
 int mrx_findall(const mrx_regex *re, const mrx_text *t, int location, mrx_spans *out);
+/* The same with the result left in HBM and no host synchronisation (matcher.mojo:266-270 for a caller whose
+ * pipeline continues on the GPU): the scan is queued on the library stream and the call returns; out->n is
+ * (size_t)-1 until mrx_spans_wait() fetches the count.  mrx_spans_count_device() is the device address of the
+ * count (uint64), valid in stream order -- what mrx_comm_allgather_device() exchanges between ranks.
+ * mrx_spans_wait: MRX_OK, or 1 when the span array (sized from the match density of the previous call on this
+ * pattern) was too small: out->n spans are valid, the caller repeats the call (the estimate has been corrected). */
+int mrx_findall_async(const mrx_regex *re, const mrx_text *t, mrx_spans *out);
+const void *mrx_spans_count_device(const mrx_spans *s);
+int mrx_spans_wait(mrx_spans *s);
 /* findall(pattern, text) with the text in HOST memory (matcher.mojo:1341-1354: the reference's callers
  * hold the text on the host and get a host MatchList back).  Equivalent to mrx_text_upload +
  * mrx_findall(MRX_OUT_HOST) + mrx_text_free, but for large texts the upload, the scan and the download
@@ -242,6 +254,9 @@ int mrx_search_batch_host(const mrx_regex *re, const uint8_t *host, size_t n, co
 int mrx_comm_unique_id(uint8_t out[128]);
 int mrx_comm_init(const uint8_t id[128], int rank, int world);
 int mrx_comm_allgather(const int64_t *values, int width /* 1..4 */, void **table_dev);
+/* One int64 per rank that is still being produced on the library stream (mrx_spans_count_device): gathered
+ * straight from device memory, ordered after everything queued on the library stream so far. */
+int mrx_comm_allgather_device(const void *value_dev, void **table_dev);
 int mrx_comm_join(void *stream /* cudaStream_t; NULL = mrx_stream() */);
 int mrx_comm_shutdown(void);
 

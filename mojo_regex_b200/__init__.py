@@ -82,10 +82,10 @@ class DfaDesc(ctypes.Structure):
 
 EXPORTS = [
     "mrx_abi_version", "mrx_init", "mrx_init_multi", "mrx_device_count", "mrx_shutdown", "mrx_last_error", "mrx_stream", "mrx_launch_count",
-    "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
+    "mrx_synchronize", "mrx_set_profiling", "mrx_last_kernel_ms", "mrx_kernel_ms_history", "mrx_compile", "mrx_dfa_pack", "mrx_regex_load", "mrx_regex_blob", "mrx_regex_info",
     "mrx_regex_free", "mrx_text_upload", "mrx_text_wrap_device", "mrx_text_set_window", "mrx_text_len",
-    "mrx_text_free", "mrx_findall", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
-    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_search_batch_host", "mrx_comm_unique_id", "mrx_comm_init", "mrx_comm_allgather", "mrx_comm_join",
+    "mrx_text_free", "mrx_findall", "mrx_findall_async", "mrx_spans_count_device", "mrx_spans_wait", "mrx_findall_host", "mrx_findall_host_shard", "mrx_search", "mrx_match_first", "mrx_search_batch", "mrx_sub",
+    "mrx_split", "mrx_sub_host", "mrx_split_host", "mrx_search_batch_host", "mrx_comm_unique_id", "mrx_comm_init", "mrx_comm_allgather", "mrx_comm_allgather_device", "mrx_comm_join",
     "mrx_comm_shutdown", "mrx_spans_free", "mrx_bytes_free", "mrx_pieces_free",
 ]
 
@@ -122,6 +122,12 @@ def _load() -> ctypes.CDLL:
     lib.mrx_text_free.argtypes = [vp]
     lib.mrx_text_free.restype = None
     lib.mrx_findall.argtypes = [vp, vp, c.c_int, P(_Spans)]
+    lib.mrx_findall_async.argtypes = [vp, vp, P(_Spans)]
+    lib.mrx_spans_count_device.argtypes = [P(_Spans)]
+    lib.mrx_spans_count_device.restype = vp
+    lib.mrx_spans_wait.argtypes = [P(_Spans)]
+    lib.mrx_kernel_ms_history.argtypes = [P(c.c_double), c.c_int]
+    lib.mrx_comm_allgather_device.argtypes = [vp, P(vp)]
     lib.mrx_findall_host.argtypes = [vp, vp, sz, P(_Spans)]
     lib.mrx_findall_host_shard.argtypes = [vp, vp, sz, sz, sz, i64, P(_Spans)]
     lib.mrx_search.argtypes = [vp, vp, i64, P(i64)]
@@ -224,6 +230,13 @@ def last_kernel_ms() -> float:
     return float(lib.mrx_last_kernel_ms())
 
 
+def kernel_ms_history(n: int):
+    """Dominant-kernel times of the last n profiled calls, oldest first (synchronises once)."""
+    buf = (ctypes.c_double * max(n, 1))()
+    got = lib.mrx_kernel_ms_history(buf, n)
+    return [float(buf[i]) for i in range(got)]
+
+
 def synchronize() -> None:
     _check(lib.mrx_synchronize())
 
@@ -247,6 +260,14 @@ def comm_allgather(values) -> int:
     arr = (ctypes.c_int64 * len(values))(*[int(v) for v in values])
     out = ctypes.c_void_p()
     _check(lib.mrx_comm_allgather(arr, len(values), ctypes.byref(out)))
+    return int(out.value or 0)
+
+
+def comm_allgather_device(value_dev: int) -> int:
+    """Queue one all-gather of ONE int64 that lives in device memory and is produced on the library stream (the count
+    of an asynchronous findall); returns the device address of the (world, 1) table."""
+    out = ctypes.c_void_p()
+    _check(lib.mrx_comm_allgather_device(ctypes.c_void_p(value_dev), ctypes.byref(out)))
     return int(out.value or 0)
 
 
@@ -466,6 +487,13 @@ class CompiledRegex:
         _check(lib.mrx_findall(self._h, text._h, OUT_DEVICE, ctypes.byref(sp)))
         return _DeviceSpans(sp)
 
+    def match_all_async(self, text: Text) -> "_DeviceSpans":
+        """findall with the spans left in HBM and no host synchronisation: `.n` is -1 until `.wait()`;
+        `.count_ptr` is the device address of the count (stream-ordered on the library stream)."""
+        sp = _Spans()
+        _check(lib.mrx_findall_async(self._h, text._h, ctypes.byref(sp)))
+        return _DeviceSpans(sp)
+
     def search_batch(self, text, doc_offsets=None, doc_stride: int = 0, n_docs: Optional[int] = None,
                      out: Optional[np.ndarray] = None) -> np.ndarray:
         """One match_next(doc, 0) per document -> (n_docs, 2) int64, (-1,-1) = no match.  `out` may be a
@@ -665,8 +693,19 @@ class _DeviceSpans:
 
     def __init__(self, sp: _Spans):
         self._sp = sp
-        self.n = int(sp.n)
+        self.n = -1 if sp.n == ctypes.c_size_t(-1).value else int(sp.n)
         self.ptr = ctypes.cast(sp.start_end, ctypes.c_void_p).value or 0
+
+    @property
+    def count_ptr(self) -> int:
+        """Device address of the span count (uint64), valid in stream order on the library stream."""
+        return int(lib.mrx_spans_count_device(ctypes.byref(self._sp)) or 0)
+
+    def wait(self) -> bool:
+        """Fetch the count of an asynchronous findall.  False: the span array was too small (repeat the call)."""
+        rc = _check(lib.mrx_spans_wait(ctypes.byref(self._sp)))
+        self.n = int(self._sp.n)
+        return rc == 0
 
     @property
     def __cuda_array_interface__(self):

@@ -42,7 +42,13 @@ struct Lib {
   unsigned long long *h_scalars = nullptr;  // pinned mirror
   bool profiling = false;
   bool prof_outer = false;  // sub / split bracket their whole kernel sequence; list jobs then do not record
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // kernel timing for the bench: a ring of event pairs, so that a loop of asynchronous calls can be timed launch by
+  // launch without a synchronisation in between (mrx_kernel_ms_history)
+  static constexpr int kProfRing = 64;
+  cudaEvent_t evs[kProfRing][2] = {};
+  unsigned ev_idx = 0, ev_count = 0;
+  cudaEvent_t begin_ev() { ++ev_idx; if (ev_count < kProfRing - 1) ++ev_count; return evs[ev_idx % kProfRing][0]; }
+  cudaEvent_t end_ev() { return evs[ev_idx % kProfRing][1]; }
   bool ev_valid = false;
 };
 // One Lib per CUDA device.  Single-device mode (mrx_init) uses the slot of the selected device; multi-device mode
@@ -134,7 +140,7 @@ struct PoolBlock {
 // must come down on every exit path
 struct ProfOuter {
   bool armed = false;
-  void arm() { if (g.profiling) { g.prof_outer = armed = true; cudaEventRecord(g.ev0, g.stream); } }
+  void arm() { if (g.profiling) { g.prof_outer = armed = true; cudaEventRecord(g.begin_ev(), g.stream); } }
   void disarm() { if (armed) { g.prof_outer = false; armed = false; } }
   ~ProfOuter() { disarm(); }
 };
@@ -421,6 +427,10 @@ struct ListJob {
   int64_t rebase;
   const uint8_t *dense = nullptr;  // DenseHdr + table when the plan has a dense automaton
   const sand::Table *sand = nullptr;  // ... and its Shift-And form when the set fits (findall plan only)
+  // mrx_findall_async: the kernel leaves its match count here (device memory owned by the result) and the call
+  // returns without reading it; *async_cap = the capacity of the span array that was launched with
+  unsigned long long *async_total = nullptr;
+  int64_t *async_cap = nullptr;
 };
 
 // MRX_NO_SAND=1: literal sets go through k_dense even when k_sand applies (the tests hold the two equal)
@@ -474,20 +484,21 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
     void *spans = b_spans.p, *keys = b_keys.p;
     CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
-    CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+    unsigned long long *d_total = job.async_total ? job.async_total : g.scalars;
+    CUDA_TRY(cudaMemsetAsync(d_total, 0, 8, g.stream));
     ScanParams p{};
     p.text = job.t->d; p.n = n; p.tile_origin = origin; p.key_lo = job.key_lo; p.key_hi = job.key_hi;
     p.key_hi_inclusive_n = at_end ? 1 : 0; p.try_at_end = at_end ? 1 : 0; p.search_start = job.key_lo;
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.out_kind = OUT_SPANS;
     p.dominated = (job.pl == &job.re->prog.findall && job.re->findall_leading_run) ? 1 : 0;
     p.n_tiles = (int)tiles; p.spans = (int64_t *)spans; p.keys = (int64_t *)keys; p.cap = cap; p.rebase = job.rebase;
-    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
-    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
+    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = d_total;
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.begin_ev(), g.stream);
     if (use_sand) {
       SandParams sp{};
       sp.text = job.t->d; sp.n = n; sp.tile_origin = origin; sp.key_lo = job.key_lo; sp.key_hi = job.key_hi;
       sp.table = job.sand; sp.n_tiles = (int)tiles; sp.tile_base = 0; sp.base0 = 0; sp.spans = (int64_t *)spans; sp.cap = cap;
-      sp.rebase = job.rebase; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket; sp.total = g.scalars;
+      sp.rebase = job.rebase; sp.desc = desc.as<unsigned long long>(); sp.ticket = g.ticket; sp.total = d_total;
       if (const char *dbg = getenv("MRX_SAND_DEBUG")) sp.debug = atoi(dbg);
       launch_sand(sp, pl.sand.k, pl.sand.tail != 0, (int)tiles, g.stream);
     } else if (job.dense && !want_keys) {
@@ -495,14 +506,20 @@ int run_scan_list(const ListJob &job, bool want_keys, DevSpans &out, int64_t **k
       dp.text = job.t->d; dp.n = n; dp.tile_origin = origin; dp.key_lo = job.key_lo; dp.key_hi = job.key_hi;
       dp.dense = job.dense; dp.table_bytes = (int32_t)(pl.dense.next.size() * 2); dp.out_kind = OUT_SPANS;
       dp.n_tiles = (int)tiles; dp.spans = (int64_t *)spans; dp.cap = cap; dp.rebase = job.rebase;
-      dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = g.scalars;
+      dp.desc = desc.as<unsigned long long>(); dp.ticket = g.ticket; dp.total = d_total;
       launch_dense(dp, (int)tiles, g.stream);
     } else {
       launch_scan(p, (int)tiles, g.stream);
     }
-    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
+    if (job.async_total) {  // no host round trip: the caller reads the count later (mrx_spans_wait)
+      out.spans = (int64_t *)b_spans.take();
+      out.n = -1;
+      *job.async_cap = cap;
+      return MRX_OK;
+    }
     if ((rc = read_scalars(0, 1))) return rc;
     const int64_t total = (int64_t)g.h_scalars[0];
     note_density(job, total);
@@ -554,17 +571,24 @@ int run_runs_list(const ListJob &job, DevSpans &out) {
     void *spans = b_spans.p;
     CUDA_TRY(cudaMemsetAsync(desc.p, 0, sizeof(unsigned long long) * tiles, g.stream));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
-    CUDA_TRY(cudaMemsetAsync(g.scalars, 0, 8, g.stream));
+    unsigned long long *d_total = job.async_total ? job.async_total : g.scalars;
+    CUDA_TRY(cudaMemsetAsync(d_total, 0, 8, g.stream));
     RunsParams p{};
     p.text = job.t->d; p.n = n; p.tile_origin = origin; p.key_lo = job.key_lo; p.key_hi = job.key_hi;
     p.prog = job.dprog; p.filt = make_filter(pl); p.mode = pl.mode; p.run_min = pl.run_min; p.run_max = pl.run_max;
     p.n_tiles = (int)tiles; p.tile_carry = d_carry; p.spans = (int64_t *)spans; p.cap = cap; p.rebase = job.rebase;
-    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
-    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
+    p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = d_total;
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.begin_ev(), g.stream);
     launch_runs(p, (int)tiles, g.stream);
-    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
+    if (job.async_total) {
+      out.spans = (int64_t *)b_spans.take();
+      out.n = -1;
+      *job.async_cap = cap;
+      return MRX_OK;
+    }
     if ((rc = read_scalars(0, 1))) return rc;
     const int64_t total = (int64_t)g.h_scalars[0];
     note_density(job, total);
@@ -914,7 +938,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
     if (t1 <= t0) continue;
     CUDA_TRY(cudaStreamWaitEvent(g.stream, pipe_event((size_t)c), 0));
     CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
-    if (g.profiling && c == 0) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && c == 0) cudaEventRecord(g.begin_ev(), g.stream);
     if (job.sand) {
       SandParams sp{};
       sp.text = dt; sp.n = n; sp.tile_origin = origin; sp.key_lo = core_begin; sp.key_hi = core_end; sp.table = job.sand;
@@ -936,7 +960,7 @@ int findall_host_pipelined(mrx_regex *re, const uint8_t *host, int64_t n, int64_
       p.desc = desc.as<unsigned long long>(); p.ticket = g.ticket; p.total = g.scalars;
       launch_runs(p, (int)(t1 - t0), g.stream);
     }
-    if (g.profiling && c == 0) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && c == 0) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     if ((rc = read_scalars(0, 1))) { cleanup(); return rc; }  // waits for this launch only; uploads keep going
@@ -990,8 +1014,7 @@ static int init_slot(int device) {  // makes `device` current for this thread an
   CUDA_TRY(cudaMalloc(&g.ticket, 64));
   CUDA_TRY(cudaMalloc(&g.scalars, 64 * sizeof(unsigned long long)));
   CUDA_TRY(cudaHostAlloc(&g.h_scalars, 64 * sizeof(unsigned long long), cudaHostAllocDefault));
-  CUDA_TRY(cudaEventCreate(&g.ev0));
-  CUDA_TRY(cudaEventCreate(&g.ev1));
+  for (auto &pair : g.evs) { CUDA_TRY(cudaEventCreate(&pair[0])); CUDA_TRY(cudaEventCreate(&pair[1])); }
   g.device = device;
   g.inited = true;
   g.launches = 0;
@@ -1010,8 +1033,7 @@ static void shutdown_slot(int device) {
     cudaFree(g.ticket);
     cudaFree(g.scalars);
     cudaFreeHost(g.h_scalars);
-    cudaEventDestroy(g.ev0);
-    cudaEventDestroy(g.ev1);
+    for (auto &pair : g.evs) { cudaEventDestroy(pair[0]); cudaEventDestroy(pair[1]); }
     for (cudaEvent_t e : g.ev_pool) cudaEventDestroy(e);
     cudaStreamDestroy(g.s_in);
     cudaStreamDestroy(g.s_out);
@@ -1060,14 +1082,29 @@ uint64_t mrx_launch_count(void) { return g.launches; }
 int mrx_set_profiling(int enabled) {
   g.profiling = enabled != 0;
   g.ev_valid = false;
+  g.ev_count = 0;
   return MRX_OK;
 }
 double mrx_last_kernel_ms(void) {
   if (!g.inited || !g.ev_valid) return -1.0;
-  if (cudaEventSynchronize(g.ev1) != cudaSuccess) return -1.0;
+  if (cudaEventSynchronize(g.end_ev()) != cudaSuccess) return -1.0;
   float ms = 0.f;
-  if (cudaEventElapsedTime(&ms, g.ev0, g.ev1) != cudaSuccess) return -1.0;
+  if (cudaEventElapsedTime(&ms, g.evs[g.ev_idx % Lib::kProfRing][0], g.end_ev()) != cudaSuccess) return -1.0;
   return (double)ms;
+}
+// The dominant-kernel times of the last `n` profiled calls, oldest first (one synchronisation, after the loop):
+// -> how many were written (at most 63, and no more than were recorded since mrx_set_profiling(1)).
+int mrx_kernel_ms_history(double *out_ms, int n) {
+  if (!g.inited || !out_ms || n <= 0) return 0;
+  if (cudaStreamSynchronize(g.stream) != cudaSuccess) return 0;
+  const int have = (int)std::min<unsigned>(g.ev_count, (unsigned)n);
+  for (int i = 0; i < have; ++i) {
+    const unsigned k = (g.ev_idx - (unsigned)(have - 1 - i)) % Lib::kProfRing;
+    float ms = -1.f;
+    if (cudaEventElapsedTime(&ms, g.evs[k][0], g.evs[k][1]) != cudaSuccess) ms = -1.f;
+    out_ms[i] = (double)ms;
+  }
+  return have;
 }
 int mrx_synchronize(void) {
   int rc = require_device();
@@ -1276,6 +1313,94 @@ int mrx_findall(const mrx_regex *re_c, const mrx_text *t, int location, mrx_span
   return finish_spans(ds, location, out);
 }
 
+// findall with the result left in HBM and NO host synchronisation: the kernel is queued and the call returns; the span
+// count stays on the device (mrx_spans_count_device: what a stream-ordered consumer or mrx_comm_allgather_device reads)
+// until mrx_spans_wait fetches it.  Served this way: plans whose scan kernel writes the final list (class runs,
+// chains, literal sets, direct attempt plans); every other plan runs mrx_findall and parks its count on the device.
+struct AsyncSpans {
+  int64_t cap = 0, keys = 0;
+  int density_index = 0;
+  mrx_regex *re = nullptr;
+  bool pending = false;
+  cudaEvent_t done = nullptr;  // recorded after the scan kernel: the blocks go back to the pool only once it has fired
+};
+static std::map<void *, AsyncSpans> &async_spans() {
+  static thread_local std::map<void *, AsyncSpans> m;  // keyed by the result's owner
+  return m;
+}
+int mrx_findall_async(const mrx_regex *re_c, const mrx_text *t, mrx_spans *out) {
+  int rc = require_device();
+  if (rc) return rc;
+  if (!re_c || !t || !out) return fail(MRX_E_INVALID, "null argument");
+  mrx_regex *re = const_cast<mrx_regex *>(re_c);
+  std::memset(out, 0, sizeof *out);
+  if ((rc = ensure_uploaded(re))) return rc;
+  const Plan &pl = re->prog.findall;
+  if (pl.unsupported) return fail(MRX_E_UNSUPPORTED, pl.why);
+  const bool single_kernel = pl.mode == MRX_MODE_CLASS_RUNS || pl.mode == MRX_MODE_UNIFORM_RUN ||
+                             ((pl.mode == MRX_MODE_LITERAL || pl.mode == MRX_MODE_EXACT_LITERAL || pl.mode == MRX_MODE_FIRST_CLASS ||
+                               pl.mode == MRX_MODE_EVERY_POS || pl.mode == MRX_MODE_REQUIRED_BYTE) && pl.direct);
+  PoolBlock slot;
+  if ((rc = dev_alloc(32, &slot.p))) return rc;
+  DevSpans ds;
+  AsyncSpans rec;
+  rec.re = re;
+  rec.keys = (int64_t)t->core_end - (int64_t)t->core_begin;
+  if (single_kernel && t->n > 0) {
+    ListJob job{re, t, &pl, re->on().d_findall, (int64_t)t->core_begin, (int64_t)t->core_end, t->global_offset};
+    if (pl.dense.valid) job.dense = re->on().d_dense_findall;
+    if (pl.sand_valid && sand_enabled()) job.sand = re->on().d_sand_findall;
+    job.async_total = (unsigned long long *)slot.p;
+    job.async_cap = &rec.cap;
+    CUDA_TRY(cudaMemsetAsync(slot.p, 0, 32, g.stream));  // (a text with no tiles launches nothing)
+    rc = (pl.mode == MRX_MODE_CLASS_RUNS || pl.mode == MRX_MODE_UNIFORM_RUN) ? run_runs_list(job, ds) : run_scan_list(job, false, ds, nullptr);
+    if (rc) return rc;
+    rec.pending = ds.n < 0;
+    if (!rec.pending) ds.n = 0;  // no tiles
+  } else {
+    if ((rc = match_list(re, t, pl, re->on().d_findall, ds))) return rc;
+  }
+  if (!rec.pending) {
+    g.h_scalars[13] = (unsigned long long)ds.n;
+    CUDA_TRY(cudaMemcpyAsync(slot.p, g.h_scalars + 13, 8, cudaMemcpyHostToDevice, g.stream));
+    CUDA_TRY(cudaStreamSynchronize(g.stream));  // (h_scalars is scratch)
+  }
+  if ((rc = finish_spans(ds, MRX_OUT_DEVICE, out))) return rc;
+  OwnedOut *own = static_cast<OwnedOut *>(out->_owner);
+  own->dev[1] = slot.take();
+  if (rec.pending) {
+    out->n = (size_t)-1;
+    CUDA_TRY(cudaEventCreateWithFlags(&rec.done, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(rec.done, g.stream));
+    async_spans()[own] = rec;
+  }
+  return MRX_OK;
+}
+const void *mrx_spans_count_device(const mrx_spans *s) {
+  if (!s || !s->_owner) return nullptr;
+  return static_cast<OwnedOut *>(s->_owner)->dev[1];
+}
+// Fetch the count of an asynchronous findall (one stream synchronisation).  MRX_OK: s->n is the number of spans.
+// 1: the span array was too small for the text (the density estimate of the previous call was off): the caller
+// repeats the call -- the estimate has been corrected.
+int mrx_spans_wait(mrx_spans *s) {
+  if (!s || !s->_owner) return fail(MRX_E_INVALID, "null argument");
+  if (s->n != (size_t)-1) return MRX_OK;
+  OwnedOut *own = static_cast<OwnedOut *>(s->_owner);
+  auto it = async_spans().find(own);
+  if (it == async_spans().end()) return fail(MRX_E_INVALID, "not an asynchronous result of this thread");
+  const AsyncSpans rec = it->second;
+  async_spans().erase(it);
+  if (rec.done) cudaEventDestroy(rec.done);
+  CUDA_TRY(cudaMemcpyAsync(g.h_scalars + 13, own->dev[1], 8, cudaMemcpyDeviceToHost, g.stream));
+  CUDA_TRY(cudaStreamSynchronize(g.stream));
+  const int64_t total = (int64_t)g.h_scalars[13];
+  if (rec.keys > 0) rec.re->on().density[0] = (double)total / (double)rec.keys;
+  if (total > rec.cap) { s->n = (size_t)rec.cap; return 1; }
+  s->n = (size_t)total;
+  return MRX_OK;
+}
+
 static int findall_host_shard_single(const mrx_regex *re_c, const uint8_t *host, size_t n, size_t core_begin, size_t core_end,
                                      int64_t global_offset, mrx_spans *out) {
   int rc = require_device();
@@ -1417,9 +1542,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     lp.rev_bytes = (int32_t)(pl.rev.rev.size() * 2); lp.fwd_bytes = (int32_t)(pl.rev.fwd.size() * 2);
     lp.fwd_start = pl.rev.fwd_start; lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
     lp.n_docs = (int64_t)n_docs; lp.out = outp; lp.req_byte = pl.rev.req_byte;
-    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.begin_ev(), g.stream);
     launch_lines(lp, g.stream);
-    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
     if (location == MRX_OUT_HOST) {
@@ -1460,9 +1585,9 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
   if (re->prog.search_via_prefilter) p.dominated = 0;  // a dominated candidate may be the first one at or after the literal
   if (tiles > 0) {
     p.n_tiles = (int)tiles;
-    if (g.profiling && !g.prof_outer) cudaEventRecord(g.ev0, g.stream);
+    if (g.profiling && !g.prof_outer) cudaEventRecord(g.begin_ev(), g.stream);
     launch_scan(p, (int)tiles, g.stream);
-    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling && !g.prof_outer) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     ++g.launches;
   }
   int64_t *outp = out_start_end;
@@ -1536,7 +1661,7 @@ static int sub_fused(mrx_regex *re, const mrx_text *t, const std::vector<int32_t
   sp.tile_carry = carry.as<long long>(); sp.out = (uint8_t *)d_out; sp.desc = desc.as<unsigned long long>();
   sp.ticket = g.ticket; sp.totals = g.scalars;
   launch_subst(sp, g.stream);
-  if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+  if (g.profiling) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
   prof.disarm();
   g.launches += 3;
   CUDA_TRY(cudaGetLastError());
@@ -1685,7 +1810,7 @@ int mrx_sub(const mrx_regex *re_c, const uint8_t *repl, size_t repl_n, int64_t c
     ap.repl_len = repl_len; ap.tpl_src = d_tpl.as<int32_t>(); ap.total = total; ap.out = (uint8_t *)d_out;
     launch_assemble(ap, g.stream);
     g.launches += total > 0 ? 1 : 0;
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
   }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)total;
@@ -1740,7 +1865,7 @@ static int split_fused(mrx_regex *re, const mrx_text *t, int location, mrx_piece
     sp.totals = g.scalars; sp.flags = reinterpret_cast<int *>(g.scalars + 2);
     prof.arm();
     launch_split(sp, g.stream);
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
     prof.disarm();
     ++g.launches;
     CUDA_TRY(cudaGetLastError());
@@ -1860,7 +1985,7 @@ int mrx_split(const mrx_regex *re_c, const mrx_text *t, int64_t maxsplit, int lo
     launch_assemble(ap, g.stream);
     if ((rc = debug_sync("split: k_assemble"))) return bail(rc);
     g.launches += total > 0 ? 1 : 0;
-    if (g.profiling) { cudaEventRecord(g.ev1, g.stream); g.ev_valid = true; }
+    if (g.profiling) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }
   }
   CUDA_TRY(cudaGetLastError());
   out->n = (size_t)(M + 1);
@@ -1998,7 +2123,7 @@ struct Exchange {
   NcclComm comm = nullptr;
   int rank = 0, world = 1;
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev = nullptr;
+  cudaEvent_t ev = nullptr, ev_in = nullptr;
   int64_t *h_ring = nullptr;  // pinned, kXRing x kXWidth
   int64_t *d_ring = nullptr;  // device mirror of the slots
   int64_t *d_table = nullptr; // world x width of the last exchange
@@ -2051,6 +2176,7 @@ extern "C" int mrx_comm_init(const uint8_t id_bytes[128], int rank, int world) {
   gx.world = world;
   CUDA_TRY(cudaStreamCreateWithFlags(&gx.stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&gx.ev, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&gx.ev_in, cudaEventDisableTiming));
   CUDA_TRY(cudaHostAlloc((void **)&gx.h_ring, sizeof(int64_t) * kXRing * kXWidth, cudaHostAllocDefault));
   CUDA_TRY(cudaMalloc((void **)&gx.d_ring, sizeof(int64_t) * kXRing * kXWidth));
   CUDA_TRY(cudaMalloc((void **)&gx.d_table, sizeof(int64_t) * (size_t)world * kXWidth));
@@ -2066,6 +2192,20 @@ extern "C" int mrx_comm_allgather(const int64_t *values, int width, void **table
   for (int i = 0; i < width; ++i) gx.h_ring[slot + i] = values[i];
   CUDA_TRY(cudaMemcpyAsync(gx.d_ring + slot, gx.h_ring + slot, sizeof(int64_t) * width, cudaMemcpyHostToDevice, gx.stream));
   const int e = gx.api.AllGather(gx.d_ring + slot, gx.d_table, (size_t)width, kNcclInt64, gx.comm, gx.stream);
+  if (e) return nccl_fail("ncclAllGather", e);
+  if (table_dev) *table_dev = gx.d_table;
+  return MRX_OK;
+}
+
+// The same exchange for ONE int64 that is still being produced on the library stream (the count of an asynchronous
+// findall, mrx_spans_count_device): the exchange stream waits for the library stream as of now and gathers straight
+// from device memory -- the host never sees the value.
+extern "C" int mrx_comm_allgather_device(const void *value_dev, void **table_dev) {
+  if (!gx.comm) return fail(MRX_E_NO_DEVICE, "mrx_comm_init has not been called");
+  if (!value_dev) return fail(MRX_E_INVALID, "null argument");
+  CUDA_TRY(cudaEventRecord(gx.ev_in, g.stream));
+  CUDA_TRY(cudaStreamWaitEvent(gx.stream, gx.ev_in, 0));
+  const int e = gx.api.AllGather(value_dev, gx.d_table, (size_t)1, kNcclInt64, gx.comm, gx.stream);
   if (e) return nccl_fail("ncclAllGather", e);
   if (table_dev) *table_dev = gx.d_table;
   return MRX_OK;
@@ -2087,6 +2227,7 @@ extern "C" int mrx_comm_shutdown(void) {
   cudaFree(gx.d_ring);
   cudaFree(gx.d_table);
   cudaEventDestroy(gx.ev);
+  cudaEventDestroy(gx.ev_in);
   cudaStreamDestroy(gx.stream);
   NcclApi keep = gx.api;
   gx = Exchange();
@@ -2538,6 +2679,13 @@ extern "C" {
 
 void mrx_spans_free(mrx_spans *s) {
   if (!s) return;
+  if (s->_owner) {
+    auto it = async_spans().find(s->_owner);
+    if (it != async_spans().end()) {  // still pending: its kernel must be done before the pool hands the blocks on
+      if (it->second.done) { cudaEventSynchronize(it->second.done); cudaEventDestroy(it->second.done); }
+      async_spans().erase(it);
+    }
+  }
   release_owner(s->_owner);
   std::memset(s, 0, sizeof *s);
 }

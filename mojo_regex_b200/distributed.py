@@ -211,6 +211,13 @@ class NativeGather:
         assert len(values) == self.width
         self.table_ptr = mr.comm_allgather(values)
 
+    def gather_device(self, value_ptr: int) -> None:
+        """The same for one int64 that is still being produced on the library stream (device address)."""
+        import mojo_regex_b200 as mr
+
+        assert self.width == 1
+        self.table_ptr = mr.comm_allgather_device(value_ptr)
+
     def table(self) -> torch.Tensor:
         """(world, width) view of the library's table, ordered after the exchanges on the current stream."""
         import mojo_regex_b200 as mr
@@ -400,6 +407,15 @@ class OpResult:
         stream, computed on demand from the gathered counts)."""
         return self._gather.base_offset() if self._gather is not None else 0
 
+    def wait(self) -> "OpResult":
+        """An asynchronous findall step: fetch the span count (one synchronisation) and fill in units / bytes."""
+        if self.units < 0 and self.holder is not None:
+            if not self.holder.wait():
+                raise RuntimeError("asynchronous findall: the span array was too small; repeat the step")
+            self.units = self.holder.n
+            self.algorithmic_bytes = self._n_text + 16 * self.holder.n
+        return self
+
     def close(self):
         if self.holder is not None and hasattr(self.holder, "close"):
             self.holder.close()
@@ -411,24 +427,35 @@ def run_op_local(rx, cfg, shard: Shard) -> OpResult:
     return run_op_device(rx, cfg, shard, exchange=False)
 
 
-def run_op_device(rx, cfg, shard: Shard, exchange: bool = True) -> OpResult:
-    """One step with the shard resident in HBM and the result left in HBM."""
+def run_op_device(rx, cfg, shard: Shard, exchange: bool = True, asynchronous: bool = False) -> OpResult:
+    """One step with the shard resident in HBM and the result left in HBM.  asynchronous=True (findall): the call
+    returns with the scan queued; OpResult.wait() fetches the count."""
     n = shard.core_bytes
     dev = shard.buffer.device
     multi = exchange and shard.world > 1
     if cfg["op"] == "findall":
-        ds = rx.match_all_device(shard.text)
         g = None
-        if multi:
-            g = _gather_for(1, dev)
-            g.gather([ds.n])
+        if asynchronous and (not multi or _NATIVE):
+            # no host round trip: the count stays on the device and is exchanged from there; OpResult.units and
+            # .algorithmic_bytes are filled in by OpResult.wait()
+            ds = rx.match_all_async(shard.text)
+            if multi:
+                g = _gather_for(1, dev)
+                g.gather_device(ds.count_ptr)
+        else:
+            ds = rx.match_all_device(shard.text)
+            if multi:
+                g = _gather_for(1, dev)
+                g.gather([ds.n])
         kernel = getattr(shard, "_findall_kernel", None)
         if kernel is None:
             info = rx.info()
             kernel = ("k_sand" if info.findall_sand and not os.environ.get("MRX_NO_SAND") else
                       "k_dense" if info.findall_dense else ("k_runs" if info.findall_mode in (4, 8) else "k_scan"))
             shard._findall_kernel = kernel
-        return OpResult(ds.n, n + 16 * ds.n, kernel, ds, g)
+        r = OpResult(ds.n, n + 16 * ds.n, kernel, ds, g)
+        r._n_text = n
+        return r
     if cfg["op"] == "search_batch":
         # the caller-provided result array lives with the shard (allocated once, like the text)
         out = getattr(shard, "_batch_out", None)

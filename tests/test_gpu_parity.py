@@ -1229,3 +1229,46 @@ def test_adversarial_all_digits_and_a_line_without_the_required_byte():
     _record_timing("email_search_1MiB_line_without_at", ms, 1 << 20)
     ds, ms = _timed_ms(lambda: rxe.match_all_device(ltxt))
     assert _spans_of(ds).shape[0] == 0
+
+
+# ---- asynchronous findall: no host round trip, the count stays in HBM -----------------------------------------------
+@pytest.mark.parametrize("config", ["c1", "c2", "c4"])
+def test_findall_async_equals_findall(config):
+    cfg = corpora.CONFIGS[config]
+    rx = mr.CompiledRegex(cfg["pattern"])                    # fresh: no density estimate yet
+    text = corpora.make(config, 6 << 20)
+    t = mr.Text(text.numpy())
+    want = rx.match_all_device(t).to_numpy()
+    results = [rx.match_all_async(t) for _ in range(3)]      # three in flight, released out of order
+    assert all(r.n == -1 for r in results)
+    cnt = torch.empty(1, dtype=torch.int64, device="cuda")
+    for r in (results[1], results[0], results[2]):
+        assert r.count_ptr != 0
+        assert r.wait()
+        assert r.n == len(want)
+        assert np.array_equal(r.to_numpy(), want)
+        r.close()
+    # released while still pending
+    rx.match_all_async(t).close()
+    # a text denser than the estimate: the array is too small, wait() says so, and the repeat fits
+    dense = np.frombuffer((b"7 " if config != "c2" else b"foo ") * 600_000, dtype=np.uint8)
+    if config != "c4":
+        td = mr.Text(dense)
+        r = rx.match_all_async(td)
+        ok = r.wait()
+        r.close()
+        r2 = rx.match_all_async(td)
+        assert r2.wait()
+        assert r2.n == len(rx.match_all_device(td).to_numpy()) and (ok or r2.n > 0)
+        r2.close()
+
+
+def test_findall_async_on_plans_that_need_the_host():
+    """Non-direct plans and empty texts run the ordinary path and park their count on the device."""
+    for pattern, text in ((r"a+1a?", b"a1aa1 aa1a"), (r"\d+", b""), (r".*", b"abc"), (r"^ab", b"abab")):
+        rx = mr.compile_regex(pattern)
+        t = mr.Text(np.frombuffer(text, dtype=np.uint8)) if text else mr.Text(np.zeros(0, np.uint8))
+        r = rx.match_all_async(t)
+        assert r.wait()
+        assert np.array_equal(r.to_numpy().reshape(-1, 2), oracle.compile(pattern).findall(np.frombuffer(text, np.uint8)).reshape(-1, 2))
+        r.close()
