@@ -36,13 +36,14 @@ GiB = 1 << 30
 
 
 def kernel_source_hash() -> str:
-    """sha256 (16 hex digits) over the CUDA sources: an ncu capture is only quoted for the code it was taken on."""
+    """sha256 (16 hex digits) over the KERNEL sources (device code: kernels.cu, k_*.cu and the headers they include;
+    not the host side of the C ABI, api.cu): an ncu capture is only quoted for the code it was taken on."""
     import hashlib
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "mojo_regex_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".hpp")):
+        if name.endswith((".cuh", ".hpp")) or (name.endswith(".cu") and name != "api.cu"):
             with open(os.path.join(csrc, name), "rb") as f:
                 h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
