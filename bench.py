@@ -35,17 +35,19 @@ sys.path.insert(0, ROOT)
 GiB = 1 << 30
 
 
-def kernel_source_hash() -> str:
-    """sha256 (16 hex digits) over the KERNEL sources (device code: kernels.cu, k_*.cu and the headers they include;
-    not the host side of the C ABI, api.cu): an ncu capture is only quoted for the code it was taken on."""
+KERNEL_FILES = {"k_sand": ["k_sand.cu", "sand.hpp"], "k_split": ["k_split.cu", "sepbits.hpp"], "k_subst": ["k_subst.cu"]}
+
+
+def kernel_source_hash(kernel: str = "") -> str:
+    """sha256 (16 hex digits) over the device code a kernel is built from (its own file and the common headers; the
+    kernels without a file of their own live in kernels.cu): an ncu capture is only quoted for the code it was taken on."""
     import hashlib
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "mojo_regex_b200", "csrc")
-    for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cuh", ".hpp")) or (name.endswith(".cu") and name != "api.cu"):
-            with open(os.path.join(csrc, name), "rb") as f:
-                h.update(name.encode() + b"\0" + f.read())
+    for name in sorted(KERNEL_FILES.get(kernel, ["kernels.cu"]) + ["device.cuh", "kernels.cuh"]):
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 
@@ -57,7 +59,7 @@ def load_traffic(config: str, n_bytes: int, kernel: str):
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             t = json.load(f).get(config)
         if (t and int(t["bytes_per_gpu"]) == int(n_bytes) and t["kernel"] == kernel
-                and t.get("src_sha") == kernel_source_hash()):
+                and t.get("src_sha") == kernel_source_hash(kernel)):
             return float(t["traffic_bytes"])
     except Exception:
         pass

@@ -1541,7 +1541,8 @@ int mrx_search_batch(const mrx_regex *re_c, const mrx_text *t, const int64_t *do
     lp.text = t->d; lp.n = n; lp.tables = re->on().d_rev_search;
     lp.rev_bytes = (int32_t)(pl.rev.rev.size() * 2); lp.fwd_bytes = (int32_t)(pl.rev.fwd.size() * 2);
     lp.fwd_start = pl.rev.fwd_start; lp.doc_offsets = offs_dev; lp.doc_stride = doc_stride;
-    lp.n_docs = (int64_t)n_docs; lp.out = outp; lp.req_byte = pl.rev.req_byte;
+    lp.n_docs = (int64_t)n_docs; lp.out = outp; lp.req_byte = pl.rev.req_byte; lp.ticket = g.ticket;
+    CUDA_TRY(cudaMemsetAsync(g.ticket, 0, 16, g.stream));
     if (g.profiling && !g.prof_outer) cudaEventRecord(g.begin_ev(), g.stream);
     launch_lines(lp, g.stream);
     if (g.profiling && !g.prof_outer) { cudaEventRecord(g.end_ev(), g.stream); g.ev_valid = true; }

@@ -1022,13 +1022,25 @@ __global__ void __launch_bounds__(kReqThreads, 1) k_lines_req(const LinesParams 
       if (j < nv && c < chunks) dst[j] = __ldg(src + c);
     }
   };
-  int64_t grp = (int64_t)blockIdx.x * kReqWarps + warp;
+  // batches by ticket, one per warp at a time, fetched two batches ahead (the atomic's latency hides behind a batch).
+  // A static split made the kernel as slow as its slowest CTA: on a multi-GPU job the previous step's all-gather
+  // kernel can still sit on an SM when this kernel starts, and the CTA of that SM began late (C3 at N = 8: 0.58 ms
+  // against 0.49 alone).  Without a ticket counter (prm.ticket == nullptr) the split is static.
+  auto take = [&](int64_t after) -> int64_t {
+    if (!prm.ticket) return after + gstep;
+    unsigned int t = 0;
+    if (lane == 0) t = atomicAdd(prm.ticket, 1u);
+    return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+  };
+  int64_t grp = prm.ticket ? take(0) : (int64_t)blockIdx.x * kReqWarps + warp;
+  int64_t nxt = take(grp);
   uint4 v[kReqMaxVecs];
   if (grp < n_groups) load_batch(grp, v);
-  for (; grp < n_groups; grp += gstep) {
+  for (; grp < n_groups;) {
     // the next batch's loads are in flight while this one is filtered, parked and (now and then) walked
     uint4 nx[kReqMaxVecs];
-    if (grp + gstep < n_groups) load_batch(grp + gstep, nx);
+    if (nxt < n_groups) load_batch(nxt, nx);
+    const int64_t after_next = take(nxt);
     const int64_t d0 = grp * 32;
     const int in_grp = (int)min((int64_t)32, prm.n_docs - d0);
     const int chunks = in_grp * nv;
@@ -1068,6 +1080,8 @@ __global__ void __launch_bounds__(kReqThreads, 1) k_lines_req(const LinesParams 
     }
 #pragma unroll
     for (int j = 0; j < kReqMaxVecs; ++j) v[j] = nx[j];
+    grp = nxt;
+    nxt = after_next;
   }
   if ((uint32_t)lane < tail - head) {
     const uint32_t slot = (head + (uint32_t)lane) & (kReqRing - 1);

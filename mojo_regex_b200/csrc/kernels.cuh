@@ -165,6 +165,7 @@ struct LinesParams {
   int32_t staged;              // 1: fixed-size, 16-byte aligned documents staged through shared memory by TMA
   int32_t line_pitch;          // shared-memory bytes per staged document (odd multiple of 16)
   int32_t req_byte;            // RevTable::req_byte: documents without this byte cannot match (-1: none)
+  unsigned int *ticket;        // k_lines_req: zeroed counter, batches of 32 documents are handed out by it
 };
 
 enum SegMode : int32_t { SEG_SUB = 0, SEG_SPLIT = 1 };

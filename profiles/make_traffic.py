@@ -16,7 +16,6 @@ LABEL = {"k_sand": "k_sand", "k_split": "k_split", "k_subst": "k_subst", "k_line
 def main():
     path = os.path.join(ROOT, "profiles", "r02_traffic.json")
     out = json.load(open(path)) if os.path.exists(path) else {}
-    sha = kernel_source_hash()
     for arg in sys.argv[1:]:
         config, rest = arg.split("=")
         rep, nbytes = rest.rsplit(":", 1)
@@ -28,7 +27,7 @@ def main():
         kernel = next(v for k, v in LABEL.items() if k in name)
         rd, wr = get("dram__bytes_read.sum"), get("dram__bytes_write.sum")
         out[config] = {"kernel": kernel, "bytes_per_gpu": int(nbytes), "traffic_bytes": rd + wr, "dram_read": rd,
-                       "dram_write": wr, "kernel_name": name, "capture": os.path.basename(rep), "src_sha": sha}
+                       "dram_write": wr, "kernel_name": name, "capture": os.path.basename(rep), "src_sha": kernel_source_hash(kernel)}
     json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out, indent=1))
 
