@@ -16,6 +16,11 @@ def load(n):
     d = json.load(open(p))
     out = {d["config"]["config"]: d}
     out.update(d.get("configs", {}))
+    # k_lines_req got its ticket counter after the full N > 1 lines were taken: C3 at N > 1 comes from a later run of
+    # the same command restricted to --configs c3 (r02_bench_n{N}_c3.json); the older value stays in the full line
+    o = os.path.join(ROOT, "profiles", "r02_bench_n%d_c3.json" % n)
+    if os.path.exists(o):
+        out["c3"] = json.load(open(o))["configs"]["c3"]
     return out
 
 
