@@ -1370,8 +1370,10 @@ int mrx_findall_async(const mrx_regex *re_c, const mrx_text *t, mrx_spans *out) 
   own->dev[1] = slot.take();
   if (rec.pending) {
     out->n = (size_t)-1;
+    OwnerGuard og{own, &out->_owner};  // an error below releases the result instead of leaking it
     CUDA_TRY(cudaEventCreateWithFlags(&rec.done, cudaEventDisableTiming));
     CUDA_TRY(cudaEventRecord(rec.done, g.stream));
+    og.commit();
     async_spans()[own] = rec;
   }
   return MRX_OK;
