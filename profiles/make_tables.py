@@ -30,7 +30,7 @@ def main():
     p = os.path.join(ROOT, "profiles", "r02_bench_ref_n1.json")
     if os.path.exists(p):
         ref = json.load(open(p))
-    lines = ["| config | GPUs | input bytes per GPU | ms per step (device, max over ranks) | input GB/s (whole job) | scaling vs N = 1 | algorithmic bytes | dominant kernel, ms | % of HBM roofline (6467.7 GB/s measured per GPU) | DRAM traffic ÷ algorithmic bytes (ncu) | e2e GB/s (host buffers, whole job) | CPU port GB/s (1 thread) |",
+    lines = ["| config | GPUs | input bytes per GPU | ms per step (device, max over ranks) | input GB/s (whole job) | scaling vs N = 1 | algorithmic bytes | dominant kernel, ms | % of HBM roofline (6467.7 GB/s measured per GPU; in brackets: of 8000 nominal) | DRAM traffic ÷ algorithmic bytes (ncu) | e2e GB/s (host buffers, whole job) | CPU port GB/s (1 thread) |",
              "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     for c in ("c1", "c2", "c3", "c4", "c5"):
         base = runs[1][c]["value"] if runs[1] and c in runs[1] else None
@@ -41,10 +41,10 @@ def main():
             r = v["roofline"]
             traffic = "%.3f" % (r["traffic"] / r["algorithmic_bytes_per_launch"]) if r.get("traffic") else "–"
             cpu = v.get("cpu_baseline") or {}
-            lines.append("| %s | %d | %d | %.4f | %.0f | %s | %s | `%s` %.4f | %.1f %% | %s | %.1f | %s |" % (
+            lines.append("| %s | %d | %d | %.4f | %.0f | %s | %s | `%s` %.4f | %.1f %% (%.1f %%) | %s | %.1f | %s |" % (
                 NAMES[c] if n == 1 else "", n, v["config"]["bytes_per_gpu"], v["ms_per_step"], v["value"],
                 "%.0f %%" % (100.0 * v["value"] / (n * base)) if base else "–", ALG[c] if n == 1 else "", r["kernel"], r["kernel_ms"],
-                100.0 * r["frac"], traffic, v["e2e"]["value"], "%.3f" % cpu["value"] if cpu.get("value") else "–"))
+                100.0 * r["frac"], 100.0 * r["achieved"] / 8000.0, traffic, v["e2e"]["value"], "%.3f" % cpu["value"] if cpu.get("value") else "–"))
     if ref:
         lines.append("")
         lines.append("Reference arm (`bench.py --impl reference`, the oracle port on all %d host threads of the GPU box, %s): %.2f GB/s."
