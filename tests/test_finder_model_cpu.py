@@ -1,5 +1,5 @@
-"""CPU check of the closed form behind the round-2 finder for `X* c Y*` patterns (C5: `\\s*,\\s*`), see
-DESIGN.md "known weak spots".  The reference's required-byte findall (matcher.mojo:864-898: memchr the byte,
+"""CPU check of the closed form behind the fused split kernel k_split for `X* c Y*` patterns (C5: `\\s*,\\s*`), see
+DESIGN.md section 5.  The reference's required-byte findall (matcher.mojo:864-898: memchr the byte,
 back-scan the first-class lookup L, one anchored DFA attempt) reduces, for the automaton S0 -X-> S1 -c-> S2(acc)
 -Y-> S3(acc), to a rule per occurrence h of c that needs only membership bits and run lengths:
 
@@ -9,8 +9,8 @@ back-scan the first-class lookup L, one anchored DFA attempt) reduces, for the a
 
 Spans of neighbouring occurrences may overlap (two commas sharing one blank run): findall reports them as the
 reference does, split then answers MRX_E_UNDEFINED.  Checked here against the oracle on the C5 corpus and on
-random texts that contain \\v, shared runs, leading/trailing separators.  A model for the next kernel, not
-product code.
+random texts that contain \\v, shared runs, leading/trailing separators.  A model of the rule, not product code
+(the kernel's own bit arithmetic is checked in tests/test_sepbits_cpu.py).
 """
 import random
 
