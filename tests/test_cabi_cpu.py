@@ -213,6 +213,15 @@ def test_matching_without_a_device_fails_loudly():
         pytest.skip("a GPU is present")
     with pytest.raises(mr.RegexCudaError):
         mr.findall(r"\d+", b"abc123")
+    # the entry points that take no text object fail the same way (no CPU fallback anywhere)
+    import ctypes
+
+    rx = mr.CompiledRegex(r"\d+")
+    sp = mr._Spans()
+    assert mr.lib.mrx_findall_async(rx._h, None, ctypes.byref(sp)) == -5       # MRX_E_NO_DEVICE
+    assert mr.lib.mrx_findall_host(rx._h, None, 0, ctypes.byref(sp)) == -5
+    assert mr.lib.mrx_comm_allgather_device(None, None) == -5
+    assert mr.lib.mrx_init_multi(2) < 0 and mr.lib.mrx_device_count() == 0
 
 
 def _random_patterns(n: int, seed: int):
