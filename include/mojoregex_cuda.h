@@ -194,7 +194,9 @@ int mrx_findall(const mrx_regex *re, const mrx_text *t, int location, mrx_spans 
  * (size_t)-1 until mrx_spans_wait() fetches the count.  mrx_spans_count_device() is the device address of the
  * count (uint64), valid in stream order -- what mrx_comm_allgather_device() exchanges between ranks.
  * mrx_spans_wait: MRX_OK, or 1 when the span array (sized from the match density of the previous call on this
- * pattern) was too small: out->n spans are valid, the caller repeats the call (the estimate has been corrected). */
+ * pattern) was too small: out->n spans are valid, the caller repeats the call (the estimate has been corrected).
+ * An asynchronous result is waited for and freed by the thread that made the call (one calling thread per handle,
+ * as everywhere in this ABI); freeing it while the scan is still running waits for that scan only. */
 int mrx_findall_async(const mrx_regex *re, const mrx_text *t, mrx_spans *out);
 const void *mrx_spans_count_device(const mrx_spans *s);
 int mrx_spans_wait(mrx_spans *s);
